@@ -1,0 +1,201 @@
+/*
+ * mitre_b200.h -- C ABI of libmitre_b200.so: the B200 (sm_100a) replacement for MITRE's MCMC
+ * likelihood hot path.  Plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the
+ * gerberlab/mitre tree).  Conventions:
+ *
+ *   * Every pointer is a DEVICE pointer unless the parameter name ends in `_host` or the
+ *     function name ends in `_host`.  `stream` is a cudaStream_t passed as void* (NULL = the
+ *     legacy default stream).  Device entry points are asynchronous and stream-ordered; they
+ *     allocate nothing -- the caller owns inputs, outputs and workspaces.
+ *   * Return value: 0 = MITRE_OK; < 0 = argument / capability error (MITRE_ERR_*);
+ *     > 0 = a cudaError_t from the runtime.  Nothing is thrown across the ABI.
+ *   * Numerical failures that the reference reports as numpy LinAlgError
+ *     (efficient_likelihoods.pyx:42, mvnpdf_cholesky.py:66) are reported through the caller's
+ *     `status` word on the device (bit flags MITRE_STATUS_*), OR-ed in by the kernels.
+ *
+ * PACKED TRUTH ROWS.  The reference keeps `flat_truth` as bool[P, N] (rules.py:510) and converts
+ * it to float64[P, N] on every sweep (logit_rules.py:214-217).  Here a row is W64 = ceil(N/64)
+ * uint64 words; subject i lives in word i/64 at bit (63 - i%64).  With that bit order, comparing
+ * rows word by word as unsigned integers is exactly the reference's lexicographic row order
+ * (subject 0 most significant, False < True; rules.py:447-450).  Padding bits are zero.
+ */
+#ifndef MITRE_B200_H
+#define MITRE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MITRE_OK 0
+#define MITRE_ERR_INVALID (-1)      /* null pointer, negative size, inconsistent shape      */
+#define MITRE_ERR_UNSUPPORTED (-2)  /* shape outside what the kernels are built for          */
+#define MITRE_ERR_WORKSPACE (-3)    /* workspace smaller than *_workspace_bytes() asks for    */
+#define MITRE_ERR_NOT_PD (-4)       /* host-synchronous entries only: Cholesky failed         */
+#define MITRE_ERR_NO_DEVICE (-5)    /* no sm_100 device / kernel image not loadable           */
+
+#define MITRE_STATUS_BASE_NOT_PD 1u   /* base system I/sigma^2 + X'OmegaX not positive definite */
+#define MITRE_STATUS_BAD_SCHUR 2u     /* a candidate's Schur complement was <= 0 or non-finite  */
+#define MITRE_STATUS_COV_NOT_PD 4u    /* dense covariance not positive definite                 */
+
+#define MITRE_MAX_P 24                /* columns of the base design matrix X the kernels accept */
+
+/* ---- library ------------------------------------------------------------------------------ */
+
+const char *mitre_version(void);
+const char *mitre_error_string(int code);
+/* sm count, compute capability and opt-in shared memory of the current device. */
+int mitre_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *smem_optin);
+
+/* ---- packing (layout conversion at the boundary) ------------------------------------------ */
+
+/* float64[P, N] (non-zero = True; the array the reference passes as `list_of_truth_vectors`,
+ * efficient_likelihoods.pyx:19) -> packed uint64[P, W64]. */
+int mitre_pack_rows_f64(void *stream, const double *truth, int64_t P, int N, uint64_t *packed);
+/* bool/uint8[P, N] (the reference's flat_truth, rules.py:510) -> packed. */
+int mitre_pack_rows_u8(void *stream, const uint8_t *truth, int64_t P, int N, uint64_t *packed);
+/* packed -> uint8[P, N] of 0/1. */
+int mitre_unpack_rows_u8(void *stream, const uint64_t *packed, int64_t P, int N, uint8_t *truth);
+
+/* ---- scoring: replaces efficient_likelihoods.likelihoods_of_all_options -------------------- */
+/*
+ * Reference: mitre/efficient_likelihoods.pyx:15-169, called from
+ * LogisticRuleModel.likelihoods_of_all_options (logit_rules.py:186-229).
+ *
+ *   out[k] = log N( z ; 0, diag(1/omega) + sigma2 * [X | v_k][X | v_k]^T ),  z = kappa/omega,
+ *   v_k = packed_truth[k] AND mask           (the AND is logit_rules.py:214-216)
+ *
+ * for all k in [0, P) in one launch.  X is float64[N, p] row-major (any real entries: rule
+ * columns, the constant column, categorical / continuous covariates, rules.py:1152-1179),
+ * kappa = y - 0.5 (logit_rules.py:222).  `mask` is packed uint64[W64] (all subjects set when
+ * the rule has no other primitive).  `workspace` must hold mitre_score_workspace_bytes(N, p)
+ * bytes and stay untouched until the launch has run.  `status` (device int32, caller-zeroed)
+ * receives MITRE_STATUS_* flags.
+ */
+size_t mitre_score_workspace_bytes(int N, int p);
+int mitre_score_all(void *stream, const uint64_t *packed_truth, int64_t P, int W64,
+                    const uint64_t *mask, const double *X, const double *omega,
+                    const double *kappa, int N, int p, double sigma2, void *workspace,
+                    size_t workspace_bytes, double *out, int32_t *status);
+
+/*
+ * Drop-in compatibility form with the reference's exact arguments, all HOST pointers
+ * (efficient_likelihoods.pyx:15-21): X[N,p], omega[N], response[N] (= kappa/omega),
+ * truth float64[P,N], prior_coefficient_variance; writes out_host[P].  Synchronous: stages the
+ * rows through the device in chunks, packs, scores and copies back.
+ * Returns MITRE_ERR_NOT_PD where the reference raises LinAlgError.
+ */
+int mitre_score_all_host(const double *X_host, const double *omega_host,
+                         const double *response_host, const double *truth_host,
+                         double sigma2, int N, int p, int64_t P, double *out_host);
+
+/* ---- dense single-rule-list likelihood: replaces mc_logpdf_np ------------------------------ */
+/*
+ * Reference: LogisticRuleModel.likelihood_z_given_X (logit_rules.py:171-177) ->
+ * mvnpdf_cholesky.mc_logpdf_np (mvnpdf_cholesky.py:53-74).  Batched so that move_primitive's
+ * 2(2R'+1) sequential calls (logit_rules.py:1375-1401) are one launch.
+ *
+ *   out[b] = log N( kappa/omega ; 0, diag(1/omega) + sigma2 * X_b X_b^T )
+ *
+ * Xs is float64[B, N, pmax] row-major; design matrix b uses its first p_b[b] columns.
+ */
+int mitre_likelihood_z_given_X_batch(void *stream, const double *Xs, const int32_t *p_b,
+                                     int pmax, const double *omega, const double *kappa,
+                                     int N, int B, double sigma2, double *out,
+                                     int32_t *status);
+/*
+ * mc_logpdf_np(x, cov) itself (mvnpdf_cholesky.py:53-74) for an arbitrary dense covariance:
+ * x[N], cov[N,N] row-major (read only), scratch[N*N] doubles of device scratch, out[1].
+ */
+int mitre_mc_logpdf(void *stream, const double *x, const double *cov, int N, double *scratch,
+                    double *out, int32_t *status);
+
+/* ---- detector evaluation: replaces DiscreteRulePopulation.mine_rules ----------------------- */
+/*
+ * Reference: mitre/rules.py:325-436 (mine_rules) = window admission (391-421),
+ * calculate_values (578-600) over PrimitiveRule.evaluate (80-141), update_base_rules
+ * (465-511) over thresholds_from_values (513-576), sort_base_rules (439-462).
+ *
+ * Series layout in HBM: the N subjects' samples are concatenated along one axis of length
+ * S = sum_s T_s; t_offsets int32[N+1] delimits each subject; times float64[S] must be
+ * non-decreasing within a subject; series float64[V, series_stride] holds variable v's samples
+ * for all subjects at series + v*series_stride (series_stride >= S, in elements).
+ */
+
+/* For every (window w, subject s): first sample index (global, into [0,S)) and the number of
+ * samples with t0 <= t <= t1 (closed both ends, rules.py:100, 406-409).  lo, cnt: int32[W, N].
+ * The caller admits a window iff min_s cnt >= 1, and its slope iff min_s cnt >= 2. */
+int mitre_window_ranges(void *stream, const double *times, const int32_t *t_offsets, int N,
+                        const double *windows, int W, int32_t *lo, int32_t *cnt);
+
+/* calculate_values: values float64[G, N].  Groups are enumerated window-major, then variable,
+ * then type (slope, average) (rules.py:474-480): group index of (w, v, type) is
+ * group_base[w] + v*(1+slope_ok[w]) + (slope_ok[w] ? type : 0), type 0 = slope, 1 = average.
+ * 'average' is bit-identical to np.mean of the masked copy (numpy pairwise summation order);
+ * 'slope' is the closed-form OLS slope of x on (t - midpoint) (rules.py:110-114 reaches the
+ * same quantity through LAPACK gelsd; values agree to ~1e-11 relative).
+ * max_T = the largest per-subject sample count (sizes the shared-memory staging).  For the
+ * TMA staging path `series` and `times` must be 16-byte aligned, series_stride even, and both
+ * arrays readable up to the next even element past S (pad by one element if S is odd). */
+int mitre_detector_values(void *stream, const double *series, int64_t series_stride,
+                          const double *times, const int32_t *t_offsets, int N, int V,
+                          const double *windows, const int32_t *lo, const int32_t *cnt,
+                          const int64_t *group_base, const uint8_t *slope_ok, int W, int max_T,
+                          double *values);
+
+/* thresholds_from_values for every group (max_thresholds = None): sort, midpoints of
+ * neighbours, unique.  thresholds float64[G, N-1] (first K[g] entries of each row valid),
+ * K int32[G]. */
+int mitre_detector_thresholds(void *stream, const double *values, int64_t G, int N,
+                              double *thresholds, int32_t *K);
+
+/* Exclusive scan of 2*K[g] -> row_offsets int64[G+1]; row_offsets[G] = P.
+ * workspace: mitre_scan_workspace_bytes(G) bytes. */
+size_t mitre_scan_workspace_bytes(int64_t n);
+int mitre_detector_row_offsets(void *stream, const int32_t *K, int64_t G, int64_t *row_offsets,
+                               void *workspace, size_t workspace_bytes);
+
+/* update_base_rules: for group g, threshold k (ascending), direction d (0 above: v > th,
+ * 1 below: v <= th; rules.py:494-497) write packed row row_offsets[g] + 2k + d. */
+int mitre_detector_rows(void *stream, const double *values, const double *thresholds,
+                        const int32_t *K, const int64_t *row_offsets, int64_t G, int N,
+                        uint64_t *packed_truth);
+
+/* sort_base_rules: stable lexicographic sort of the packed rows (np.lexsort(np.rot90(truth)),
+ * rules.py:450).  perm int64[P]: perm[i] = enumeration index of the row at sorted position i
+ * (the reference's _reordering_cache); sorted_rows uint64[P, W64] may be NULL. */
+size_t mitre_lexsort_workspace_bytes(int64_t P, int W64);
+int mitre_lexsort_rows(void *stream, const uint64_t *rows, int64_t P, int W64, int N,
+                       int64_t *perm, uint64_t *sorted_rows, void *workspace,
+                       size_t workspace_bytes);
+
+/* ---- proposal draw: replaces the host-side weight assembly + choose_from_relative_probabilities
+ *
+ * Reference: weights = likelihoods + primitive_priors + multinomial_priors + log(relative_rates)
+ * (logit_rules.py:861-862) then choose_from_relative_probabilities(np.exp(weights))
+ * (rules.py:1261-1264: cumsum, marker = u * total, index = #{cum < marker}).
+ *
+ * mitre_weight_stats: (max, sum exp(w - max)) of w = a + b (b may be NULL) -- stats[0] = max,
+ *   stats[1] = sum; log-sum-exp = stats[0] + log(stats[1]).  This 16-byte pair is what ranks
+ *   all-gather for the two-stage multi-GPU draw.
+ * mitre_draw_index: index_out[0] = #{ i : cumsum(exp(w - shift))[i] < u * total }.
+ *   stabilise = 0: shift = 0, i.e. the reference's raw np.exp(weights) including its underflow
+ *   behaviour; stabilise = 1: shift = max w (stats is then computed first and must be non-NULL).
+ *   The cumulative sum is hierarchical, not np.cumsum's strict left-to-right order: the drawn
+ *   index can differ from the reference only when u*total is within rounding of a partial sum.
+ */
+size_t mitre_draw_workspace_bytes(int64_t P);
+int mitre_weight_stats(void *stream, const double *a, const double *b, int64_t P, double *stats,
+                       void *workspace, size_t workspace_bytes);
+int mitre_draw_index(void *stream, const double *a, const double *b, int64_t P, double u,
+                     int stabilise, double *stats, int64_t *index_out, void *workspace,
+                     size_t workspace_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MITRE_B200_H */

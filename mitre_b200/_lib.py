@@ -1,0 +1,92 @@
+"""ctypes binding of libmitre_b200.so (the C ABI in include/mitre_b200.h).
+
+There is no fallback: if the library is missing or fails to load, importing this module's
+`lib()` raises.  Build it with `python -m mitre_b200.build` (nvcc, sm_100a).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmitre_b200.so")
+
+c_void_p = ctypes.c_void_p
+c_int = ctypes.c_int
+c_i64 = ctypes.c_int64
+c_double = ctypes.c_double
+c_size_t = ctypes.c_size_t
+
+MITRE_OK = 0
+MITRE_ERR_NOT_PD = -4
+STATUS_BASE_NOT_PD = 1
+STATUS_BAD_SCHUR = 2
+STATUS_COV_NOT_PD = 4
+MAX_P = 24
+
+# name -> (restype, argtypes); every symbol include/mitre_b200.h declares
+SIGNATURES = {
+    "mitre_version": (ctypes.c_char_p, []),
+    "mitre_error_string": (ctypes.c_char_p, [c_int]),
+    "mitre_device_info": (c_int, [ctypes.POINTER(c_int)] * 3 + [ctypes.POINTER(c_size_t)]),
+    "mitre_pack_rows_f64": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p]),
+    "mitre_pack_rows_u8": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p]),
+    "mitre_unpack_rows_u8": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p]),
+    "mitre_score_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "mitre_score_all": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_int, c_int, c_double, c_void_p, c_size_t, c_void_p,
+                                c_void_p]),
+    "mitre_score_all_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_int,
+                                     c_int, c_i64, c_void_p]),
+    "mitre_likelihood_z_given_X_batch": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                                 c_void_p, c_int, c_int, c_double, c_void_p,
+                                                 c_void_p]),
+    "mitre_mc_logpdf": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                c_void_p]),
+    "mitre_window_ranges": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int,
+                                    c_void_p, c_void_p]),
+    "mitre_detector_values": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_int,
+                                      c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_int, c_int, c_void_p]),
+    "mitre_detector_thresholds": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p]),
+    "mitre_scan_workspace_bytes": (c_size_t, [c_i64]),
+    "mitre_detector_row_offsets": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_void_p,
+                                           c_size_t]),
+    "mitre_detector_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64,
+                                    c_int, c_void_p]),
+    "mitre_lexsort_workspace_bytes": (c_size_t, [c_i64, c_int]),
+    "mitre_lexsort_rows": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p,
+                                   c_void_p, c_size_t]),
+    "mitre_draw_workspace_bytes": (c_size_t, [c_i64]),
+    "mitre_weight_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p,
+                                   c_size_t]),
+    "mitre_draw_index": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_double, c_int, c_void_p,
+                                 c_void_p, c_void_p, c_size_t]),
+}
+
+_lib = None
+
+
+class MitreError(RuntimeError):
+    pass
+
+
+def lib():
+    """The loaded library.  Raises (loudly) if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "libmitre_b200.so not found at %s -- build it with `python -m mitre_b200.build`; "
+                "mitre_b200 has no CPU fallback" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)     # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(code, what=""):
+    if code != MITRE_OK:
+        msg = lib().mitre_error_string(int(code)).decode()
+        raise MitreError("%s failed: %s (code %d)" % (what or "libmitre_b200 call", msg, code))

@@ -1,0 +1,236 @@
+// draw.cu -- proposal draw over all candidates (replaces the host-side weight assembly and
+// choose_from_relative_probabilities, mitre/rules.py:1261-1264 as used at
+// logit_rules.py:861-863, 958-959, 1168-1170):
+//
+//     p = cumsum(exp(w));  marker = u * p[-1];  index = #{ p < marker }
+//
+// mitre_weight_stats gives (max w, sum exp(w - max)) -- the 16-byte pair ranks exchange for the
+// two-stage multi-GPU draw and the log-sum-exp the add/remove moves need
+// (logit_rules.py:959, 1035-1036, 1064).
+//
+// The cumulative sum is hierarchical (8 consecutive elements per thread, warp scan, tile of
+// 2048, sequential over tiles): exact for the selection except when `marker` falls within
+// rounding of a partial sum, where a sequential np.cumsum could differ by one index.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace mitre {
+
+constexpr int kDrawTile = 2048;
+
+__device__ __forceinline__ double weight_at(const double *__restrict__ a, const double *__restrict__ b,
+                                            int64_t i)
+{
+    return b ? a[i] + b[i] : a[i];
+}
+
+// (max, sum exp(x - max)) merge; empty = (-inf, 0)
+struct MaxSum {
+    double m, s;
+};
+__device__ __forceinline__ MaxSum ms_merge(MaxSum x, MaxSum y)
+{
+    if (y.s == 0.0 && y.m == -INFINITY) return x;
+    if (x.s == 0.0 && x.m == -INFINITY) return y;
+    MaxSum r;
+    if (x.m >= y.m) { r.m = x.m; r.s = x.s + y.s * exp(y.m - x.m); }
+    else { r.m = y.m; r.s = y.s + x.s * exp(x.m - y.m); }
+    return r;
+}
+
+__global__ void __launch_bounds__(256)
+stats_partial_kernel(const double *__restrict__ a, const double *__restrict__ b, int64_t P,
+                     double *__restrict__ part /*[grid][2]*/)
+{
+    __shared__ double sm[256], ss[256];
+    MaxSum acc = {-INFINITY, 0.0};
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += stride) {
+        const double w = weight_at(a, b, i);
+        if (w == -INFINITY) continue;
+        if (w > acc.m) { acc.s = acc.s * exp(acc.m - w) + 1.0; acc.m = w; }
+        else acc.s += exp(w - acc.m);
+    }
+    sm[threadIdx.x] = acc.m; ss[threadIdx.x] = acc.s;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            MaxSum x = {sm[threadIdx.x], ss[threadIdx.x]}, y = {sm[threadIdx.x + s], ss[threadIdx.x + s]};
+            x = ms_merge(x, y);
+            sm[threadIdx.x] = x.m; ss[threadIdx.x] = x.s;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { part[2 * blockIdx.x] = sm[0]; part[2 * blockIdx.x + 1] = ss[0]; }
+}
+
+__global__ void __launch_bounds__(256)
+stats_final_kernel(const double *__restrict__ part, int nparts, double *__restrict__ stats)
+{
+    __shared__ double sm[256], ss[256];
+    MaxSum acc = {-INFINITY, 0.0};
+    for (int i = threadIdx.x; i < nparts; i += 256) {
+        MaxSum y = {part[2 * i], part[2 * i + 1]};
+        acc = ms_merge(acc, y);
+    }
+    sm[threadIdx.x] = acc.m; ss[threadIdx.x] = acc.s;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            MaxSum x = {sm[threadIdx.x], ss[threadIdx.x]}, y = {sm[threadIdx.x + s], ss[threadIdx.x + s]};
+            x = ms_merge(x, y);
+            sm[threadIdx.x] = x.m; ss[threadIdx.x] = x.s;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { stats[0] = sm[0]; stats[1] = ss[0]; }
+}
+
+// Inclusive scan of one 2048-element tile of exp(w - shift); returns this thread's 8 inclusive
+// values in inc[] and the tile total through smem.
+__device__ __forceinline__ void tile_scan(const double *__restrict__ a, const double *__restrict__ b, int64_t P,
+                                          int64_t tile, double shift, double (&inc)[8], double *swarp,
+                                          double *tile_total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t i0 = tile * kDrawTile + (int64_t)threadIdx.x * 8;
+    double run = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const double e = (i0 + j < P) ? exp(weight_at(a, b, i0 + j) - shift) : 0.0;
+        run += e;
+        inc[j] = run;
+    }
+    double winc = run;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, winc, off);
+        if (lane >= off) winc += t;
+    }
+    if (lane == 31) swarp[wid] = winc;
+    __syncthreads();
+    double base = winc - run;
+    double tot = 0.0;
+    for (int w = 0; w < 8; ++w) {
+        if (w < wid) base += swarp[w];
+        tot += swarp[w];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) inc[j] += base;
+    if (threadIdx.x == 0) *tile_total = tot;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+draw_tile_sums_kernel(const double *__restrict__ a, const double *__restrict__ b, int64_t P,
+                      const double *__restrict__ stats, int stabilise, double *__restrict__ tile_sums)
+{
+    __shared__ double swarp[8];
+    __shared__ double tot;
+    double inc[8];
+    const double shift = stabilise ? stats[0] : 0.0;
+    tile_scan(a, b, P, blockIdx.x, shift, inc, swarp, &tot);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+
+// single CTA: sequential inclusive prefix over tiles (fp64, left to right), locate the tile the
+// marker falls in, rescan that tile, count.
+__global__ void __launch_bounds__(256)
+draw_select_kernel(const double *__restrict__ a, const double *__restrict__ b, int64_t P,
+                   const double *__restrict__ stats, int stabilise, double *__restrict__ tile_sums,
+                   int64_t ntiles, double u, int64_t *__restrict__ index_out)
+{
+    __shared__ double swarp[8];
+    __shared__ double tot;
+    __shared__ long long s_tile;
+    __shared__ double s_before, s_marker;
+    if (threadIdx.x == 0) {
+        double total = 0.0;
+        for (int64_t t = 0; t < ntiles; ++t) total += tile_sums[t];
+        const double marker = u * total;
+        double run = 0.0;
+        long long sel = ntiles;   // all partial sums < marker
+        double before = total;
+        for (int64_t t = 0; t < ntiles; ++t) {
+            const double nxt = run + tile_sums[t];
+            if (!(nxt < marker)) { sel = t; before = run; break; }
+            run = nxt;
+        }
+        s_tile = sel; s_before = before; s_marker = marker;
+    }
+    __syncthreads();
+    const long long sel = s_tile;
+    if (sel >= ntiles) {
+        if (threadIdx.x == 0) *index_out = P;
+        return;
+    }
+    double inc[8];
+    const double shift = stabilise ? stats[0] : 0.0;
+    tile_scan(a, b, P, sel, shift, inc, swarp, &tot);
+    int c = 0;
+    const int64_t i0 = sel * kDrawTile + (int64_t)threadIdx.x * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        if (i0 + j < P && (s_before + inc[j]) < s_marker) ++c;
+    // block sum of c
+    __shared__ int scount[256];
+    scount[threadIdx.x] = c;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) scount[threadIdx.x] += scount[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *index_out = sel * kDrawTile + scount[0];
+}
+
+constexpr int kStatsBlocks = 592;   // 148 SMs x 4
+
+}  // namespace mitre
+
+using namespace mitre;
+
+extern "C" size_t mitre_draw_workspace_bytes(int64_t P)
+{
+    if (P < 0) return 0;
+    const size_t ntiles = (size_t)ceil_div64(P > 0 ? P : 1, kDrawTile);
+    return sizeof(double) * (2 * (size_t)kStatsBlocks + 2 + ntiles);
+}
+
+extern "C" int mitre_weight_stats(void *stream, const double *a, const double *b, int64_t P, double *stats,
+                                  void *workspace, size_t workspace_bytes)
+{
+    if (P <= 0 || !a || !stats || !workspace) return MITRE_ERR_INVALID;
+    if (workspace_bytes < mitre_draw_workspace_bytes(P)) return MITRE_ERR_WORKSPACE;
+    cudaStream_t st = as_stream(stream);
+    double *part = static_cast<double *>(workspace);
+    int64_t blocks = ceil_div64(P, 256);
+    if (blocks > kStatsBlocks) blocks = kStatsBlocks;
+    stats_partial_kernel<<<(unsigned)blocks, 256, 0, st>>>(a, b, P, part);
+    MITRE_LAUNCH_CHECK();
+    stats_final_kernel<<<1, 256, 0, st>>>(part, (int)blocks, stats);
+    MITRE_LAUNCH_CHECK();
+    return MITRE_OK;
+}
+
+extern "C" int mitre_draw_index(void *stream, const double *a, const double *b, int64_t P, double u,
+                                int stabilise, double *stats, int64_t *index_out, void *workspace,
+                                size_t workspace_bytes)
+{
+    if (P <= 0 || !a || !index_out || !workspace) return MITRE_ERR_INVALID;
+    if (stabilise && !stats) return MITRE_ERR_INVALID;
+    if (workspace_bytes < mitre_draw_workspace_bytes(P)) return MITRE_ERR_WORKSPACE;
+    cudaStream_t st = as_stream(stream);
+    if (stabilise) {
+        int rc = mitre_weight_stats(stream, a, b, P, stats, workspace, workspace_bytes);
+        if (rc != MITRE_OK) return rc;
+    }
+    const int64_t ntiles = ceil_div64(P, kDrawTile);
+    if (ntiles > 0x7fffffffll) return MITRE_ERR_UNSUPPORTED;
+    double *tile_sums = static_cast<double *>(workspace) + 2 * kStatsBlocks + 2;
+    draw_tile_sums_kernel<<<(unsigned)ntiles, 256, 0, st>>>(a, b, P, stats, stabilise, tile_sums);
+    MITRE_LAUNCH_CHECK();
+    draw_select_kernel<<<1, 256, 0, st>>>(a, b, P, stats, stabilise, tile_sums, ntiles, u, index_out);
+    MITRE_LAUNCH_CHECK();
+    return MITRE_OK;
+}

@@ -1,0 +1,242 @@
+// lib.cu -- library plumbing: version / errors / device info, row packing kernels, and the
+// host-pointer compatibility entry with the reference's exact argument list.
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace mitre {
+
+static int g_sm_count = 0;
+static size_t g_smem_optin = 0;
+
+static void query_device()
+{
+    if (g_sm_count) return;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return;
+    g_sm_count = prop.multiProcessorCount;
+    g_smem_optin = prop.sharedMemPerBlockOptin;
+}
+
+int sm_count()
+{
+    query_device();
+    return g_sm_count > 0 ? g_sm_count : 148;
+}
+
+size_t smem_optin()
+{
+    query_device();
+    return g_smem_optin ? g_smem_optin : 227 * 1024;
+}
+
+// ---- packing -----------------------------------------------------------------------------------
+// One warp per (row, 32-subject half word): lanes read 32 consecutive subjects (coalesced),
+// ballot, bit-reverse so that subject i lands at bit 63-(i&63).
+template <typename T>
+__global__ void __launch_bounds__(256)
+pack_rows_kernel(const T *__restrict__ truth, int64_t P, int N, uint64_t *__restrict__ packed)
+{
+    const int W64 = words_for(N);
+    const int halves = 2 * W64;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    uint32_t *packed32 = reinterpret_cast<uint32_t *>(packed);
+    for (int64_t item = warp0; item < P * halves; item += nwarps) {
+        const int64_t row = item / halves;
+        const int h = (int)(item % halves);
+        const int i = h * 32 + lane;
+        const bool t = (i < N) && (truth[row * N + i] != (T)0);
+        const uint32_t bits = __brev(__ballot_sync(0xffffffffu, t));
+        // little-endian: the high 32 bits of word w are packed32[2w+1]
+        if (lane == 0) packed32[(row * W64 + (h >> 1)) * 2 + ((h & 1) ? 0 : 1)] = bits;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+unpack_rows_kernel(const uint64_t *__restrict__ packed, int64_t P, int N, uint8_t *__restrict__ truth)
+{
+    const int W64 = words_for(N);
+    const int64_t total = P * N;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const int64_t row = e / N;
+        const int i = (int)(e % N);
+        truth[e] = (packed[row * W64 + (i >> 6)] & subject_bit(i)) ? 1 : 0;
+    }
+}
+
+static unsigned grid_for(int64_t work_items, int threads)
+{
+    int64_t blocks = ceil_div64(work_items, threads);
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (unsigned)blocks;
+}
+
+}  // namespace mitre
+
+using namespace mitre;
+
+extern "C" const char *mitre_version(void) { return "mitre_b200 0.1.0 (sm_100a)"; }
+
+extern "C" const char *mitre_error_string(int code)
+{
+    switch (code) {
+        case MITRE_OK: return "ok";
+        case MITRE_ERR_INVALID: return "invalid argument";
+        case MITRE_ERR_UNSUPPORTED: return "unsupported shape";
+        case MITRE_ERR_WORKSPACE: return "workspace too small";
+        case MITRE_ERR_NOT_PD: return "matrix is not positive definite";
+        case MITRE_ERR_NO_DEVICE: return "no usable CUDA device";
+        default: break;
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "unknown error";
+}
+
+extern "C" int mitre_device_info(int *sm, int *cc_major, int *cc_minor, size_t *smem)
+{
+    int dev = 0;
+    MITRE_CUDA_TRY(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    MITRE_CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (sm) *sm = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    if (smem) *smem = prop.sharedMemPerBlockOptin;
+    return MITRE_OK;
+}
+
+extern "C" int mitre_pack_rows_f64(void *stream, const double *truth, int64_t P, int N, uint64_t *packed)
+{
+    if (P < 0 || N <= 0 || (P > 0 && (!truth || !packed))) return MITRE_ERR_INVALID;
+    if (P == 0) return MITRE_OK;
+    pack_rows_kernel<double><<<grid_for(P * 2 * words_for(N) * 32, 256), 256, 0, as_stream(stream)>>>(
+        truth, P, N, packed);
+    MITRE_LAUNCH_CHECK();
+    return MITRE_OK;
+}
+
+extern "C" int mitre_pack_rows_u8(void *stream, const uint8_t *truth, int64_t P, int N, uint64_t *packed)
+{
+    if (P < 0 || N <= 0 || (P > 0 && (!truth || !packed))) return MITRE_ERR_INVALID;
+    if (P == 0) return MITRE_OK;
+    pack_rows_kernel<uint8_t><<<grid_for(P * 2 * words_for(N) * 32, 256), 256, 0, as_stream(stream)>>>(
+        truth, P, N, packed);
+    MITRE_LAUNCH_CHECK();
+    return MITRE_OK;
+}
+
+extern "C" int mitre_unpack_rows_u8(void *stream, const uint64_t *packed, int64_t P, int N, uint8_t *truth)
+{
+    if (P < 0 || N <= 0 || (P > 0 && (!truth || !packed))) return MITRE_ERR_INVALID;
+    if (P == 0) return MITRE_OK;
+    unpack_rows_kernel<<<grid_for(P * N, 256), 256, 0, as_stream(stream)>>>(packed, P, N, truth);
+    MITRE_LAUNCH_CHECK();
+    return MITRE_OK;
+}
+
+// ---- host-pointer compatibility entry -------------------------------------------------------------
+// Same arguments as efficient_likelihoods.likelihoods_of_all_options (pyx:15-21).  The float64
+// truth matrix is staged through two pinned buffers so that the H2D copy of chunk c+1 overlaps
+// packing + scoring of chunk c.
+extern "C" int mitre_score_all_host(const double *X_host, const double *omega_host,
+                                    const double *response_host, const double *truth_host, double sigma2,
+                                    int N, int p, int64_t P, double *out_host)
+{
+    if (N <= 0 || p <= 0 || P < 0 || !X_host || !omega_host || !response_host) return MITRE_ERR_INVALID;
+    if (P > 0 && (!truth_host || !out_host)) return MITRE_ERR_INVALID;
+    if (p > MITRE_MAX_P) return MITRE_ERR_UNSUPPORTED;
+    const int W64 = words_for(N);
+    const size_t ws_bytes = mitre_score_workspace_bytes(N, p);
+    // chunk: ~64 MiB of float64 rows
+    int64_t chunk = (64ll << 20) / ((int64_t)N * 8);
+    if (chunk < 1024) chunk = 1024;
+    if (chunk > P) chunk = P > 0 ? P : 1;
+
+    double *d_X = nullptr, *d_omega = nullptr, *d_kappa = nullptr, *d_out[2] = {nullptr, nullptr};
+    double *d_truth[2] = {nullptr, nullptr}, *h_stage[2] = {nullptr, nullptr}, *h_kappa = nullptr;
+    uint64_t *d_packed[2] = {nullptr, nullptr};
+    void *d_ws[2] = {nullptr, nullptr};
+    int32_t *d_status = nullptr;
+    cudaStream_t st[2] = {nullptr, nullptr};
+    int rc = MITRE_OK;
+    int32_t h_status = 0;
+#define TRY(expr)                                   \
+    do {                                            \
+        cudaError_t _e = (expr);                    \
+        if (_e != cudaSuccess) { rc = (int)_e; goto cleanup; } \
+    } while (0)
+#define TRYRC(expr)                                 \
+    do {                                            \
+        rc = (expr);                                \
+        if (rc != MITRE_OK) goto cleanup;           \
+    } while (0)
+    h_kappa = (double *)malloc(sizeof(double) * N);
+    for (int i = 0; i < N; ++i) h_kappa[i] = response_host[i] * omega_host[i];  // z = kappa/omega
+    TRY(cudaMalloc(&d_X, sizeof(double) * N * p));
+    TRY(cudaMalloc(&d_omega, sizeof(double) * N));
+    TRY(cudaMalloc(&d_kappa, sizeof(double) * N));
+    TRY(cudaMalloc(&d_status, sizeof(int32_t)));
+    TRY(cudaMemset(d_status, 0, sizeof(int32_t)));
+    TRY(cudaMemcpy(d_X, X_host, sizeof(double) * N * p, cudaMemcpyHostToDevice));
+    TRY(cudaMemcpy(d_omega, omega_host, sizeof(double) * N, cudaMemcpyHostToDevice));
+    TRY(cudaMemcpy(d_kappa, h_kappa, sizeof(double) * N, cudaMemcpyHostToDevice));
+    for (int b = 0; b < 2; ++b) {
+        TRY(cudaStreamCreateWithFlags(&st[b], cudaStreamNonBlocking));
+        TRY(cudaMalloc(&d_truth[b], sizeof(double) * chunk * N));
+        TRY(cudaMalloc(&d_packed[b], sizeof(uint64_t) * chunk * W64));
+        TRY(cudaMalloc(&d_out[b], sizeof(double) * chunk));
+        TRY(cudaMalloc(&d_ws[b], ws_bytes));
+        TRY(cudaMallocHost(&h_stage[b], sizeof(double) * chunk * N));
+    }
+    {
+        int64_t done = 0;
+        int b = 0;
+        // out copies land directly in the caller's (pageable) buffer after each chunk's sync
+        while (done < P) {
+            const int64_t n = (P - done < chunk) ? (P - done) : chunk;
+            TRY(cudaStreamSynchronize(st[b]));  // previous use of this buffer pair finished
+            memcpy(h_stage[b], truth_host + done * N, sizeof(double) * n * N);
+            TRY(cudaMemcpyAsync(d_truth[b], h_stage[b], sizeof(double) * n * N, cudaMemcpyHostToDevice, st[b]));
+            TRYRC(mitre_pack_rows_f64(st[b], d_truth[b], n, N, d_packed[b]));
+            TRYRC(mitre_score_all(st[b], d_packed[b], n, W64, nullptr, d_X, d_omega, d_kappa, N, p, sigma2,
+                                  d_ws[b], ws_bytes, d_out[b], d_status));
+            TRY(cudaMemcpyAsync(out_host + done, d_out[b], sizeof(double) * n, cudaMemcpyDeviceToHost, st[b]));
+            done += n;
+            b ^= 1;
+        }
+        TRY(cudaStreamSynchronize(st[0]));
+        TRY(cudaStreamSynchronize(st[1]));
+        if (P == 0) {
+            TRYRC(mitre_score_all(st[0], nullptr, 0, W64, nullptr, d_X, d_omega, d_kappa, N, p, sigma2, d_ws[0],
+                                  ws_bytes, nullptr, d_status));
+            TRY(cudaStreamSynchronize(st[0]));
+        }
+        TRY(cudaMemcpy(&h_status, d_status, sizeof(int32_t), cudaMemcpyDeviceToHost));
+        if (h_status & (MITRE_STATUS_BASE_NOT_PD | MITRE_STATUS_BAD_SCHUR)) rc = MITRE_ERR_NOT_PD;
+    }
+cleanup:
+#undef TRY
+#undef TRYRC
+    for (int b = 0; b < 2; ++b) {
+        if (st[b]) cudaStreamDestroy(st[b]);
+        cudaFree(d_truth[b]);
+        cudaFree(d_packed[b]);
+        cudaFree(d_out[b]);
+        cudaFree(d_ws[b]);
+        if (h_stage[b]) cudaFreeHost(h_stage[b]);
+    }
+    cudaFree(d_X);
+    cudaFree(d_omega);
+    cudaFree(d_kappa);
+    cudaFree(d_status);
+    free(h_kappa);
+    return rc;
+}

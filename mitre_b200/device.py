@@ -1,0 +1,267 @@
+"""Torch-tensor wrappers over the C ABI (include/mitre_b200.h).
+
+PyTorch is only the carrier here: it owns device memory and the current stream; every compute
+step is a kernel in libmitre_b200.so.  All functions take / return CUDA tensors, are
+asynchronous on torch's current stream, and raise if no CUDA device is present -- there is no
+CPU path.
+
+Packed truth rows are carried as torch.int64 tensors [P, W64] holding the uint64 bit patterns
+(subject i -> word i//64, bit 63 - i%64; see the header).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib
+
+F64 = torch.float64
+I64 = torch.int64
+I32 = torch.int32
+U8 = torch.uint8
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("mitre_b200 needs a CUDA device (built for sm_100a / B200); "
+                           "there is no CPU fallback")
+
+
+def dev():
+    require_cuda()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def words_for(N):
+    return (int(N) + 63) // 64
+
+
+def _dev_f64(a):
+    if isinstance(a, torch.Tensor):
+        return a.to(device=dev(), dtype=F64).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=dev())
+
+
+def device_info():
+    sm, ma, mi = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    smem = ctypes.c_size_t()
+    check(lib().mitre_device_info(ctypes.byref(sm), ctypes.byref(ma), ctypes.byref(mi),
+                                  ctypes.byref(smem)), "mitre_device_info")
+    return dict(sm_count=sm.value, cc=(ma.value, mi.value), smem_optin=smem.value)
+
+
+# ---- packing ---------------------------------------------------------------------------------
+
+def pack_mask(mask_bool):
+    """Host helper: bool[N] -> packed int64[W64] numpy (bit layout of the header)."""
+    m = np.asarray(mask_bool, dtype=bool)
+    N = m.shape[0]
+    out = np.zeros(words_for(N), dtype=np.uint64)
+    idx = np.nonzero(m)[0]
+    np.bitwise_or.at(out, idx // 64, np.uint64(1) << (np.uint64(63) - (idx % 64).astype(np.uint64)))
+    return out.view(np.int64)
+
+
+def pack_rows(truth):
+    """bool / uint8 / float64 [P, N] (tensor or ndarray) -> packed int64[P, W64] on the device."""
+    require_cuda()
+    if not isinstance(truth, torch.Tensor):
+        truth = np.asarray(truth)
+        if truth.dtype == np.bool_:
+            truth = truth.view(np.uint8)
+        truth = torch.as_tensor(np.ascontiguousarray(truth), device=dev())
+    if truth.dtype == torch.bool:
+        truth = truth.view(U8)
+    truth = truth.to(dev()).contiguous()
+    P, N = truth.shape
+    packed = torch.empty((P, words_for(N)), dtype=I64, device=dev())
+    if truth.dtype == F64:
+        check(lib().mitre_pack_rows_f64(_stream(), _p(truth), P, N, _p(packed)), "mitre_pack_rows_f64")
+    elif truth.dtype == U8:
+        check(lib().mitre_pack_rows_u8(_stream(), _p(truth), P, N, _p(packed)), "mitre_pack_rows_u8")
+    else:
+        raise TypeError("truth rows must be bool, uint8 or float64, got %s" % truth.dtype)
+    return packed
+
+
+def unpack_rows(packed, N):
+    """packed int64[P, W64] -> uint8[P, N] (0/1) on the device."""
+    P = packed.shape[0]
+    out = torch.empty((P, N), dtype=U8, device=packed.device)
+    check(lib().mitre_unpack_rows_u8(_stream(), _p(packed), P, int(N), _p(out)), "mitre_unpack_rows_u8")
+    return out
+
+
+# ---- scoring -----------------------------------------------------------------------------------
+
+class ScoreBuffers:
+    """Reusable per-model device buffers for mitre_score_all (workspace, status, output)."""
+
+    def __init__(self, P, N, max_p=_lib.MAX_P):
+        self.P, self.N = int(P), int(N)
+        nbytes = lib().mitre_score_workspace_bytes(self.N, max_p)
+        self.workspace = torch.empty(nbytes, dtype=U8, device=dev())
+        self.status = torch.zeros(1, dtype=I32, device=dev())
+        self.out = torch.empty(self.P, dtype=F64, device=dev())
+
+
+def score_all(packed, N, X, omega, kappa, sigma2, mask=None, buffers=None, out=None):
+    """log N(kappa/omega; 0, Omega^-1 + sigma2 [X|v_k][X|v_k]^T) for every packed row k.
+
+    packed int64[P, W64]; X [N, p]; omega, kappa [N]; mask: packed int64[W64] tensor or None.
+    Returns (out float64[P], status int32[1]) on the device, asynchronously."""
+    P, W64 = packed.shape
+    X = _dev_f64(X)
+    omega = _dev_f64(omega)
+    kappa = _dev_f64(kappa)
+    p = X.shape[1]
+    if buffers is None:
+        buffers = ScoreBuffers(P, N, p)
+    if out is None:
+        out = buffers.out if buffers.out.shape[0] == P else torch.empty(P, dtype=F64, device=dev())
+    ws = buffers.workspace
+    check(lib().mitre_score_all(_stream(), _p(packed), P, W64, _p(mask), _p(X), _p(omega), _p(kappa),
+                                int(N), int(p), float(sigma2), _p(ws), ws.numel(), _p(out),
+                                _p(buffers.status)), "mitre_score_all")
+    return out, buffers.status
+
+
+def raise_on_status(status):
+    """Synchronises; maps device status flags to numpy's LinAlgError like the reference
+    (efficient_likelihoods.pyx:42 -> np.linalg.cholesky)."""
+    s = int(status.item())
+    if s:
+        status.zero_()
+        raise np.linalg.LinAlgError("Matrix is not positive definite (status flags %d)" % s)
+
+
+def likelihood_z_given_X_batch(Xs, omega, kappa, sigma2, p_b=None):
+    """Xs [B, N, pmax] -> float64[B] dense log-likelihoods (logit_rules.py:171-177)."""
+    Xs = _dev_f64(Xs)
+    B, N, pmax = Xs.shape
+    omega = _dev_f64(omega)
+    kappa = _dev_f64(kappa)
+    pb = None
+    if p_b is not None:
+        pb = torch.as_tensor(np.asarray(p_b, dtype=np.int32), device=dev())
+    out = torch.empty(B, dtype=F64, device=dev())
+    status = torch.zeros(1, dtype=I32, device=dev())
+    check(lib().mitre_likelihood_z_given_X_batch(_stream(), _p(Xs), _p(pb), pmax, _p(omega),
+                                                 _p(kappa), N, B, float(sigma2), _p(out),
+                                                 _p(status)), "mitre_likelihood_z_given_X_batch")
+    return out, status
+
+
+def mc_logpdf(x, cov):
+    x = _dev_f64(x)
+    cov = _dev_f64(cov)
+    N = x.shape[0]
+    scratch = torch.empty((N, N), dtype=F64, device=dev())
+    out = torch.empty(1, dtype=F64, device=dev())
+    status = torch.zeros(1, dtype=I32, device=dev())
+    check(lib().mitre_mc_logpdf(_stream(), _p(x), _p(cov), N, _p(scratch), _p(out), _p(status)),
+          "mitre_mc_logpdf")
+    return out, status
+
+
+# ---- detector evaluation ---------------------------------------------------------------------
+
+def window_ranges(times, t_offsets, windows):
+    """times f64[S_pad], t_offsets i32[N+1], windows f64[W,2] -> (lo, cnt) int32[W, N]."""
+    N = t_offsets.shape[0] - 1
+    W = windows.shape[0]
+    lo = torch.empty((W, N), dtype=I32, device=dev())
+    cnt = torch.empty((W, N), dtype=I32, device=dev())
+    check(lib().mitre_window_ranges(_stream(), _p(times), _p(t_offsets), N, _p(windows), W, _p(lo),
+                                    _p(cnt)), "mitre_window_ranges")
+    return lo, cnt
+
+
+def detector_values(series, times, t_offsets, windows, lo, cnt, group_base, slope_ok, G, max_T):
+    V, stride = series.shape
+    N = t_offsets.shape[0] - 1
+    W = windows.shape[0]
+    values = torch.empty((G, N), dtype=F64, device=dev())
+    check(lib().mitre_detector_values(_stream(), _p(series), stride, _p(times), _p(t_offsets), N, V,
+                                      _p(windows), _p(lo), _p(cnt), _p(group_base), _p(slope_ok), W,
+                                      int(max_T), _p(values)), "mitre_detector_values")
+    return values
+
+
+def detector_thresholds(values):
+    G, N = values.shape
+    thresholds = torch.empty((G, max(N - 1, 0)), dtype=F64, device=dev())
+    K = torch.empty(G, dtype=I32, device=dev())
+    check(lib().mitre_detector_thresholds(_stream(), _p(values), G, N, _p(thresholds), _p(K)),
+          "mitre_detector_thresholds")
+    return thresholds, K
+
+
+def detector_row_offsets(K):
+    G = K.shape[0]
+    nbytes = lib().mitre_scan_workspace_bytes(G)
+    ws = torch.empty(nbytes, dtype=U8, device=dev())
+    offsets = torch.empty(G + 1, dtype=I64, device=dev())
+    check(lib().mitre_detector_row_offsets(_stream(), _p(K), G, _p(offsets), _p(ws), nbytes),
+          "mitre_detector_row_offsets")
+    return offsets
+
+
+def detector_rows(values, thresholds, K, row_offsets, P):
+    G, N = values.shape
+    packed = torch.empty((P, words_for(N)), dtype=I64, device=dev())
+    check(lib().mitre_detector_rows(_stream(), _p(values), _p(thresholds), _p(K), _p(row_offsets), G,
+                                    N, _p(packed)), "mitre_detector_rows")
+    return packed
+
+
+def lexsort_rows(rows, N, want_sorted=True):
+    """Stable lexicographic sort (np.lexsort(np.rot90(truth)) order).  Returns (perm int64[P],
+    sorted_rows int64[P, W64] or None)."""
+    P, W64 = rows.shape
+    perm = torch.empty(P, dtype=I64, device=dev())
+    sorted_rows = torch.empty_like(rows) if want_sorted else None
+    nbytes = lib().mitre_lexsort_workspace_bytes(P, W64)
+    ws = torch.empty(max(nbytes, 1), dtype=U8, device=dev())
+    check(lib().mitre_lexsort_rows(_stream(), _p(rows), P, W64, int(N), _p(perm), _p(sorted_rows),
+                                   _p(ws), nbytes), "mitre_lexsort_rows")
+    return perm, sorted_rows
+
+
+# ---- draw ------------------------------------------------------------------------------------------
+
+class DrawBuffers:
+    def __init__(self, P):
+        nbytes = lib().mitre_draw_workspace_bytes(int(P))
+        self.workspace = torch.empty(nbytes, dtype=U8, device=dev())
+        self.stats = torch.empty(2, dtype=F64, device=dev())
+        self.index = torch.empty(1, dtype=I64, device=dev())
+
+
+def weight_stats(a, b=None, buffers=None):
+    """(max, sum exp(w - max)) of w = a (+ b) as a float64[2] device tensor."""
+    P = a.shape[0]
+    buffers = buffers or DrawBuffers(P)
+    check(lib().mitre_weight_stats(_stream(), _p(a), _p(b), P, _p(buffers.stats),
+                                   _p(buffers.workspace), buffers.workspace.numel()),
+          "mitre_weight_stats")
+    return buffers.stats
+
+
+def draw_index(a, b, u, stabilise=False, buffers=None):
+    """#{cumsum(exp(w)) < u * total} (rules.py:1261-1264) as an int64[1] device tensor."""
+    P = a.shape[0]
+    buffers = buffers or DrawBuffers(P)
+    check(lib().mitre_draw_index(_stream(), _p(a), _p(b), P, float(u), int(bool(stabilise)),
+                                 _p(buffers.stats), _p(buffers.index), _p(buffers.workspace),
+                                 buffers.workspace.numel()), "mitre_draw_index")
+    return buffers.index

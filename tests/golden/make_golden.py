@@ -1,0 +1,183 @@
+#!/usr/bin/env python
+"""Generate the golden vectors in tests/golden/ FROM THE REFERENCE ITSELF.
+
+Runs only in the build container (needs /root/reference):
+  * detector fixtures come from the reference's own mitre/rules.py, imported unmodified in logic
+    through oracle/ref_shim.py (DiscreteRulePopulation.mine_rules, rules.py:325-436);
+  * scoring fixtures come from the reference's own Cython kernel, compiled from the unmodified
+    mitre/efficient_likelihoods.pyx by oracle/build_ref.py;
+  * dense fixtures come from the source text of mc_logpdf_np (mvnpdf_cholesky.py:53-74)
+    executed as-is (the rest of that file has py2 print statements and cannot be imported).
+
+Inputs are seeded (numpy RandomState) and produced by mitre_b200/synthetic.py, so the tests
+regenerate identical inputs on the GPU box and compare against the stored reference outputs.
+
+    python tests/golden/make_golden.py
+"""
+import os
+import re
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from mitre_b200 import synthetic          # noqa: E402  (host-side generator only)
+from oracle import build_ref, ref_shim    # noqa: E402
+from oracle.detectors_oracle import pack_rows   # noqa: E402
+
+# name -> make_series kwargs + population kwargs
+DETECTOR_CASES = {
+    "det_small": dict(series=dict(N=12, V=3, T=(5, 8), span=(0.0, 10.0), seed=11),
+                      pop=dict(tmin=1.0, N_intervals=4, tmax=None)),
+    "det_bokulich": dict(series=dict(N=35, V=6, T=(8, 25), span=(0.0, 375.0), seed=12),
+                         pop=dict(tmin=1.0, N_intervals=12, tmax=180.0)),
+    "det_digiulio": dict(series=dict(N=40, V=10, T=(4, 10), span=(140.0, 210.0), seed=13),
+                         pop=dict(tmin=1.0, N_intervals=1, tmax=100.0)),
+    "det_twoword": dict(series=dict(N=70, V=3, T=(4, 9), span=(0.0, 60.0), seed=14),
+                        pop=dict(tmin=1.0, N_intervals=3, tmax=None)),
+    "det_n64": dict(series=dict(N=64, V=2, T=(6, 12), span=(0.0, 30.0), seed=15,
+                                zero_fraction=0.3),
+                    pop=dict(tmin=5.0, N_intervals=3, tmax=None)),
+    "det_long": dict(series=dict(N=9, V=2, T=(140, 300), span=(0.0, 100.0), seed=16),
+                     pop=dict(tmin=1.0, N_intervals=2, tmax=None)),
+}
+
+TYPE_INDEX = {"slope": 0, "average": 1}
+DIR_INDEX = {"above": 0, "below": 1}
+
+
+def make_detector_case(rules, name, cfg):
+    d = synthetic.make_series(**cfg["series"])
+    V = cfg["series"]["V"]
+    data = rules.Dataset(d["X"], d["T"], d["y"], ["v%d" % i for i in range(V)],
+                         d["variable_weights"], d["experiment_start"], d["experiment_end"])
+    pop = rules.DiscreteRulePopulation(None, cfg["pop"]["tmin"], cfg["pop"]["N_intervals"],
+                                       tmax=cfg["pop"]["tmax"], data=data)
+    windows = np.array(pop.windows, dtype=np.float64).reshape(-1, 2)
+    wl = {tuple(w): i for i, w in enumerate(pop.windows)}
+    # values in enumeration order (window-major, variable, slope/average)
+    groups, vals = [], []
+    for wi, (w, ok) in enumerate(zip(pop.windows, pop.windows_ok_for_slope)):
+        for v in range(V):
+            for t in ("slope", "average"):
+                if t == "slope" and not ok:
+                    continue
+                groups.append((wi, v, TYPE_INDEX[t]))
+                vals.append(pop.primitive_values[(w, v, t)])
+    flat = pop.flat_rules
+    out = dict(
+        windows=windows, ok_slope=np.array(pop.windows_ok_for_slope, dtype=bool),
+        groups=np.array(groups, dtype=np.int32).reshape(-1, 3),
+        values=np.vstack(vals) if vals else np.zeros((0, len(d["X"]))),
+        order=np.asarray(pop._reordering_cache, dtype=np.int64),
+        sorted_truth_packed=pack_rows(np.asarray(pop.flat_truth, dtype=bool)),
+        rule_variable=np.array([r[0] for r in flat], dtype=np.int32),
+        rule_window=np.array([wl[tuple(r[1])] for r in flat], dtype=np.int32),
+        rule_type=np.array([TYPE_INDEX[r[2]] for r in flat], dtype=np.int8),
+        rule_direction=np.array([DIR_INDEX[r[3]] for r in flat], dtype=np.int8),
+        rule_threshold=np.array([r[4] for r in flat], dtype=np.float64),
+        flat_durations=np.asarray(pop.flat_durations, dtype=np.float64),
+        flat_variable_weights=np.asarray(pop.flat_variable_weights, dtype=np.float64),
+        n_subjects=np.int64(len(d["X"])),
+    )
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print("%-14s N=%d V=%d W=%d G=%d P=%d" % (name, len(d["X"]), V, len(windows), len(groups),
+                                             len(flat)))
+    return d, pop
+
+
+def scoring_inputs(seed, N, p, P, continuous=False, duplicate=False, mask_kind="random"):
+    """Seeded scoring case; the same function is imported by the tests to rebuild the inputs."""
+    rng = np.random.RandomState(seed)
+    X = (rng.rand(N, p) > 0.5).astype(np.float64)
+    X[:, -1] = 1.0
+    if duplicate and p >= 3:
+        X[:, 1] = X[:, 0]
+    if continuous and p >= 2:
+        c = rng.normal(size=N)
+        X[:, 0] = c - c.mean()
+    omega = rng.gamma(2.0, 1.0 / 8.0, size=N) + 0.05
+    y = rng.rand(N) > 0.5
+    truth = rng.rand(P, N) > rng.rand(P, 1)
+    if P >= 4:
+        truth[0] = False
+        truth[1] = True
+        truth[2] = X[:, min(1, p - 1)] > 0
+        truth[3] = ~truth[2]
+    truth = truth[np.lexsort(np.rot90(truth))]
+    if mask_kind == "all":
+        mask = np.ones(N, dtype=bool)
+    elif mask_kind == "none":
+        mask = np.zeros(N, dtype=bool)
+    else:
+        mask = rng.rand(N) > 0.3
+    return dict(X=X, omega=omega, y=y, truth=truth, mask=mask, sigma2=100.0)
+
+
+SCORING_CASES = {
+    "score_n35_p2": dict(seed=21, N=35, p=2, P=4000),
+    "score_n35_p7_dup": dict(seed=22, N=35, p=7, P=3000, duplicate=True),
+    "score_n12_p1": dict(seed=23, N=12, p=1, P=500, mask_kind="all"),
+    "score_n64_p4_cont": dict(seed=24, N=64, p=4, P=2000, continuous=True),
+    "score_n70_p4": dict(seed=25, N=70, p=4, P=1500),
+    "score_n200_p11": dict(seed=26, N=200, p=11, P=400),
+    "score_n35_p3_nomask": dict(seed=27, N=35, p=3, P=300, mask_kind="none"),
+    "score_n40_p13": dict(seed=28, N=40, p=13, P=1000),
+}
+
+
+def make_scoring_case(ref, name, cfg):
+    c = scoring_inputs(**cfg)
+    opts = (c["truth"] * c["mask"]).astype(np.float64)           # logit_rules.py:214-217
+    response = (c["y"] - 0.5) / c["omega"]                        # logit_rules.py:222-223
+    ll = ref.likelihoods_of_all_options(c["X"], c["omega"], response, opts, np.float64(c["sigma2"]))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), loglik=ll)
+    print("%-20s P=%d  loglik in [%.3f, %.3f]" % (name, len(ll), ll.min(), ll.max()))
+
+
+def reference_mc_logpdf_np():
+    """Execute the reference's mc_logpdf_np source text as-is (mvnpdf_cholesky.py:53-74)."""
+    path = os.path.join(ref_shim.REFERENCE, "mitre", "mvnpdf_cholesky.py")
+    src = open(path).read()
+    m = re.search(r"^def mc_logpdf_np\(.*?(?=^def )", src, re.S | re.M)
+    import scipy.linalg
+    ns = {"np": np, "scipy": scipy}
+    exec(compile(m.group(0), path, "exec"), ns)
+    return ns["mc_logpdf_np"]
+
+
+def dense_inputs(seed, N, p):
+    rng = np.random.RandomState(seed)
+    X = (rng.rand(N, p) > 0.5).astype(np.float64)
+    X[:, -1] = 1.0
+    omega = rng.gamma(2.0, 1.0 / 8.0, size=N) + 0.05
+    y = rng.rand(N) > 0.5
+    return dict(X=X, omega=omega, y=y, sigma2=100.0)
+
+
+DENSE_CASES = [(31, 35, 1), (32, 35, 4), (33, 40, 11), (34, 70, 6), (35, 200, 8), (36, 5, 2)]
+
+
+def main():
+    rules = ref_shim.load_rules()
+    ref = build_ref.load()
+    for name, cfg in DETECTOR_CASES.items():
+        make_detector_case(rules, name, cfg)
+    for name, cfg in SCORING_CASES.items():
+        make_scoring_case(ref, name, cfg)
+    mc = reference_mc_logpdf_np()
+    vals = []
+    for seed, N, p in DENSE_CASES:
+        c = dense_inputs(seed, N, p)
+        z = (c["y"] - 0.5) / c["omega"]
+        cov = np.diag(1.0 / c["omega"]) + c["sigma2"] * c["X"].dot(c["X"].T)   # logit_rules.py:175-176
+        vals.append(mc(z, cov))
+    np.savez_compressed(os.path.join(HERE, "dense.npz"), loglik=np.array(vals))
+    print("dense", vals)
+
+
+if __name__ == "__main__":
+    main()

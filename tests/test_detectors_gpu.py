@@ -1,0 +1,126 @@
+"""GPU parity of detector evaluation against the golden vectors generated from the reference's
+rules.py and against the numpy oracle.  Truth tables, sort order and mean values/thresholds are
+compared BIT-EXACTLY; slope values within 1e-9 relative (closed form vs LAPACK gelsd)."""
+import os
+
+import numpy as np
+import pytest
+
+from mitre_b200 import synthetic
+from oracle import detectors_oracle as DO
+from tests.golden import make_golden as MG
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def build_gpu_population(d, pop_cfg):
+    from mitre_b200 import rules as R
+    V = d["X"][0].shape[0]
+    data = R.Dataset(d["X"], d["T"], d["y"], ["v%d" % i for i in range(V)], d["variable_weights"],
+                     d["experiment_start"], d["experiment_end"])
+    pop = R.DiscreteRulePopulation(None, pop_cfg["tmin"], pop_cfg["N_intervals"], tmax=pop_cfg["tmax"],
+                                   data=data)
+    return data, pop
+
+
+def check_population(pop, gold_windows, gold_ok, gold_groups, gold_values, gold_order, gold_packed,
+                     gold_rule, N):
+    assert np.array_equal(np.array(pop.windows, dtype=np.float64).reshape(-1, 2), gold_windows)
+    assert np.array_equal(np.array(pop.windows_ok_for_slope, dtype=bool), gold_ok)
+    got_groups = np.stack([pop._group_window, pop._group_variable, pop._group_type], 1)
+    assert np.array_equal(got_groups, gold_groups)
+    vals = pop._values.cpu().numpy()
+    is_mean = gold_groups[:, 2] == 1
+    assert np.array_equal(vals[is_mean], gold_values[is_mean]), "window means must be bit-exact"
+    sl, gs = vals[~is_mean], gold_values[~is_mean]
+    if sl.size:
+        scale = np.maximum(np.abs(gs).max(axis=1, keepdims=True), 1e-300)
+        assert np.max(np.abs(sl - gs) / scale) < 1e-9
+    assert pop.n_primitives == gold_packed.shape[0]
+    got_packed = pop.packed_truth.cpu().numpy().view(np.uint64)
+    assert np.array_equal(got_packed, gold_packed), "sorted truth table must be bit-exact"
+    assert np.array_equal(pop._perm_host(), gold_order), "lexsort permutation must match np.lexsort"
+    # rule descriptors in sorted order
+    var, win, typ, dirn, thr = gold_rule
+    P = len(var)
+    idx = np.unique(np.r_[0:min(P, 50), np.linspace(0, P - 1, 200).astype(int)])
+    for i in idx:
+        t = pop.flat_rules[int(i)]
+        assert t[0] == var[i] and tuple(t[1]) == tuple(gold_windows[win[i]])
+        assert t[2] == ("slope", "average")[typ[i]] and t[3] == ("above", "below")[dirn[i]]
+        if typ[i] == 1:
+            assert t[4] == thr[i], "mean thresholds must be bit-exact"
+        else:
+            assert abs(t[4] - thr[i]) <= 1e-9 * max(abs(thr[i]), 1e-300) + 1e-300
+        assert pop.primitive_index[t] == i
+        assert np.array_equal(pop.truth_table[t], DO.unpack_rows(gold_packed[i:i + 1], N)[0])
+
+
+@pytest.mark.parametrize("name", sorted(MG.DETECTOR_CASES))
+def test_population_vs_reference_golden(name):
+    cfg = MG.DETECTOR_CASES[name]
+    gold = np.load(os.path.join(GOLD, name + ".npz"))
+    d = synthetic.make_series(**cfg["series"])
+    data, pop = build_gpu_population(d, cfg["pop"])
+    N = int(gold["n_subjects"])
+    check_population(pop, gold["windows"], gold["ok_slope"], gold["groups"], gold["values"], gold["order"],
+                     gold["sorted_truth_packed"],
+                     (gold["rule_variable"], gold["rule_window"], gold["rule_type"], gold["rule_direction"],
+                      gold["rule_threshold"]), N)
+    assert np.array_equal(pop.flat_durations, gold["flat_durations"])
+    assert np.array_equal(pop.flat_variable_weights, gold["flat_variable_weights"])
+    assert np.array_equal(pop.flat_truth, DO.unpack_rows(gold["sorted_truth_packed"], N))
+
+
+@pytest.mark.parametrize("N,V,T,nint", [(3, 2, (2, 4), 2), (33, 5, (3, 20), 6), (100, 3, (5, 9), 4),
+                                        (257, 2, (4, 6), 2)])
+def test_population_vs_oracle(N, V, T, nint):
+    d = synthetic.make_series(N=N, V=V, T=T, span=(0.0, 90.0), seed=N + V, zero_fraction=0.2)
+    ref = DO.build_population(d["X"], d["T"], 0.0, 90.0, nint, 1.0, None)
+    data, pop = build_gpu_population(d, dict(tmin=1.0, N_intervals=nint, tmax=None))
+    o = ref["order"]
+    check_population(pop, ref["windows"], ref["ok_slope"],
+                     np.stack([ref["group_window"], ref["group_variable"], ref["group_type"]], 1),
+                     ref["values"], o, DO.pack_rows(ref["truth"][o]),
+                     (ref["variable"][o], ref["window"][o], ref["type"][o], ref["direction"][o],
+                      ref["threshold"][o]), N)
+
+
+def test_structural_invariants_at_scale():
+    """S2-shaped problem (200 variables): below == NOT above, rows sorted, K <= N-1,
+    counts consistent -- the size-independent properties of SURVEY 8c."""
+    d = synthetic.make_shape("S2", seed=0)
+    data, pop = build_gpu_population(d, dict(tmin=d["tmin"], N_intervals=d["N_intervals"], tmax=d["tmax"]))
+    N = 35
+    rows = pop.packed_truth.cpu().numpy().view(np.uint64)[:, 0]
+    assert np.all(rows[1:] >= rows[:-1])                                  # lexsorted
+    K = pop._K_host
+    assert K.max() <= N - 1 and pop.n_primitives == 2 * int(K.sum())
+    valid = np.uint64(((1 << N) - 1) << (64 - N))
+    perm = pop._perm_host()
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(len(perm))
+    above = rows[inv[0::2]]
+    below = rows[inv[1::2]]
+    assert np.array_equal(below, ~above & valid)
+    # stability: equal rows keep enumeration order
+    same = rows[1:] == rows[:-1]
+    assert np.all(perm[1:][same] > perm[:-1][same])
+
+
+def test_no_windows_and_single_subject_edge_cases():
+    d = synthetic.make_series(N=4, V=2, T=(3, 5), span=(0.0, 10.0), seed=1)
+    data, pop = build_gpu_population(d, dict(tmin=100.0, N_intervals=3, tmax=None))   # no window long enough
+    assert len(pop) == 0 and pop.windows == [] and pop.flat_truth.shape == (0, 4)
+    d1 = synthetic.make_series(N=1, V=2, T=(6, 6), span=(0.0, 10.0), seed=2)
+    data1, pop1 = build_gpu_population(d1, dict(tmin=1.0, N_intervals=2, tmax=None))
+    assert len(pop1) == 0 and len(pop1.windows) > 0          # one subject => no thresholds
+
+
+def test_update_truths_rebuilds_identically():
+    d = synthetic.make_series(N=20, V=3, T=(5, 9), span=(0.0, 40.0), seed=5)
+    data, pop = build_gpu_population(d, dict(tmin=1.0, N_intervals=4, tmax=None))
+    before = pop.packed_truth.cpu().numpy().copy()
+    pop._update_truths()
+    assert np.array_equal(pop.packed_truth.cpu().numpy(), before)
