@@ -371,8 +371,11 @@ class DiscreteRulePopulation:
             self._row_offsets_host = self._row_offsets.cpu().numpy()
             self._K_host = self._K.cpu().numpy()
             self._P = int(self._row_offsets_host[-1])
-            self._rows = D.detector_rows(self._values, self._thresholds, self._K, self._row_offsets,
-                                         self._P)
+            if self._P > 0:
+                self._rows = D.detector_rows(self._values, self._thresholds, self._K,
+                                             self._row_offsets, self._P)
+            else:
+                self._rows = torch.empty((0, D.words_for(N)), dtype=torch.int64, device=D.dev())
         self.truth_table = _TruthTable(self)
         self._host_cache = {}
 

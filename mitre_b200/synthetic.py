@@ -40,7 +40,7 @@ def sample_times(rng, n, t_start, t_end):
 
 
 def make_series(N, V, T=(8, 25), span=(0.0, 375.0), seed=0, zero_fraction=0.1,
-                perturb=True, dtype=np.float64, **_ignored):
+                perturb=True, dtype=np.float64, allow_constant=False, **_ignored):
     """Returns dict(X=list of [V, T_s] arrays, T=list of [T_s] arrays, y=bool[N],
     variable_weights=float64[V], experiment_start, experiment_end)."""
     rng = np.random.RandomState(seed)
@@ -61,6 +61,11 @@ def make_series(N, V, T=(8, 25), span=(0.0, 375.0), seed=0, zero_fraction=0.1,
             x[np.ix_(pert_vars, inside)] *= 8.0
         x = np.clip(x, 0.0, 1.0)
         zero = rng.rand(V) < zero_fraction
+        if not allow_constant and V - zero.sum() < 2:
+            # a subject with a single non-zero variable has the CONSTANT relative abundance 1.0,
+            # whose least-squares slope is LAPACK rounding noise in the reference (DESIGN.md,
+            # "slope parity"); keep at least two variables alive
+            zero[rng.choice(V, size=min(2, V), replace=False)] = False
         x[zero, :] = 0.0
         tot = x.sum(axis=0)
         tot[tot == 0.0] = 1.0

@@ -124,3 +124,26 @@ def test_update_truths_rebuilds_identically():
     before = pop.packed_truth.cpu().numpy().copy()
     pop._update_truths()
     assert np.array_equal(pop.packed_truth.cpu().numpy(), before)
+
+
+def test_constant_series_slope_divergence_is_confined_to_slope_rows():
+    """DESIGN.md "slope parity": a constant non-zero series has slope exactly 0 in closed form and
+    ~1e-20 LAPACK noise in the reference, which changes the tie structure of that slope group only.
+    Every 'average' primitive of the reference must still be present with an identical truth row."""
+    cfg = MG.DIVERGENT_CASES["det_constslope"]
+    gold = np.load(os.path.join(GOLD, "det_constslope.npz"))
+    d = synthetic.make_series(**cfg["series"])
+    data, pop = build_gpu_population(d, cfg["pop"])
+    N = int(gold["n_subjects"])
+    truth = DO.unpack_rows(gold["sorted_truth_packed"], N)
+    n_avg = 0
+    for i in np.nonzero(gold["rule_type"] == 1)[0]:
+        key = (int(gold["rule_variable"][i]), tuple(gold["windows"][gold["rule_window"][i]]), "average",
+               ("above", "below")[gold["rule_direction"][i]], gold["rule_threshold"][i])
+        assert key in pop.truth_table
+        assert np.array_equal(pop.truth_table[key], truth[i])
+        n_avg += 1
+    assert n_avg > 0
+    # and the divergence really is there: some slope row differs
+    got = pop.packed_truth.cpu().numpy().view(np.uint64)
+    assert got.shape != gold["sorted_truth_packed"].shape or not np.array_equal(got, gold["sorted_truth_packed"])
