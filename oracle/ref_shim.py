@@ -34,3 +34,58 @@ def load_rules():
     mod.zip = lambda *a: list(builtins.zip(*a))
     exec(compile(src, path, "exec"), mod.__dict__)
     return mod
+
+
+def load_reference_mc_logpdf_np():
+    """mc_logpdf_np's own source text (mvnpdf_cholesky.py:53-74), executed as-is; the rest of
+    that file holds py2 print statements and cannot be imported."""
+    import re
+    import numpy as np
+    import scipy.linalg
+    path = os.path.join(REFERENCE, "mitre", "mvnpdf_cholesky.py")
+    src = open(path).read()
+    m = re.search(r"^def mc_logpdf_np\(.*?(?=^def )", src, re.S | re.M)
+    ns = {"np": np, "scipy": scipy}
+    exec(compile(m.group(0), path, "exec"), ns)
+    return ns["mc_logpdf_np"]
+
+
+def load_logit_rules(pg_module, efficient_likelihoods_module):
+    """The reference's mitre/logit_rules.py under py3, unmodified in logic, with its two
+    unavailable imports supplied by the caller:
+      * `pypolyagamma` (third party, not vendored, not pinned: logit_rules.py:13, 62) ->
+        `pg_module`, which must offer PyPolyaGamma(seed).pgdrawv(n, z, out);
+      * `efficient_likelihoods` (logit_rules.py:17) -> the extension built by build_ref.py.
+    py2 -> py3 shims: implicit relative imports (6-7, 12), `from Queue import Empty` (15),
+    `np.array(counts.values())` (74), builtin reduce (204), xrange, .iteritems().
+    Returns (rules_module, logit_rules_module)."""
+    import queue
+    import sys
+    rules_mod = load_rules()
+    mvn = types.ModuleType("mvnpdf_cholesky")
+    mvn.mc_logpdf_np = load_reference_mc_logpdf_np()
+    saved = {k: sys.modules.get(k) for k in
+             ("rules", "mvnpdf_cholesky", "pypolyagamma", "Queue", "efficient_likelihoods")}
+    sys.modules["rules"] = rules_mod
+    sys.modules["mvnpdf_cholesky"] = mvn
+    sys.modules["pypolyagamma"] = pg_module
+    sys.modules["Queue"] = queue
+    sys.modules["efficient_likelihoods"] = efficient_likelihoods_module
+    try:
+        path = os.path.join(REFERENCE, "mitre", "logit_rules.py")
+        src = open(path).read()
+        src = src.replace("from scipy.misc import logsumexp", "from scipy.special import logsumexp")
+        src = src.replace(".iteritems()", ".items()")
+        src = src.replace("np.array(counts.values())", "np.array(list(counts.values()))")
+        mod = types.ModuleType("mitre_reference_logit_rules")
+        mod.__file__ = path
+        mod.xrange = range
+        mod.reduce = functools.reduce
+        exec(compile(src, path, "exec"), mod.__dict__)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return rules_mod, mod

@@ -1,0 +1,72 @@
+"""CPU-side tests of host logic that needs no device: the Polya-Gamma sampler, mask packing,
+the synthetic generator, RuleList / PrimitiveRule semantics."""
+import numpy as np
+
+from mitre_b200 import polyagamma, synthetic
+from mitre_b200.device import pack_mask, words_for
+from mitre_b200.rules import PrimitiveRule, RuleList
+from oracle.detectors_oracle import pack_rows
+
+
+def test_polyagamma_moments():
+    pg = polyagamma.PyPolyaGamma(3)
+    for z in [0.0, 1.0, 4.0]:
+        x = np.array([pg.pgdraw(1, z) for _ in range(20000)])
+        mean = 0.25 if z == 0 else np.tanh(z / 2) / (2 * z)
+        var = 1 / 24.0 if z == 0 else (np.sinh(z) - z) / (4 * z ** 3 * np.cosh(z / 2) ** 2)
+        assert abs(x.mean() - mean) < 5 * np.sqrt(var / len(x))
+        assert abs(x.var() - var) < 0.1 * var
+    out = np.zeros(4)
+    pg.pgdrawv(np.ones(4), np.array([0.1, -2.0, 3.0, 0.0]), out)
+    assert np.all(out > 0)
+
+
+def test_polyagamma_is_seed_deterministic():
+    a = polyagamma.PyPolyaGamma(5)
+    b = polyagamma.PyPolyaGamma(5)
+    assert [a.pgdraw(1, 0.7) for _ in range(50)] == [b.pgdraw(1, 0.7) for _ in range(50)]
+
+
+def test_pack_mask_layout_matches_oracle():
+    rng = np.random.RandomState(0)
+    for N in [1, 35, 64, 65, 200]:
+        m = rng.rand(N) > 0.5
+        assert np.array_equal(pack_mask(m).view(np.uint64), pack_rows(m[None])[0])
+        assert words_for(N) == (N + 63) // 64
+
+
+def test_synthetic_series_shape_and_no_constant_series():
+    d = synthetic.make_series(N=30, V=3, T=(4, 9), span=(0.0, 50.0), seed=1, zero_fraction=0.4)
+    assert len(d["X"]) == 30 and d["X"][0].shape[0] == 3
+    for x, t in zip(d["X"], d["T"]):
+        assert np.all(np.diff(t) > 0) and t[0] >= 0.0 and t[-1] <= 50.0
+        assert (x.sum(axis=1) > 0).sum() >= 2          # never a single live variable
+        assert np.allclose(x.sum(axis=0), 1.0)
+    assert d["y"].sum() == 15
+
+
+def test_primitive_rule_and_rule_list_semantics():
+    p = PrimitiveRule(1, (0.0, 10.0), "average", "above", 0.5)
+    assert PrimitiveRule(*p.as_tuple()).as_tuple() == p.as_tuple()
+    X = np.array([[0.0, 0.0, 0.0], [0.2, 0.9, 1.0]])
+    t = np.array([1.0, 5.0, 20.0])
+    assert p.evaluate(X[1], t) == np.mean([0.2, 0.9])
+    assert p.apply(X, t)
+    q = PrimitiveRule(1, (0.0, 10.0), "slope", "below", 0.0)
+    assert abs(q.evaluate(X[1], t) - 0.7 / 4.0) < 1e-12
+    rl = RuleList([[p, q], [p.as_tuple()]])
+    assert len(rl) == 2 and len(rl[0]) == 2
+    assert list(rl.apply_rules(X, t)) == [False, True]
+    c = rl.copy()
+    del c[0]
+    assert len(rl) == 2 and len(c) == 1
+    try:
+        RuleList([[]])
+        assert False
+    except ValueError:
+        pass
+    try:
+        PrimitiveRule(0, (30.0, 40.0), "average", "above", 0.0).evaluate(X[0], t)
+        assert False
+    except ValueError:
+        pass
