@@ -297,6 +297,13 @@ def build_population(args, rank, torch):
     torch.cuda.synchronize()
     marks["wall_s"] = time.perf_counter() - t0
     del pop.calculate_values, pop.update_base_rules, pop.sort_base_rules
+    # kernel-only time of detector evaluation: re-launch the fused kernel on the prepared inputs
+    from mitre_b200 import device as D
+    if pop._fused_args is not None:
+        D.detectors_fused(*pop._fused_args)
+        marks["detector_kernel_ms"] = cuda_time_ms(torch, lambda: D.detectors_fused(*pop._fused_args), 3)
+        marks["detector_kernel"] = "fused_detectors_kernel"
+    torch.cuda.empty_cache()
     return data, pop, marks
 
 
@@ -429,7 +436,7 @@ def run_b200(args):
         peak, peak_src = peaks()
         achieved = 16.0 * P / (kernel_ms * 1e-3) / 1e9
         det_bytes = detector_bytes(pop, data)
-        det_ms = build_marks["values"] + build_marks["thresholds_rows"]
+        det_ms = build_marks.get("detector_kernel_ms", build_marks["values"] + build_marks["thresholds_rows"])
         line = {
             "metric": METRIC, "value": P_total / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
@@ -451,9 +458,11 @@ def run_b200(args):
             "detector_eval": {"groups": int(pop._G), "algorithmic_bytes": det_bytes,
                               "ms": det_ms, "achieved_gbs": det_bytes / (det_ms * 1e-3) / 1e9,
                               "frac_of_hbm_peak": det_bytes / (det_ms * 1e-3) / 1e9 / peak,
-                              "values_ms": build_marks["values"],
-                              "thresholds_rows_ms": build_marks["thresholds_rows"],
-                              "lexsort_ms": build_marks["lexsort"], "build_wall_s": build_marks["wall_s"]},
+                              "kernel": build_marks.get("detector_kernel", "phase-by-phase kernels + host"),
+                              "host_phase_ms": {"values": build_marks["values"],
+                                                "thresholds_rows": build_marks["thresholds_rows"],
+                                                "lexsort": build_marks["lexsort"]},
+                              "build_wall_s": build_marks["wall_s"]},
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, pop, state, N, P, torch, D)

@@ -173,6 +173,47 @@ int mitre_lexsort_rows(void *stream, const uint64_t *rows, int64_t P, int W64, i
                        int64_t *perm, uint64_t *sorted_rows, void *workspace,
                        size_t workspace_bytes);
 
+/* ---- fused detector evaluation (N <= 63): values + thresholds + truth rows in ONE launch --------
+ *
+ * Same outputs as mitre_detector_values / _thresholds / _rows, but one thread owns one
+ * (window, variable, type) group end to end (register-resident sorting network), so HBM sees only
+ * the algorithmic output.
+ *
+ * mitre_window_lists precomputes, once per window set, everything that does not depend on the
+ * variable (ld = row stride of the per-sample lists, >= S):
+ *   lo, cnt, start int32[W, N]; inv_n, inv_sxx float64[W, N]; idx int32[W, ld]; dt float64[W, ld]
+ *   -- first sample / sample count / position in the window's flat sample list; 1/cnt and
+ *   1/sum((t - mid) - tbar)^2; the flat list of global sample indices and of centred times.
+ *
+ * mitre_detectors_fused:
+ *   series_t     float64[S_pad, vstride]: the series TRANSPOSED (sample-major, variable fastest,
+ *                vstride >= V), so the 32 lanes of a warp read 32 consecutive variables of one sample
+ *   task_window / task_type  int32 / int8 [n_tasks_wt]: the (window, type) pairs to evaluate
+ *                (type 0 = slope, only for windows with slope_ok; 1 = average)
+ *   rows_padded  uint64[G, 2(N-1)]: group g's first 2*K[g] slots hold its (above, below) row pairs
+ *                in threshold order; unused slots hold the sentinel ~0.  A stable lexsort of this
+ *                padded table with N+1 significant bits (mitre_lexsort_rows(..., N + 1, ...)) leaves
+ *                the P = 2*sum K valid rows first, in the reference order; mitre_densify_perm maps
+ *                the padded slot indices of that permutation to the reference's dense enumeration
+ *                indices (row_offsets[g] + slot).
+ * mitre_selftest_divide is a test hook: the kernel's exact small-integer division (window means)
+ *   next to the IEEE divide, elementwise.
+ */
+int mitre_window_lists(void *stream, const double *times, const int32_t *t_offsets, int N,
+                       const double *windows, int W, int64_t ld, int32_t *lo, int32_t *cnt,
+                       int32_t *start, double *inv_n, double *inv_sxx, int32_t *idx, double *dt);
+int mitre_detectors_fused(void *stream, const double *series_t, int64_t vstride, int N, int V,
+                          const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
+                          const double *winv_n, const double *winv_sxx, const int32_t *widx,
+                          const double *wdt, int64_t ld, const int64_t *group_base,
+                          const uint8_t *slope_ok, const int32_t *task_window,
+                          const int8_t *task_type, int n_tasks_wt, double *values,
+                          double *thresholds, int32_t *K, uint64_t *rows_padded);
+int mitre_densify_perm(void *stream, const int64_t *perm_padded, int64_t P, int N,
+                       const int64_t *row_offsets, int64_t *perm);
+int mitre_selftest_divide(void *stream, const double *a, const int32_t *n, int64_t count,
+                          double *fast, double *exact);
+
 /* ---- proposal draw: replaces the host-side weight assembly + choose_from_relative_probabilities
  *
  * Reference: weights = likelihoods + primitive_priors + multinomial_priors + log(relative_rates)

@@ -55,6 +55,12 @@ SIGNATURES = {
     "mitre_lexsort_workspace_bytes": (c_size_t, [c_i64, c_int]),
     "mitre_lexsort_rows": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p, c_size_t]),
+    "mitre_window_lists": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_i64] +
+                           [c_void_p] * 7),
+    "mitre_detectors_fused": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int] + [c_void_p] * 7 +
+                              [c_i64] + [c_void_p] * 4 + [c_int] + [c_void_p] * 4),
+    "mitre_selftest_divide": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p]),
+    "mitre_densify_perm": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p]),
     "mitre_draw_workspace_bytes": (c_size_t, [c_i64]),
     "mitre_weight_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p,
                                    c_size_t]),

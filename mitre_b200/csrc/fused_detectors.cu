@@ -1,0 +1,189 @@
+// fused_detectors.cu -- C ABI entry points of the fused detector path (kernel: fused_detectors.cuh,
+// instantiated per sorting-network size in fused_inst.cu).
+#include "fused_detectors.cuh"
+
+namespace mitre {
+int launch_fused_nb4(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
+                     const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
+                     const double *winv_n, const double *winv_sxx, const int32_t *widx,
+                     const double *wdt, int64_t ld, const int64_t *group_base,
+                     const uint8_t *slope_ok, const int32_t *task_window, const int8_t *task_type,
+                     int n_wt, double *values, double *thresholds, int32_t *K, uint64_t *rows);
+int launch_fused_nb8(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
+                     const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
+                     const double *winv_n, const double *winv_sxx, const int32_t *widx,
+                     const double *wdt, int64_t ld, const int64_t *group_base,
+                     const uint8_t *slope_ok, const int32_t *task_window, const int8_t *task_type,
+                     int n_wt, double *values, double *thresholds, int32_t *K, uint64_t *rows);
+int launch_fused_nb12(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
+                     const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
+                     const double *winv_n, const double *winv_sxx, const int32_t *widx,
+                     const double *wdt, int64_t ld, const int64_t *group_base,
+                     const uint8_t *slope_ok, const int32_t *task_window, const int8_t *task_type,
+                     int n_wt, double *values, double *thresholds, int32_t *K, uint64_t *rows);
+int launch_fused_nb16(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
+                     const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
+                     const double *winv_n, const double *winv_sxx, const int32_t *widx,
+                     const double *wdt, int64_t ld, const int64_t *group_base,
+                     const uint8_t *slope_ok, const int32_t *task_window, const int8_t *task_type,
+                     int n_wt, double *values, double *thresholds, int32_t *K, uint64_t *rows);
+int launch_fused_nb20(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
+                     const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
+                     const double *winv_n, const double *winv_sxx, const int32_t *widx,
+                     const double *wdt, int64_t ld, const int64_t *group_base,
+                     const uint8_t *slope_ok, const int32_t *task_window, const int8_t *task_type,
+                     int n_wt, double *values, double *thresholds, int32_t *K, uint64_t *rows);
+int launch_fused_nb24(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
+                     const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
+                     const double *winv_n, const double *winv_sxx, const int32_t *widx,
+                     const double *wdt, int64_t ld, const int64_t *group_base,
+                     const uint8_t *slope_ok, const int32_t *task_window, const int8_t *task_type,
+                     int n_wt, double *values, double *thresholds, int32_t *K, uint64_t *rows);
+int launch_fused_nb28(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
+                     const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
+                     const double *winv_n, const double *winv_sxx, const int32_t *widx,
+                     const double *wdt, int64_t ld, const int64_t *group_base,
+                     const uint8_t *slope_ok, const int32_t *task_window, const int8_t *task_type,
+                     int n_wt, double *values, double *thresholds, int32_t *K, uint64_t *rows);
+int launch_fused_nb32(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
+                     const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
+                     const double *winv_n, const double *winv_sxx, const int32_t *widx,
+                     const double *wdt, int64_t ld, const int64_t *group_base,
+                     const uint8_t *slope_ok, const int32_t *task_window, const int8_t *task_type,
+                     int n_wt, double *values, double *thresholds, int32_t *K, uint64_t *rows);
+int launch_fused_nb36(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
+                     const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
+                     const double *winv_n, const double *winv_sxx, const int32_t *widx,
+                     const double *wdt, int64_t ld, const int64_t *group_base,
+                     const uint8_t *slope_ok, const int32_t *task_window, const int8_t *task_type,
+                     int n_wt, double *values, double *thresholds, int32_t *K, uint64_t *rows);
+int launch_fused_nb40(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
+                     const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
+                     const double *winv_n, const double *winv_sxx, const int32_t *widx,
+                     const double *wdt, int64_t ld, const int64_t *group_base,
+                     const uint8_t *slope_ok, const int32_t *task_window, const int8_t *task_type,
+                     int n_wt, double *values, double *thresholds, int32_t *K, uint64_t *rows);
+int launch_fused_nb44(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
+                     const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
+                     const double *winv_n, const double *winv_sxx, const int32_t *widx,
+                     const double *wdt, int64_t ld, const int64_t *group_base,
+                     const uint8_t *slope_ok, const int32_t *task_window, const int8_t *task_type,
+                     int n_wt, double *values, double *thresholds, int32_t *K, uint64_t *rows);
+int launch_fused_nb48(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
+                     const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
+                     const double *winv_n, const double *winv_sxx, const int32_t *widx,
+                     const double *wdt, int64_t ld, const int64_t *group_base,
+                     const uint8_t *slope_ok, const int32_t *task_window, const int8_t *task_type,
+                     int n_wt, double *values, double *thresholds, int32_t *K, uint64_t *rows);
+int launch_fused_nb52(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
+                     const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
+                     const double *winv_n, const double *winv_sxx, const int32_t *widx,
+                     const double *wdt, int64_t ld, const int64_t *group_base,
+                     const uint8_t *slope_ok, const int32_t *task_window, const int8_t *task_type,
+                     int n_wt, double *values, double *thresholds, int32_t *K, uint64_t *rows);
+int launch_fused_nb56(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
+                     const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
+                     const double *winv_n, const double *winv_sxx, const int32_t *widx,
+                     const double *wdt, int64_t ld, const int64_t *group_base,
+                     const uint8_t *slope_ok, const int32_t *task_window, const int8_t *task_type,
+                     int n_wt, double *values, double *thresholds, int32_t *K, uint64_t *rows);
+int launch_fused_nb60(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
+                     const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
+                     const double *winv_n, const double *winv_sxx, const int32_t *widx,
+                     const double *wdt, int64_t ld, const int64_t *group_base,
+                     const uint8_t *slope_ok, const int32_t *task_window, const int8_t *task_type,
+                     int n_wt, double *values, double *thresholds, int32_t *K, uint64_t *rows);
+int launch_fused_nb64(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
+                     const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
+                     const double *winv_n, const double *winv_sxx, const int32_t *widx,
+                     const double *wdt, int64_t ld, const int64_t *group_base,
+                     const uint8_t *slope_ok, const int32_t *task_window, const int8_t *task_type,
+                     int n_wt, double *values, double *thresholds, int32_t *K, uint64_t *rows);
+
+// padded slot index -> dense enumeration index (the reference's _reordering_cache values)
+__global__ void __launch_bounds__(256)
+densify_perm_kernel(const int64_t *__restrict__ perm_pad, int64_t P, int L,
+                    const int64_t *__restrict__ row_offsets, int64_t *__restrict__ perm)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += stride) {
+        const int64_t r = perm_pad[i];
+        const int64_t g = r / L;
+        perm[i] = row_offsets[g] + (r - g * L);
+    }
+}
+}  // namespace mitre
+
+using namespace mitre;
+
+extern "C" int mitre_window_lists(void *stream, const double *times, const int32_t *t_offsets, int N,
+                                  const double *windows, int W, int64_t ld, int32_t *lo, int32_t *cnt,
+                                  int32_t *start, double *inv_n, double *inv_sxx, int32_t *idx, double *dt)
+{
+    if (N <= 0 || W < 0 || ld <= 0 || !times || !t_offsets) return MITRE_ERR_INVALID;
+    if (W == 0) return MITRE_OK;
+    if (!windows || !lo || !cnt || !start || !inv_n || !inv_sxx || !idx || !dt) return MITRE_ERR_INVALID;
+    window_lists_kernel<<<(W + 127) / 128, 128, 0, as_stream(stream)>>>(times, t_offsets, N, windows, W, ld, lo,
+                                                                        cnt, start, inv_n, inv_sxx, idx, dt);
+    MITRE_LAUNCH_CHECK();
+    return MITRE_OK;
+}
+
+extern "C" int mitre_detectors_fused(void *stream, const double *series_t, int64_t vstride, int N, int V,
+                                     const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
+                                     const double *winv_n, const double *winv_sxx, const int32_t *widx,
+                                     const double *wdt, int64_t ld, const int64_t *group_base,
+                                     const uint8_t *slope_ok, const int32_t *task_window,
+                                     const int8_t *task_type, int n_tasks_wt, double *values,
+                                     double *thresholds, int32_t *K, uint64_t *rows_padded)
+{
+    if (N < 2 || N > 63) return MITRE_ERR_UNSUPPORTED;
+    if (V <= 0 || n_tasks_wt < 0 || vstride < V || ld <= 0) return MITRE_ERR_INVALID;
+    if (n_tasks_wt == 0) return MITRE_OK;
+    if (!series_t || !wlo || !wcnt || !wstart || !winv_n || !winv_sxx || !widx || !wdt || !group_base ||
+        !slope_ok || !task_window || !task_type || !values || !thresholds || !K || !rows_padded)
+        return MITRE_ERR_INVALID;
+    if (N <= 4) return launch_fused_nb4(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, values, thresholds, K, rows_padded);
+    if (N <= 8) return launch_fused_nb8(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, values, thresholds, K, rows_padded);
+    if (N <= 12) return launch_fused_nb12(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, values, thresholds, K, rows_padded);
+    if (N <= 16) return launch_fused_nb16(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, values, thresholds, K, rows_padded);
+    if (N <= 20) return launch_fused_nb20(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, values, thresholds, K, rows_padded);
+    if (N <= 24) return launch_fused_nb24(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, values, thresholds, K, rows_padded);
+    if (N <= 28) return launch_fused_nb28(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, values, thresholds, K, rows_padded);
+    if (N <= 32) return launch_fused_nb32(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, values, thresholds, K, rows_padded);
+    if (N <= 36) return launch_fused_nb36(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, values, thresholds, K, rows_padded);
+    if (N <= 40) return launch_fused_nb40(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, values, thresholds, K, rows_padded);
+    if (N <= 44) return launch_fused_nb44(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, values, thresholds, K, rows_padded);
+    if (N <= 48) return launch_fused_nb48(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, values, thresholds, K, rows_padded);
+    if (N <= 52) return launch_fused_nb52(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, values, thresholds, K, rows_padded);
+    if (N <= 56) return launch_fused_nb56(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, values, thresholds, K, rows_padded);
+    if (N <= 60) return launch_fused_nb60(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, values, thresholds, K, rows_padded);
+    if (N <= 64) return launch_fused_nb64(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, values, thresholds, K, rows_padded);
+    return MITRE_ERR_UNSUPPORTED;
+}
+
+extern "C" int mitre_densify_perm(void *stream, const int64_t *perm_padded, int64_t P, int N,
+                                  const int64_t *row_offsets, int64_t *perm)
+{
+    if (P < 0 || N < 2) return MITRE_ERR_INVALID;
+    if (P == 0) return MITRE_OK;
+    if (!perm_padded || !row_offsets || !perm) return MITRE_ERR_INVALID;
+    int64_t blocks = ceil_div64(P, 256);
+    if (blocks > 16 * sm_count()) blocks = 16 * sm_count();
+    densify_perm_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(perm_padded, P, 2 * (N - 1), row_offsets,
+                                                                         perm);
+    MITRE_LAUNCH_CHECK();
+    return MITRE_OK;
+}
+
+// Test hook: the exact small-integer division used for window means vs the IEEE divide.
+extern "C" int mitre_selftest_divide(void *stream, const double *a, const int32_t *n, int64_t count,
+                                     double *fast, double *exact)
+{
+    if (count < 0 || (count > 0 && (!a || !n || !fast || !exact))) return MITRE_ERR_INVALID;
+    if (count == 0) return MITRE_OK;
+    selftest_divide_kernel<<<(unsigned)ceil_div64(count, 256), 256, 0, as_stream(stream)>>>(a, n, count, fast,
+                                                                                          exact);
+    MITRE_LAUNCH_CHECK();
+    return MITRE_OK;
+}

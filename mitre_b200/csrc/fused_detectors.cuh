@@ -1,0 +1,474 @@
+// fused_detectors.cuh -- single-launch detector evaluation for N <= 63 subjects
+// (DiscreteRulePopulation.calculate_values + thresholds_from_values + update_base_rules,
+// mitre/rules.py:465-600, in one kernel).
+//
+// One THREAD owns one (window, variable, type) group: a warp is 32 consecutive variables of one
+// window and type.  Every per-group quantity -- the N subject values, their sort, the neighbour
+// midpoints, the unique thresholds and the 2K truth rows -- lives in that thread's registers, so
+// the only HBM traffic is the algorithmic output (values, thresholds, K, rows) plus the series,
+// which is read through L2 from a sample-major transposed copy (series_t[j][v]: all 32 lanes of a
+// warp read the same sample j of consecutive variables = one coalesced 256-byte request).
+//
+//   sort      Batcher merge-exchange network over NB = N rounded up to 8 (+inf padding),
+//             generated at compile time, fully unrolled, values + subject ids in registers
+//   rows      with the values sorted, {s : v_s > theta_k} is a suffix of the sorted order:
+//             S[k] = OR of subject bits at ranks > k, with the run of values EQUAL to the
+//             midpoint excluded (T[k], see below) -- identical to comparing every value with
+//             the threshold as the reference does (rules.py:494-497), ties and midpoint
+//             rounding included
+//   output    staged per warp in shared memory and written back as contiguous 8-byte-per-lane
+//             runs (full sectors), rows in the PADDED layout rows[g][2(N-1)]: the first 2K[g]
+//             slots of a group hold (above, below) pairs in threshold order, the rest hold the
+//             sentinel ~0 so that a stable sort of the padded table leaves the valid rows first,
+//             in the reference's enumeration order among equals.
+//
+// Compiled with -fmad=false: 'average' must reproduce numpy's pairwise summation bit for bit.
+#pragma once
+#include <math.h>
+
+#include <utility>
+
+#include "common.cuh"
+
+namespace mitre {
+
+// ---- compile-time Batcher merge-exchange network for n inputs ------------------------------------
+template <int N>
+struct Network {
+    int a[N * 12];
+    int b[N * 12];
+    int count;
+};
+
+template <int N>
+constexpr Network<N> make_network()
+{
+    Network<N> net{};
+    int c = 0;
+    for (int p = 1; p < N; p *= 2)
+        for (int k = p; k >= 1; k /= 2)
+            for (int j = k % p; j + k < N; j += 2 * k) {
+                const int lim = (k < N - j - k) ? k : (N - j - k);
+                for (int i = 0; i < lim; ++i)
+                    if ((i + j) / (2 * p) == (i + j + k) / (2 * p)) {
+                        net.a[c] = i + j;
+                        net.b[c] = i + j + k;
+                        ++c;
+                    }
+            }
+    net.count = c;
+    return net;
+}
+
+template <int N>
+struct NetHolder {
+    static constexpr Network<N> net = make_network<N>();
+};
+
+__device__ __forceinline__ void cmp_exchange(double &x, double &y, int &ix, int &iy)
+{
+    const bool sw = x > y;
+    const double lo = sw ? y : x, hi = sw ? x : y;
+    const int ilo = sw ? iy : ix, ihi = sw ? ix : iy;
+    x = lo; y = hi; ix = ilo; iy = ihi;
+}
+
+template <int N, size_t... I>
+__device__ __forceinline__ void run_network(double (&v)[N], int (&id)[N], std::index_sequence<I...>)
+{
+    (cmp_exchange(v[NetHolder<N>::net.a[I]], v[NetHolder<N>::net.b[I]], id[NetHolder<N>::net.a[I]],
+                  id[NetHolder<N>::net.b[I]]),
+     ...);
+}
+
+// ---- numpy pairwise sum over a strided column --------------------------------------------------
+struct Column {
+    const double *base;   // &series_t[lo * stride + v]
+    int64_t stride;
+    __device__ __forceinline__ double operator()(int j) const { return __ldg(base + (int64_t)j * stride); }
+};
+
+__device__ __forceinline__ double pw_leaf_col(const Column &x, int off, int n)
+{
+    if (n < 8) {
+        double res = -0.0;
+        for (int i = 0; i < n; ++i) res = __dadd_rn(res, x(off + i));
+        return res;
+    }
+    double r0 = x(off + 0), r1 = x(off + 1), r2 = x(off + 2), r3 = x(off + 3);
+    double r4 = x(off + 4), r5 = x(off + 5), r6 = x(off + 6), r7 = x(off + 7);
+    int i = 8;
+    const int lim = n - (n % 8);
+    for (; i < lim; i += 8) {
+        r0 = __dadd_rn(r0, x(off + i + 0));
+        r1 = __dadd_rn(r1, x(off + i + 1));
+        r2 = __dadd_rn(r2, x(off + i + 2));
+        r3 = __dadd_rn(r3, x(off + i + 3));
+        r4 = __dadd_rn(r4, x(off + i + 4));
+        r5 = __dadd_rn(r5, x(off + i + 5));
+        r6 = __dadd_rn(r6, x(off + i + 6));
+        r7 = __dadd_rn(r7, x(off + i + 7));
+    }
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r0, r1), __dadd_rn(r2, r3)),
+                           __dadd_rn(__dadd_rn(r4, r5), __dadd_rn(r6, r7)));
+    for (; i < n; ++i) res = __dadd_rn(res, x(off + i));
+    return res;
+}
+
+static __device__ __noinline__ double pw_tree_col(const Column &x, int n)
+{
+    int st_off[40], st_n[40];
+    bool st_open[40];
+    double vals[40];
+    int top = 1, vtop = 0;
+    st_off[0] = 0; st_n[0] = n; st_open[0] = false;
+    while (top > 0) {
+        const int off = st_off[top - 1], m = st_n[top - 1];
+        if (m <= 128) {
+            --top;
+            vals[vtop++] = pw_leaf_col(x, off, m);
+        } else if (!st_open[top - 1]) {
+            st_open[top - 1] = true;
+            int n2 = m / 2;
+            n2 -= n2 % 8;
+            st_off[top] = off + n2; st_n[top] = m - n2; st_open[top] = false; ++top;
+            st_off[top] = off; st_n[top] = n2; st_open[top] = false; ++top;
+        } else {
+            --top;
+            const double right = vals[--vtop];
+            const double left = vals[--vtop];
+            vals[vtop++] = __dadd_rn(left, right);
+        }
+    }
+    return vals[0];
+}
+
+__device__ __forceinline__ double pairwise_sum_col(const Column &x, int n)
+{
+    return n <= 128 ? pw_leaf_col(x, 0, n) : pw_tree_col(x, n);
+}
+
+// ---- per-window tables shared by every variable ----------------------------------------------
+// One thread per window.  For window w (row stride `ld` = S_pad for the per-sample lists):
+//   lo, cnt [W, N]       first global sample index / number of samples with t0 <= t <= t1
+//   start   [W, N]       position of the subject's first sample in the window's flat sample list
+//   inv_n   [W, N]       1/cnt (correctly rounded)      inv_sxx [W, N]  1 / sum ((t-mid) - tbar)^2
+//   idx     [W, ld]      flat list of the window's global sample indices, subjects concatenated
+//   dt      [W, ld]      (t - mid) - tbar for the same positions (the variable-independent half of
+//                        the centred least-squares slope; same arithmetic as ols_slope in detectors.cu)
+static __global__ void __launch_bounds__(128)
+window_lists_kernel(const double *__restrict__ times, const int32_t *__restrict__ t_offsets, int N,
+                    const double *__restrict__ windows, int W, int64_t ld, int32_t *__restrict__ lo,
+                    int32_t *__restrict__ cnt, int32_t *__restrict__ start, double *__restrict__ inv_n,
+                    double *__restrict__ inv_sxx, int32_t *__restrict__ idx, double *__restrict__ dt)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W) return;
+    const double t0 = windows[2 * w], t1 = windows[2 * w + 1];
+    const double mid = (t0 + t1) * 0.5;
+    int pos = 0;
+    for (int s = 0; s < N; ++s) {
+        const int b = t_offsets[s], eend = t_offsets[s + 1];
+        int first = eend, c = 0;
+        for (int j = b; j < eend; ++j) {
+            const double t = times[j];
+            if (t >= t0 && t <= t1) {
+                if (c == 0) first = j;
+                ++c;
+            }
+        }
+        double st = 0.0;
+        for (int j = 0; j < c; ++j) st += times[first + j] - mid;
+        const double tb = c > 0 ? st / c : 0.0;
+        double sx = 0.0;
+        for (int j = 0; j < c; ++j) {
+            const double d = (times[first + j] - mid) - tb;
+            sx = fma(d, d, sx);
+            idx[(int64_t)w * ld + pos + j] = first + j;
+            dt[(int64_t)w * ld + pos + j] = d;
+        }
+        lo[w * N + s] = first;
+        cnt[w * N + s] = c;
+        start[w * N + s] = pos;
+        inv_n[w * N + s] = c > 0 ? 1.0 / c : 0.0;
+        inv_sxx[w * N + s] = 1.0 / sx;
+        pos += c;
+    }
+}
+
+// ---- the fused kernel -------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async8(void *dst_smem, const void *src_gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// a / n for a small positive integer n with y = RN(1/n): q = RN(a y), r = a - n q (exact, one
+// fma), q' = RN(q + r y) is the correctly rounded quotient (Markstein); the guard sends values
+// near the ends of the exponent range to the IEEE divide.  Bit-identical to __ddiv_rn
+// (tests/test_detectors_gpu.py::test_exact_division_selftest).
+__device__ __forceinline__ double div_small_int(double a, double n, double y)
+{
+    const double aa = fabs(a);
+    if (!(aa > 1e-280 && aa < 1e280)) return __ddiv_rn(a, n);
+    const double q = __dmul_rn(a, y);
+    const double r = __fma_rn(-q, n, a);
+    return __fma_rn(r, y, q);
+}
+
+// numpy pairwise sum of this lane's column x[0..n) staged as x[j * 32] (n <= kFusedCap <= 128)
+__device__ __forceinline__ double pw_sum_staged(const double *x, int n)
+{
+    if (n < 8) {
+        double res = -0.0;
+#pragma unroll
+        for (int i = 0; i < 7; ++i)
+            if (i < n) res = __dadd_rn(res, x[i * 32]);
+        return res;
+    }
+    double r0 = x[0], r1 = x[32], r2 = x[64], r3 = x[96], r4 = x[128], r5 = x[160], r6 = x[192], r7 = x[224];
+    int i = 8;
+    const int lim = n & ~7;
+    for (; i < lim; i += 8) {
+        const double *xi = x + i * 32;
+        r0 = __dadd_rn(r0, xi[0]);
+        r1 = __dadd_rn(r1, xi[32]);
+        r2 = __dadd_rn(r2, xi[64]);
+        r3 = __dadd_rn(r3, xi[96]);
+        r4 = __dadd_rn(r4, xi[128]);
+        r5 = __dadd_rn(r5, xi[160]);
+        r6 = __dadd_rn(r6, xi[192]);
+        r7 = __dadd_rn(r7, xi[224]);
+    }
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r0, r1), __dadd_rn(r2, r3)),
+                           __dadd_rn(__dadd_rn(r4, r5), __dadd_rn(r6, r7)));
+#pragma unroll
+    for (int t = 0; t < 7; ++t)
+        if (i + t < n) res = __dadd_rn(res, x[(i + t) * 32]);
+    return res;
+}
+
+constexpr int kFusedCap = 40;   // samples per staging chunk ([cap][32 lanes] doubles = 10 KB per warp)
+
+// Oversized subject (more in-window samples than a staging chunk): straight from global memory.
+static __device__ __noinline__ double subject_value_global(const double *series_t, int64_t vstride, int lo_s,
+                                                            int vc, int n, int type, const double *dts,
+                                                            double inv_n, double inv_sxx)
+{
+    const Column x{series_t + (int64_t)lo_s * vstride + vc, vstride};
+    if (type == 1) return __ddiv_rn(pairwise_sum_col(x, n), (double)n);
+    double sx = 0.0;
+    for (int j = 0; j < n; ++j) sx += x(j);
+    const double xb = sx * inv_n;
+    double sxy = 0.0;
+    for (int j = 0; j < n; ++j) sxy = fma(__ldg(dts + j), x(j) - xb, sxy);
+    return sxy * inv_sxx;
+}
+
+template <int NB>
+__global__ void __launch_bounds__(256, 1)
+fused_detectors_kernel(const double *__restrict__ series_t, int64_t vstride, int N, int V,
+                       const int32_t *__restrict__ wlo, const int32_t *__restrict__ wcnt,
+                       const int32_t *__restrict__ wstart, const double *__restrict__ winv_n,
+                       const double *__restrict__ winv_sxx, const int32_t *__restrict__ widx,
+                       const double *__restrict__ wdt, int64_t ld, const int64_t *__restrict__ group_base,
+                       const uint8_t *__restrict__ slope_ok, const int32_t *__restrict__ task_window,
+                       const int8_t *__restrict__ task_type, int n_wt, double *__restrict__ values,
+                       double *__restrict__ thresholds, int32_t *__restrict__ K,
+                       uint64_t *__restrict__ rows)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int warps_per_cta = blockDim.x >> 5;
+    const int L = 2 * (N - 1);                 // row slots per group
+    const int vs_stride = N | 1;               // odd 8-byte stride: conflict-free per-lane columns
+    const size_t per_warp = (size_t)kFusedCap * 32 + (size_t)32 * vs_stride + 3 * NB;   // 8-byte units
+    double *samples = reinterpret_cast<double *>(smem_raw) + (size_t)wid * per_warp;   // [cap][32]
+    double *vals = samples + kFusedCap * 32;                                          // [32][vs_stride]
+    double *s_invn = vals + 32 * vs_stride;                                           // [NB]
+    double *s_invsxx = s_invn + NB;                                                   // [NB]
+    int *s_cnt = reinterpret_cast<int *>(s_invsxx + NB);                              // [NB]
+    int *s_start = s_cnt + NB;                                                        // [NB]
+
+    const int n_vtiles = (V + 31) >> 5;
+    const int64_t n_tasks = (int64_t)n_wt * n_vtiles;
+    const int64_t warp0 = (int64_t)blockIdx.x * warps_per_cta + wid;
+    const int64_t nwarps = (int64_t)gridDim.x * warps_per_cta;
+    const uint64_t valid = ~0ull << (64 - N);
+
+    for (int64_t task = warp0; task < n_tasks; task += nwarps) {
+        const int wt = (int)(task / n_vtiles);
+        const int vt = (int)(task % n_vtiles);
+        const int w = task_window[wt];
+        const int type = task_type[wt];                 // 0 slope, 1 average
+        const int nt = 1 + slope_ok[w];
+        const int v = vt * 32 + lane;
+        const bool live = v < V;
+        const int vc = live ? v : V - 1;               // dead lanes recompute a live column, store nothing
+        const int64_t g = group_base[w] + (nt == 2 ? type : 0) + (int64_t)vc * nt;
+        const double *col = series_t + vc;
+        const int32_t *idx_w = widx + (int64_t)w * ld;
+        const double *dt_w = wdt + (int64_t)w * ld;
+
+        __syncwarp();
+        for (int s = lane; s < N; s += 32) {
+            s_cnt[s] = wcnt[w * N + s];
+            s_start[s] = wstart[w * N + s];
+            s_invn[s] = winv_n[w * N + s];
+            s_invsxx[s] = winv_sxx[w * N + s];
+        }
+        __syncwarp();
+
+        // ---- values (rules.py:80-141): subjects in chunks whose samples fit the staging buffer,
+        //      fetched with cp.async (no register round trip, every load of a chunk in flight) ----
+        for (int s = 0; s < N;) {
+            int e = s, tot = 0;
+            while (e < N && tot + s_cnt[e] <= kFusedCap) { tot += s_cnt[e]; ++e; }
+            if (e == s) {
+                vals[lane * vs_stride + s] =
+                    subject_value_global(series_t, vstride, wlo[w * N + s], vc, s_cnt[s], type,
+                                         dt_w + s_start[s], s_invn[s], s_invsxx[s]);
+                ++s;
+                continue;
+            }
+            const int p0 = s_start[s];
+#pragma unroll 4
+            for (int j = 0; j < tot; ++j)
+                cp_async8(samples + j * 32 + lane, col + (int64_t)__ldg(idx_w + p0 + j) * vstride);
+            cp_async_wait_all();
+            __syncwarp();
+            for (int q = s; q < e; ++q) {
+                const int n = s_cnt[q];
+                const int off = s_start[q] - p0;
+                const double *x = samples + off * 32 + lane;
+                double vq;
+                if (type == 1) {
+                    vq = div_small_int(pw_sum_staged(x, n), (double)n, s_invn[q]);
+                } else {
+                    double sx = 0.0;
+                    for (int j = 0; j < n; ++j) sx += x[j * 32];
+                    const double xb = sx * s_invn[q];
+                    const double *dq = dt_w + p0 + off;
+                    double sxy = 0.0;
+                    for (int j = 0; j < n; ++j) sxy = fma(__ldg(dq + j), x[j * 32] - xb, sxy);
+                    vq = sxy * s_invsxx[q];
+                }
+                vals[lane * vs_stride + q] = vq;
+            }
+            __syncwarp();
+            s = e;
+        }
+        double val[NB];
+        int id[NB];
+#pragma unroll
+        for (int s = 0; s < NB; ++s) {
+            id[s] = s;
+            val[s] = (s < N) ? vals[lane * vs_stride + s] : INFINITY;
+        }
+        if (live) {
+            double *vg = values + g * N;
+#pragma unroll
+            for (int s = 0; s < NB; ++s)
+                if (s < N) vg[s] = val[s];
+        }
+
+        // ---- sort (rules.py:536) ----
+        run_network<NB>(val, id, std::make_index_sequence<NetHolder<NB>::net.count>{});
+
+        // ---- thresholds (rules.py:539, 576): neighbour midpoints, first of every run ----
+        int kcount = 0;
+        {
+            double *tg = thresholds + g * (N - 1);
+            double prev = 0.0;
+#pragma unroll
+            for (int k = 0; k < NB - 1; ++k) {
+                if (k < N - 1) {
+                    const double m = __dmul_rn(0.5, __dadd_rn(val[k], val[k + 1]));
+                    if (k == 0 || m != prev) {
+                        if (live) tg[kcount] = m;
+                        ++kcount;
+                    }
+                    prev = m;
+                }
+            }
+            if (live) {
+                for (int k2 = kcount; k2 < N - 1; ++k2) tg[k2] = 0.0;
+                K[g] = kcount;
+            }
+        }
+
+        // ---- rows (rules.py:490-497), walking the sorted order downwards:
+        //      acc = subjects at ranks > k; Tn = subjects after the run of values equal to val[k+1].
+        //      {s : v_s > m_k} = acc unless the midpoint rounds onto val[k+1], then Tn. ----
+        {
+            ulonglong2 *rg = reinterpret_cast<ulonglong2 *>(rows + g * L);
+            uint64_t acc = 0, Tn = 0;
+            int pos = kcount - 1;
+#pragma unroll
+            for (int k = NB - 1; k >= 0; --k) {
+                if (k == N - 1) {
+                    acc = 1ull << (63 - id[k]);
+                    Tn = 0;
+                } else if (k < N - 1) {
+                    const double m = __dmul_rn(0.5, __dadd_rn(val[k], val[k + 1]));
+                    bool uniq = true;
+                    if (k > 0) uniq = m != __dmul_rn(0.5, __dadd_rn(val[k - 1], val[k]));
+                    if (uniq) {
+                        const uint64_t above = (m == val[k + 1]) ? Tn : acc;
+                        if (live) rg[pos] = make_ulonglong2(above, ~above & valid);
+                        --pos;
+                    }
+                    Tn = (val[k] == val[k + 1]) ? Tn : acc;
+                    acc |= 1ull << (63 - id[k]);
+                }
+            }
+            if (live)
+                for (int k2 = kcount; k2 < N - 1; ++k2) rg[k2] = make_ulonglong2(~0ull, ~0ull);
+        }
+    }
+}
+
+template <int NB>
+static int launch_fused_impl(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
+                             const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
+                             const double *winv_n, const double *winv_sxx, const int32_t *widx,
+                             const double *wdt, int64_t ld, const int64_t *group_base,
+                             const uint8_t *slope_ok, const int32_t *task_window, const int8_t *task_type,
+                             int n_wt, double *values, double *thresholds, int32_t *K, uint64_t *rows)
+{
+    const int vs_stride = N | 1;
+    const size_t per_warp = ((size_t)kFusedCap * 32 + (size_t)32 * vs_stride + 3 * NB) * sizeof(double);
+    int warps = (int)((smem_optin() - 1024) / per_warp);
+    if (warps > 8) warps = 8;
+    if (warps < 1) return MITRE_ERR_UNSUPPORTED;
+    const size_t smem = per_warp * warps;
+    auto kern = fused_detectors_kernel<NB>;
+    MITRE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    MITRE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
+    if (per_sm < 1) return MITRE_ERR_UNSUPPORTED;
+    const int64_t n_tasks = (int64_t)n_wt * ((V + 31) / 32);
+    int64_t blocks = (int64_t)sm_count() * per_sm;
+    const int64_t need = ceil_div64(n_tasks, warps);
+    if (need < blocks) blocks = need;
+    if (blocks < 1) blocks = 1;
+    kern<<<(unsigned)blocks, warps * 32, smem, st>>>(series_t, vstride, N, V, wlo, wcnt, wstart, winv_n,
+                                                     winv_sxx, widx, wdt, ld, group_base, slope_ok,
+                                                     task_window, task_type, n_wt, values, thresholds, K,
+                                                     rows);
+    MITRE_LAUNCH_CHECK();
+    return MITRE_OK;
+}
+
+// test hook: div_small_int against the IEEE divide
+static __global__ void selftest_divide_kernel(const double *a, const int32_t *n, int64_t count, double *fast,
+                                              double *exact)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const double nd = (double)n[i];
+    fast[i] = div_small_int(a[i], nd, __ddiv_rn(1.0, nd));
+    exact[i] = __ddiv_rn(a[i], nd);
+}
+
+}  // namespace mitre

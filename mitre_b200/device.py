@@ -224,6 +224,58 @@ def detector_rows(values, thresholds, K, row_offsets, P):
     return packed
 
 
+def window_lists(times, t_offsets, windows):
+    """Variable-independent per-window tables for the fused detector kernel (mitre_window_lists)."""
+    N = t_offsets.shape[0] - 1
+    W = windows.shape[0]
+    ld = times.shape[0]
+    t = dict(lo=torch.empty((W, N), dtype=I32, device=dev()),
+             cnt=torch.empty((W, N), dtype=I32, device=dev()),
+             start=torch.empty((W, N), dtype=I32, device=dev()),
+             inv_n=torch.empty((W, N), dtype=F64, device=dev()),
+             inv_sxx=torch.empty((W, N), dtype=F64, device=dev()),
+             idx=torch.zeros((W, ld), dtype=I32, device=dev()),
+             dt=torch.zeros((W, ld), dtype=F64, device=dev()), ld=ld)
+    check(lib().mitre_window_lists(_stream(), _p(times), _p(t_offsets), N, _p(windows), W, ld, _p(t['lo']),
+                                   _p(t['cnt']), _p(t['start']), _p(t['inv_n']), _p(t['inv_sxx']),
+                                   _p(t['idx']), _p(t['dt'])), "mitre_window_lists")
+    return t
+
+
+def detectors_fused(series_t, N, V, lists, group_base, slope_ok, task_window, task_type, G):
+    """One launch: values f64[G, N], thresholds f64[G, N-1], K i32[G], rows_padded i64[G, 2(N-1)]."""
+    L = 2 * (N - 1)
+    values = torch.empty((G, N), dtype=F64, device=dev())
+    thresholds = torch.empty((G, N - 1), dtype=F64, device=dev())
+    K = torch.empty(G, dtype=I32, device=dev())
+    rows = torch.empty((G, L), dtype=I64, device=dev())
+    check(lib().mitre_detectors_fused(_stream(), _p(series_t), series_t.shape[1], int(N), int(V),
+                                      _p(lists['lo']), _p(lists['cnt']), _p(lists['start']),
+                                      _p(lists['inv_n']), _p(lists['inv_sxx']), _p(lists['idx']),
+                                      _p(lists['dt']), lists['ld'], _p(group_base), _p(slope_ok),
+                                      _p(task_window), _p(task_type), task_window.shape[0], _p(values),
+                                      _p(thresholds), _p(K), _p(rows)), "mitre_detectors_fused")
+    return values, thresholds, K, rows
+
+
+def selftest_divide(a, n):
+    a = _dev_f64(a)
+    n = torch.as_tensor(np.asarray(n, dtype=np.int32), device=dev())
+    fast = torch.empty_like(a)
+    exact = torch.empty_like(a)
+    check(lib().mitre_selftest_divide(_stream(), _p(a), _p(n), a.shape[0], _p(fast), _p(exact)),
+          "mitre_selftest_divide")
+    return fast, exact
+
+
+def densify_perm(perm_padded, N, row_offsets):
+    P = perm_padded.shape[0]
+    perm = torch.empty(P, dtype=I64, device=dev())
+    check(lib().mitre_densify_perm(_stream(), _p(perm_padded), P, int(N), _p(row_offsets), _p(perm)),
+          "mitre_densify_perm")
+    return perm
+
+
 def lexsort_rows(rows, N, want_sorted=True):
     """Stable lexicographic sort (np.lexsort(np.rot90(truth)) order).  Returns (perm int64[P],
     sorted_rows int64[P, W64] or None)."""

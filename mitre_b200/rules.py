@@ -253,6 +253,8 @@ class _PrimitiveValues:
 class DiscreteRulePopulation:
     """rules.py:245-810, mined on the GPU."""
 
+    use_fused = True    # N <= 63: single-launch detector evaluation; False forces the phase-by-phase path
+
     def __init__(self, model, tmin, N_intervals, tmax=None, data=None, max_thresholds=None):
         self.model = model
         self.data = model.data if data is None else data
@@ -272,7 +274,8 @@ class DiscreteRulePopulation:
         state = dict(self.__dict__)
         for k in list(state):
             if k.startswith('_d_') or k in ('_values', '_thresholds', '_K', '_row_offsets', '_rows',
-                                            '_perm', '_sorted_rows', '_row_group'):
+                                            '_perm', '_sorted_rows', '_row_group', '_rows_padded', '_fused', '_fused_args', '_active_rows',
+                                            '_d_windows'):
                 state[k] = None
         state['_host_cache'] = {}
         return state
@@ -347,11 +350,28 @@ class DiscreteRulePopulation:
             return
         self._d_windows = torch.as_tensor(np.array(self.windows, dtype=np.float64).reshape(-1, 2),
                                           device=D.dev())
-        lo, cnt = D.window_ranges(ds['times'], ds['t_offsets'], self._d_windows)
         d_gb = torch.as_tensor(group_base[:-1].copy(), device=D.dev())
         d_ok = torch.as_tensor(ok, device=D.dev())
-        self._values = D.detector_values(ds['series'], ds['times'], ds['t_offsets'], self._d_windows,
-                                         lo, cnt, d_gb, d_ok, self._G, ds['max_T'])
+        N = self.data.n_subjects
+        self._fused = None
+        self._fused_args = None
+        if self.use_fused and 2 <= N <= 63:
+            # one launch: values + thresholds + K + padded truth rows (fused_detectors.cuh)
+            lists = D.window_lists(ds['times'], ds['t_offsets'], self._d_windows)
+            tw, tt = [], []
+            for w in range(W):
+                if ok[w]:
+                    tw.append(w); tt.append(0)
+                tw.append(w); tt.append(1)
+            d_tw = torch.as_tensor(np.array(tw, dtype=np.int32), device=D.dev())
+            d_tt = torch.as_tensor(np.array(tt, dtype=np.int8), device=D.dev())
+            self._fused_args = (ds['series_t'], N, V, lists, d_gb, d_ok, d_tw, d_tt, self._G)
+            self._values, thr, K, rows_padded = D.detectors_fused(*self._fused_args)
+            self._fused = (thr, K, rows_padded)
+        else:
+            lo, cnt = D.window_ranges(ds['times'], ds['t_offsets'], self._d_windows)
+            self._values = D.detector_values(ds['series'], ds['times'], ds['t_offsets'],
+                                             self._d_windows, lo, cnt, d_gb, d_ok, self._G, ds['max_T'])
         self.primitive_values = _PrimitiveValues(self)
 
     # -- step 3 (rules.py:465-511) ------------------------------------------------------------------------
@@ -364,8 +384,18 @@ class DiscreteRulePopulation:
             self._K_host = np.zeros(0, dtype=np.int32)
             self._row_offsets_host = np.zeros(1, dtype=np.int64)
             self._rows = torch.empty((0, D.words_for(N)), dtype=torch.int64, device=D.dev())
+            self._rows_padded = None
             self._thresholds = torch.empty((0, max(N - 1, 0)), dtype=torch.float64, device=D.dev())
+        elif getattr(self, '_fused', None) is not None:
+            self._thresholds, self._K, self._rows_padded = self._fused
+            self._fused = None
+            self._row_offsets = D.detector_row_offsets(self._K)
+            self._row_offsets_host = self._row_offsets.cpu().numpy()
+            self._K_host = self._K.cpu().numpy()
+            self._P = int(self._row_offsets_host[-1])
+            self._rows = None
         else:
+            self._rows_padded = None
             self._thresholds, self._K = D.detector_thresholds(self._values)
             self._row_offsets = D.detector_row_offsets(self._K)
             self._row_offsets_host = self._row_offsets.cpu().numpy()
@@ -384,12 +414,20 @@ class DiscreteRulePopulation:
         from . import device as D
         import torch
         N = self.data.n_subjects
+        padded = getattr(self, '_rows_padded', None)
         if self._P == 0:
             self._perm = torch.empty(0, dtype=torch.int64, device=D.dev())
-            self._sorted_rows = self._rows
+            self._sorted_rows = torch.empty((0, D.words_for(N)), dtype=torch.int64, device=D.dev())
+        elif padded is not None:
+            # padded table: sentinel slots sort last (N + 1 significant bits), valid rows keep the
+            # reference's enumeration order among equals; slot indices -> dense enumeration indices
+            perm_pad, sorted_pad = D.lexsort_rows(padded.view(-1, 1), N + 1)
+            self._sorted_rows = sorted_pad[:self._P].contiguous()
+            self._perm = D.densify_perm(perm_pad[:self._P], N, self._row_offsets)
         else:
             self._perm, self._sorted_rows = D.lexsort_rows(self._rows, N)
         self._rows = None   # enumeration-order rows are no longer needed
+        self._rows_padded = None
         self._host_cache = {}
         self.reset_filter()
 
@@ -694,10 +732,15 @@ class Dataset:
                 times[offsets[s]:offsets[s + 1]] = t
                 if len(t):
                     series[:, offsets[s]:offsets[s + 1]] = x
+            # sample-major transposed copy for the fused kernel: [S_pad, V rounded up to 32]
+            Vp = (self.n_variables + 31) & ~31
+            series_t = np.zeros((S_pad, Vp), dtype=np.float64)
+            series_t[:, :self.n_variables] = series.T
             self._device_series = dict(
                 times=torch.as_tensor(times, device=D.dev()),
                 t_offsets=torch.as_tensor(offsets, device=D.dev()),
                 series=torch.as_tensor(series, device=D.dev()),
+                series_t=torch.as_tensor(series_t, device=D.dev()),
                 max_T=int(lens.max()) if len(lens) else 1, S=S)
         return self._device_series
 

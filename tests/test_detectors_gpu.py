@@ -14,13 +14,19 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
-def build_gpu_population(d, pop_cfg):
+def build_gpu_population(d, pop_cfg, fused=True):
+    """fused=True: single-launch thread-per-group kernel (N <= 63); False: phase-by-phase kernels."""
     from mitre_b200 import rules as R
     V = d["X"][0].shape[0]
     data = R.Dataset(d["X"], d["T"], d["y"], ["v%d" % i for i in range(V)], d["variable_weights"],
                      d["experiment_start"], d["experiment_end"])
-    pop = R.DiscreteRulePopulation(None, pop_cfg["tmin"], pop_cfg["N_intervals"], tmax=pop_cfg["tmax"],
-                                   data=data)
+    old = R.DiscreteRulePopulation.use_fused
+    R.DiscreteRulePopulation.use_fused = fused
+    try:
+        pop = R.DiscreteRulePopulation(None, pop_cfg["tmin"], pop_cfg["N_intervals"], tmax=pop_cfg["tmax"],
+                                       data=data)
+    finally:
+        R.DiscreteRulePopulation.use_fused = old
     return data, pop
 
 
@@ -57,12 +63,13 @@ def check_population(pop, gold_windows, gold_ok, gold_groups, gold_values, gold_
         assert np.array_equal(pop.truth_table[t], DO.unpack_rows(gold_packed[i:i + 1], N)[0])
 
 
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("name", sorted(MG.DETECTOR_CASES))
-def test_population_vs_reference_golden(name):
+def test_population_vs_reference_golden(name, fused):
     cfg = MG.DETECTOR_CASES[name]
     gold = np.load(os.path.join(GOLD, name + ".npz"))
     d = synthetic.make_series(**cfg["series"])
-    data, pop = build_gpu_population(d, cfg["pop"])
+    data, pop = build_gpu_population(d, cfg["pop"], fused)
     N = int(gold["n_subjects"])
     check_population(pop, gold["windows"], gold["ok_slope"], gold["groups"], gold["values"], gold["order"],
                      gold["sorted_truth_packed"],
@@ -73,12 +80,18 @@ def test_population_vs_reference_golden(name):
     assert np.array_equal(pop.flat_truth, DO.unpack_rows(gold["sorted_truth_packed"], N))
 
 
-@pytest.mark.parametrize("N,V,T,nint", [(3, 2, (2, 4), 2), (33, 5, (3, 20), 6), (100, 3, (5, 9), 4),
-                                        (257, 2, (4, 6), 2)])
-def test_population_vs_oracle(N, V, T, nint):
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("N,V,T,nint", [(2, 3, (2, 3), 1), (3, 2, (2, 4), 2), (8, 40, (3, 6), 3), (9, 33, (3, 6), 3),
+                                        (16, 3, (2, 5), 2), (24, 2, (3, 5), 2), (33, 5, (3, 20), 6),
+                                        (40, 70, (3, 7), 2), (41, 2, (3, 7), 2), (48, 3, (3, 7), 2),
+                                        (56, 2, (3, 7), 2), (63, 3, (3, 7), 2), (64, 3, (3, 7), 2),
+                                        (100, 3, (5, 9), 4), (257, 2, (4, 6), 2)])
+def test_population_vs_oracle(N, V, T, nint, fused):
+    if not fused and N < 64 and N not in (3, 33, 63):
+        pytest.skip("phase-by-phase path covered at a subset of sizes")
     d = synthetic.make_series(N=N, V=V, T=T, span=(0.0, 90.0), seed=N + V, zero_fraction=0.2)
     ref = DO.build_population(d["X"], d["T"], 0.0, 90.0, nint, 1.0, None)
-    data, pop = build_gpu_population(d, dict(tmin=1.0, N_intervals=nint, tmax=None))
+    data, pop = build_gpu_population(d, dict(tmin=1.0, N_intervals=nint, tmax=None), fused)
     o = ref["order"]
     check_population(pop, ref["windows"], ref["ok_slope"],
                      np.stack([ref["group_window"], ref["group_variable"], ref["group_type"]], 1),
@@ -147,3 +160,48 @@ def test_constant_series_slope_divergence_is_confined_to_slope_rows():
     # and the divergence really is there: some slope row differs
     got = pop.packed_truth.cpu().numpy().view(np.uint64)
     assert got.shape != gold["sorted_truth_packed"].shape or not np.array_equal(got, gold["sorted_truth_packed"])
+
+
+def test_all_tied_group_and_sentinel_rows():
+    """A variable that is zero for EVERY subject gives one threshold (0) whose 'below' row is all
+    True -- the row that collides with the fused path's sentinel unless the padded sort uses N+1 bits."""
+    for N in (8, 35, 40):
+        d = synthetic.make_series(N=N, V=3, T=(4, 6), span=(0.0, 20.0), seed=N, zero_fraction=0.0)
+        for x in d["X"]:
+            x[1, :] = 0.0
+        ref = DO.build_population(d["X"], d["T"], 0.0, 20.0, 2, 1.0, None)
+        for fused in (True, False):
+            data, pop = build_gpu_population(d, dict(tmin=1.0, N_intervals=2, tmax=None), fused)
+            o = ref["order"]
+            assert np.array_equal(pop.packed_truth.cpu().numpy().view(np.uint64), DO.pack_rows(ref["truth"][o]))
+            assert np.array_equal(pop._perm_host(), o)
+
+
+def test_long_windows_exceed_the_fused_staging_buffer():
+    """Subjects with more in-window samples than one staging chunk holds take the direct-load path."""
+    d = synthetic.make_series(N=6, V=34, T=(150, 200), span=(0.0, 50.0), seed=77, zero_fraction=0.0)
+    ref = DO.build_population(d["X"], d["T"], 0.0, 50.0, 1, 1.0, None)
+    data, pop = build_gpu_population(d, dict(tmin=1.0, N_intervals=1, tmax=None), True)
+    o = ref["order"]
+    assert np.array_equal(pop.packed_truth.cpu().numpy().view(np.uint64), DO.pack_rows(ref["truth"][o]))
+    is_mean = ref["group_type"] == 1
+    assert np.array_equal(pop._values.cpu().numpy()[is_mean], ref["values"][is_mean])
+
+
+def test_exact_division_selftest():
+    """Window means divide a pairwise sum by a small integer count with a 3-instruction exact
+    sequence instead of the IEEE divide; it must be bit-identical (np.mean parity depends on it)."""
+    from mitre_b200 import device as D
+    rng = np.random.RandomState(0)
+    n = rng.randint(1, 400, size=2000000).astype(np.int32)
+    a = rng.rand(2000000) * 10.0 ** rng.uniform(-12, 3, size=2000000)
+    a[:1000] = 0.0
+    a[1000:2000] = n[1000:2000] * rng.rand(1000)          # near-exact quotients
+    a[2000:3000] = np.nextafter(n[2000:3000].astype(np.float64), 0) * 3.0
+    a[3000:3100] = 1e-300
+    a[3100:3200] = 1e300
+    a[3200:4200] = -a[3200:4200]
+    fast, exact = D.selftest_divide(a, n)
+    fast, exact = fast.cpu().numpy(), exact.cpu().numpy()
+    assert np.array_equal(fast, exact)
+    assert np.array_equal(exact, a / n)
