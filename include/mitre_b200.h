@@ -183,7 +183,8 @@ int mitre_lexsort_rows(void *stream, const uint64_t *rows, int64_t P, int W64, i
  * variable (ld = row stride of the per-sample lists, >= S):
  *   lo, cnt, start int32[W, N]; inv_n, inv_sxx float64[W, N]; idx int32[W, ld]; dt float64[W, ld]
  *   -- first sample / sample count / position in the window's flat sample list; 1/cnt and
- *   1/sum((t - mid) - tbar)^2; the flat list of global sample indices and of centred times.
+ *   1/sum((t - mid) - tbar)^2; the flat list of element offsets (sample index * vstride, must fit
+ *   int32) into series_t and of centred times.
  *
  * mitre_detectors_fused:
  *   series_t     float64[S_pad, vstride]: the series TRANSPOSED (sample-major, variable fastest,
@@ -200,8 +201,9 @@ int mitre_lexsort_rows(void *stream, const uint64_t *rows, int64_t P, int W64, i
  *   next to the IEEE divide, elementwise.
  */
 int mitre_window_lists(void *stream, const double *times, const int32_t *t_offsets, int N,
-                       const double *windows, int W, int64_t ld, int32_t *lo, int32_t *cnt,
-                       int32_t *start, double *inv_n, double *inv_sxx, int32_t *idx, double *dt);
+                       const double *windows, int W, int64_t ld, int64_t vstride, int32_t *lo,
+                       int32_t *cnt, int32_t *start, double *inv_n, double *inv_sxx, int32_t *idx,
+                       double *dt);
 int mitre_detectors_fused(void *stream, const double *series_t, int64_t vstride, int N, int V,
                           const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
                           const double *winv_n, const double *winv_sxx, const int32_t *widx,

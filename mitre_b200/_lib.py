@@ -55,7 +55,7 @@ SIGNATURES = {
     "mitre_lexsort_workspace_bytes": (c_size_t, [c_i64, c_int]),
     "mitre_lexsort_rows": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p, c_size_t]),
-    "mitre_window_lists": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_i64] +
+    "mitre_window_lists": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_i64, c_i64] +
                            [c_void_p] * 7),
     "mitre_detectors_fused": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int] + [c_void_p] * 7 +
                               [c_i64] + [c_void_p] * 4 + [c_int] + [c_void_p] * 4),

@@ -117,14 +117,17 @@ densify_perm_kernel(const int64_t *__restrict__ perm_pad, int64_t P, int L,
 using namespace mitre;
 
 extern "C" int mitre_window_lists(void *stream, const double *times, const int32_t *t_offsets, int N,
-                                  const double *windows, int W, int64_t ld, int32_t *lo, int32_t *cnt,
-                                  int32_t *start, double *inv_n, double *inv_sxx, int32_t *idx, double *dt)
+                                  const double *windows, int W, int64_t ld, int64_t vstride, int32_t *lo,
+                                  int32_t *cnt, int32_t *start, double *inv_n, double *inv_sxx, int32_t *idx,
+                                  double *dt)
 {
-    if (N <= 0 || W < 0 || ld <= 0 || !times || !t_offsets) return MITRE_ERR_INVALID;
+    if (N <= 0 || W < 0 || ld <= 0 || vstride <= 0 || !times || !t_offsets) return MITRE_ERR_INVALID;
+    if (ld * vstride >= 0x7fffffffll) return MITRE_ERR_UNSUPPORTED;   // int32 element offsets
     if (W == 0) return MITRE_OK;
     if (!windows || !lo || !cnt || !start || !inv_n || !inv_sxx || !idx || !dt) return MITRE_ERR_INVALID;
-    window_lists_kernel<<<(W + 127) / 128, 128, 0, as_stream(stream)>>>(times, t_offsets, N, windows, W, ld, lo,
-                                                                        cnt, start, inv_n, inv_sxx, idx, dt);
+    window_lists_kernel<<<(W + 127) / 128, 128, 0, as_stream(stream)>>>(times, t_offsets, N, windows, W, ld,
+                                                                        vstride, lo, cnt, start, inv_n, inv_sxx,
+                                                                        idx, dt);
     MITRE_LAUNCH_CHECK();
     return MITRE_OK;
 }

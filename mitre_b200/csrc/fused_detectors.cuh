@@ -68,7 +68,7 @@ struct NetHolder {
 __device__ __forceinline__ void cmp_exchange(double &x, double &y, int &ix, int &iy)
 {
     const bool sw = x > y;
-    const double lo = sw ? y : x, hi = sw ? x : y;
+    const double lo = fmin(x, y), hi = fmax(x, y);     // DMNMX: values are never NaN here
     const int ilo = sw ? iy : ix, ihi = sw ? ix : iy;
     x = lo; y = hi; ix = ilo; iy = ihi;
 }
@@ -153,13 +153,14 @@ __device__ __forceinline__ double pairwise_sum_col(const Column &x, int n)
 //   lo, cnt [W, N]       first global sample index / number of samples with t0 <= t <= t1
 //   start   [W, N]       position of the subject's first sample in the window's flat sample list
 //   inv_n   [W, N]       1/cnt (correctly rounded)      inv_sxx [W, N]  1 / sum ((t-mid) - tbar)^2
-//   idx     [W, ld]      flat list of the window's global sample indices, subjects concatenated
+//   idx     [W, ld]      flat list of the window's global sample indices TIMES vstride (element
+//                        offsets into series_t), subjects concatenated
 //   dt      [W, ld]      (t - mid) - tbar for the same positions (the variable-independent half of
 //                        the centred least-squares slope; same arithmetic as ols_slope in detectors.cu)
 static __global__ void __launch_bounds__(128)
 window_lists_kernel(const double *__restrict__ times, const int32_t *__restrict__ t_offsets, int N,
-                    const double *__restrict__ windows, int W, int64_t ld, int32_t *__restrict__ lo,
-                    int32_t *__restrict__ cnt, int32_t *__restrict__ start, double *__restrict__ inv_n,
+                    const double *__restrict__ windows, int W, int64_t ld, int64_t vstride,
+                    int32_t *__restrict__ lo, int32_t *__restrict__ cnt, int32_t *__restrict__ start, double *__restrict__ inv_n,
                     double *__restrict__ inv_sxx, int32_t *__restrict__ idx, double *__restrict__ dt)
 {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -184,7 +185,7 @@ window_lists_kernel(const double *__restrict__ times, const int32_t *__restrict_
         for (int j = 0; j < c; ++j) {
             const double d = (times[first + j] - mid) - tb;
             sx = fma(d, d, sx);
-            idx[(int64_t)w * ld + pos + j] = first + j;
+            idx[(int64_t)w * ld + pos + j] = (int32_t)((first + j) * vstride);
             dt[(int64_t)w * ld + pos + j] = d;
         }
         lo[w * N + s] = first;
@@ -210,10 +211,12 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ double div_small_int(double a, double n, double y)
 {
     const double aa = fabs(a);
-    if (!(aa > 1e-280 && aa < 1e280)) return __ddiv_rn(a, n);
     const double q = __dmul_rn(a, y);
     const double r = __fma_rn(-q, n, a);
-    return __fma_rn(r, y, q);
+    const double fast = __fma_rn(r, y, q);
+    if (aa == 0.0) return a;                                   // +-0 / n
+    if (aa > 1e-280 && aa < 1e280) return fast;
+    return __ddiv_rn(a, n);
 }
 
 // numpy pairwise sum of this lane's column x[0..n) staged as x[j * 32] (n <= kFusedCap <= 128)
@@ -248,6 +251,9 @@ __device__ __forceinline__ double pw_sum_staged(const double *x, int n)
     return res;
 }
 
+// launch bound 256 threads => up to 255 registers/thread: the NB values + ids stay in registers
+// (a 128-register bound spills the network and measured slower)
+template <int NB> constexpr int fused_threads() { return 256; }
 constexpr int kFusedCap = 40;   // samples per staging chunk ([cap][32 lanes] doubles = 10 KB per warp)
 
 // Oversized subject (more in-window samples than a staging chunk): straight from global memory.
@@ -266,7 +272,7 @@ static __device__ __noinline__ double subject_value_global(const double *series_
 }
 
 template <int NB>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(fused_threads<NB>(), 1)
 fused_detectors_kernel(const double *__restrict__ series_t, int64_t vstride, int N, int V,
                        const int32_t *__restrict__ wlo, const int32_t *__restrict__ wcnt,
                        const int32_t *__restrict__ wstart, const double *__restrict__ winv_n,
@@ -332,9 +338,14 @@ fused_detectors_kernel(const double *__restrict__ series_t, int64_t vstride, int
                 continue;
             }
             const int p0 = s_start[s];
-#pragma unroll 4
-            for (int j = 0; j < tot; ++j)
-                cp_async8(samples + j * 32 + lane, col + (int64_t)__ldg(idx_w + p0 + j) * vstride);
+            for (int j0 = 0; j0 < tot; j0 += 32) {
+                const int mine = (j0 + lane < tot) ? __ldg(idx_w + p0 + j0 + lane) : 0;   // coalesced
+                const int nn = min(32, tot - j0);
+                double *dst = samples + j0 * 32 + lane;
+#pragma unroll 8
+                for (int j = 0; j < nn; ++j)
+                    cp_async8(dst + j * 32, col + __shfl_sync(0xffffffffu, mine, j));
+            }
             cp_async_wait_all();
             __syncwarp();
             for (int q = s; q < e; ++q) {
@@ -384,10 +395,9 @@ fused_detectors_kernel(const double *__restrict__ series_t, int64_t vstride, int
             for (int k = 0; k < NB - 1; ++k) {
                 if (k < N - 1) {
                     const double m = __dmul_rn(0.5, __dadd_rn(val[k], val[k + 1]));
-                    if (k == 0 || m != prev) {
-                        if (live) tg[kcount] = m;
-                        ++kcount;
-                    }
+                    const bool u = (k == 0) || (m != prev);
+                    if (u && live) tg[kcount] = m;
+                    kcount += u;
                     prev = m;
                 }
             }
@@ -413,11 +423,9 @@ fused_detectors_kernel(const double *__restrict__ series_t, int64_t vstride, int
                     const double m = __dmul_rn(0.5, __dadd_rn(val[k], val[k + 1]));
                     bool uniq = true;
                     if (k > 0) uniq = m != __dmul_rn(0.5, __dadd_rn(val[k - 1], val[k]));
-                    if (uniq) {
-                        const uint64_t above = (m == val[k + 1]) ? Tn : acc;
-                        if (live) rg[pos] = make_ulonglong2(above, ~above & valid);
-                        --pos;
-                    }
+                    const uint64_t above = (m == val[k + 1]) ? Tn : acc;
+                    if (uniq && live) rg[pos] = make_ulonglong2(above, ~above & valid);
+                    pos -= uniq;
                     Tn = (val[k] == val[k + 1]) ? Tn : acc;
                     acc |= 1ull << (63 - id[k]);
                 }
@@ -439,7 +447,7 @@ static int launch_fused_impl(cudaStream_t st, const double *series_t, int64_t vs
     const int vs_stride = N | 1;
     const size_t per_warp = ((size_t)kFusedCap * 32 + (size_t)32 * vs_stride + 3 * NB) * sizeof(double);
     int warps = (int)((smem_optin() - 1024) / per_warp);
-    if (warps > 8) warps = 8;
+    if (warps > fused_threads<NB>() / 32) warps = fused_threads<NB>() / 32;
     if (warps < 1) return MITRE_ERR_UNSUPPORTED;
     const size_t smem = per_warp * warps;
     auto kern = fused_detectors_kernel<NB>;

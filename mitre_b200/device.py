@@ -224,7 +224,7 @@ def detector_rows(values, thresholds, K, row_offsets, P):
     return packed
 
 
-def window_lists(times, t_offsets, windows):
+def window_lists(times, t_offsets, windows, vstride):
     """Variable-independent per-window tables for the fused detector kernel (mitre_window_lists)."""
     N = t_offsets.shape[0] - 1
     W = windows.shape[0]
@@ -236,7 +236,8 @@ def window_lists(times, t_offsets, windows):
              inv_sxx=torch.empty((W, N), dtype=F64, device=dev()),
              idx=torch.zeros((W, ld), dtype=I32, device=dev()),
              dt=torch.zeros((W, ld), dtype=F64, device=dev()), ld=ld)
-    check(lib().mitre_window_lists(_stream(), _p(times), _p(t_offsets), N, _p(windows), W, ld, _p(t['lo']),
+    check(lib().mitre_window_lists(_stream(), _p(times), _p(t_offsets), N, _p(windows), W, ld, int(vstride),
+                                   _p(t['lo']),
                                    _p(t['cnt']), _p(t['start']), _p(t['inv_n']), _p(t['inv_sxx']),
                                    _p(t['idx']), _p(t['dt'])), "mitre_window_lists")
     return t

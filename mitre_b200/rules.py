@@ -355,9 +355,11 @@ class DiscreteRulePopulation:
         N = self.data.n_subjects
         self._fused = None
         self._fused_args = None
-        if self.use_fused and 2 <= N <= 63:
+        if (self.use_fused and 2 <= N <= 63 and
+                ds['series_t'].shape[0] * ds['series_t'].shape[1] < 2 ** 31 - 1):
             # one launch: values + thresholds + K + padded truth rows (fused_detectors.cuh)
-            lists = D.window_lists(ds['times'], ds['t_offsets'], self._d_windows)
+            lists = D.window_lists(ds['times'], ds['t_offsets'], self._d_windows,
+                                   ds['series_t'].shape[1])
             tw, tt = [], []
             for w in range(W):
                 if ok[w]:
