@@ -83,6 +83,20 @@ int mitre_score_all(void *stream, const uint64_t *packed_truth, int64_t P, int W
                     size_t workspace_bytes, double *out, int32_t *status);
 
 /*
+ * Same sweep, additionally reducing (max, sum exp(w - max)) of w = out (+ log_prior, float64[P] or
+ * NULL) into stats[2] in the scoring kernel's epilogue (N <= 64; for N > 64 a second pass over
+ * `out` using stats_workspace of mitre_draw_workspace_bytes(P) bytes).  log-sum-exp =
+ * stats[0] + log(stats[1]): what the add/remove moves need (logit_rules.py:959, 1064) and the
+ * 16-byte pair ranks exchange in the two-stage multi-GPU draw.
+ */
+int mitre_score_all_stats(void *stream, const uint64_t *packed_truth, int64_t P, int W64,
+                          const uint64_t *mask, const double *X, const double *omega,
+                          const double *kappa, int N, int p, double sigma2, void *workspace,
+                          size_t workspace_bytes, double *out, int32_t *status,
+                          const double *log_prior, double *stats, void *stats_workspace,
+                          size_t stats_workspace_bytes);
+
+/*
  * Drop-in compatibility form with the reference's exact arguments, all HOST pointers
  * (efficient_likelihoods.pyx:15-21): X[N,p], omega[N], response[N] (= kappa/omega),
  * truth float64[P,N], prior_coefficient_variance; writes out_host[P].  Synchronous: stages the

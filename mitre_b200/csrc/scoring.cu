@@ -29,7 +29,107 @@ namespace mitre {
 // workspace layout (doubles): header[8] then q[N][EP]
 //   header[0] = base log-likelihood C0, [1] = 1/sigma2, [2] = sigma2
 constexpr int kHdr = 8;
+constexpr int kMaxStatCtas = 2048;   // per-CTA (max, sum-exp) partials live at the end of the workspace
 __host__ __device__ inline int ep_for(int p) { return (p + 2 + 1) & ~1; }  // even, >= p+2
+
+// ---------------------------------------------------------------------------------------------
+// Table-driven log / reciprocal / exp for the per-candidate epilogue.  The stock fp64 log and
+// divide cost ~70 instructions per candidate; here s = 2^e * m, m in [1,2) is reduced against
+// c_i = 1 + (i + 1/2)/128 (i = top 7 mantissa bits): r = m/c_i - 1, |r| <= 2^-8, and
+//   log s = e ln2 + log c_i + log1p(r)          (degree-6 series, truncation 2e-18)
+//   1/s   = 2^-e (1/c_i) (1-r)(1+r^2)(1+r^4)    (= sum_{k<8} (-r)^k, truncation 5e-20)
+// Absolute error ~3e-16 in the log, ~4 ulp in the reciprocal: far inside the 1e-9 contract.
+// ---------------------------------------------------------------------------------------------
+constexpr int kLogTab = 128;
+constexpr int kExpTab = 64;
+
+__device__ __forceinline__ void build_math_tables(double2 *logtab, double *exptab)
+{
+    for (int i = threadIdx.x; i < kLogTab; i += blockDim.x) {
+        const double c = 1.0 + (i + 0.5) / kLogTab;
+        logtab[i] = make_double2(1.0 / c, log(c));
+    }
+    for (int j = threadIdx.x; j < kExpTab; j += blockDim.x) exptab[j] = exp2((double)j / kExpTab);
+}
+
+// s must be a positive normal double.  half_rcp = 1/(2s).
+__device__ __forceinline__ void log_and_half_rcp(double s, const double2 *__restrict__ logtab, double &log_s,
+                                                 double &half_rcp)
+{
+    const int hi = __double2hiint(s), lo = __double2loint(s);
+    const int e = (hi >> 20) - 1023;
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+    const double2 t = logtab[(hi >> 13) & (kLogTab - 1)];
+    const double r = fma(m, t.x, -1.0);
+    const double r2 = r * r;
+    double p = fma(r, -1.0 / 6.0, 0.2);
+    p = fma(r, p, -0.25);
+    p = fma(r, p, 1.0 / 3.0);
+    p = fma(r, p, -0.5);
+    const double l1p = fma(r2, p, r);
+    log_s = fma((double)e, 0.69314718055994530942, t.y) + l1p;
+    const double r4 = r2 * r2;
+    const double q = ((1.0 - r) * (1.0 + r2)) * (1.0 + r4);
+    half_rcp = (t.x * q) * __hiloint2double((1022 - e) << 20, 0);
+}
+
+// exp(x) for x <= 0 (returns 0 below the double range); 2^(j/64) table + degree-5 series.
+__device__ __forceinline__ double exp_nonpos(double x, const double *__restrict__ exptab)
+{
+    if (!(x > -700.0)) return 0.0;
+    const double t = fma(x, 92.332482616893656877, 6755399441055744.0);   // 64/ln2, 1.5*2^52
+    const int n = __double2loint(t);
+    const double nd = t - 6755399441055744.0;
+    double r = fma(nd, -0.010830424667801708, x);                          // ln2/64 hi (29 bits)
+    r = fma(nd, -2.8447437476627285e-11, r);                               // ln2/64 lo
+    double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    p = fma(r, p, 1.0 / 6.0);
+    p = fma(r, p, 0.5);
+    p = fma(r * r, p, r);                                                   // exp(r) - 1
+    const double b = exptab[n & (kExpTab - 1)];
+    const double v = fma(b, p, b);
+    return __hiloint2double(__double2hiint(v) + ((n >> 6) << 20), __double2loint(v));
+}
+
+// (max, sum exp(w - max)) pairs; empty = (-inf, 0)
+struct MaxSum {
+    double m, s;
+};
+__device__ __forceinline__ MaxSum ms_merge(MaxSum x, MaxSum y)
+{
+    if (y.s == 0.0) return x;
+    if (x.s == 0.0) return y;
+    MaxSum r;
+    if (x.m >= y.m) { r.m = x.m; r.s = x.s + y.s * exp(y.m - x.m); }
+    else { r.m = y.m; r.s = y.s + x.s * exp(x.m - y.m); }
+    return r;
+}
+__device__ __forceinline__ void ms_push(MaxSum &a, double w, const double *__restrict__ exptab)
+{
+    if (w == -INFINITY) return;
+    const double e = exp_nonpos(-fabs(w - a.m), exptab);
+    if (w > a.m) { a.s = fma(a.s, e, 1.0); a.m = w; }
+    else a.s += e;
+}
+
+__global__ void __launch_bounds__(256)
+score_stats_final_kernel(const double *__restrict__ part, int nparts, double *__restrict__ stats)
+{
+    __shared__ double sm[256], ss[256];
+    MaxSum acc = {-INFINITY, 0.0};
+    for (int i = threadIdx.x; i < nparts; i += 256) acc = ms_merge(acc, MaxSum{part[2 * i], part[2 * i + 1]});
+    sm[threadIdx.x] = acc.m; ss[threadIdx.x] = acc.s;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            const MaxSum x = ms_merge(MaxSum{sm[threadIdx.x], ss[threadIdx.x]},
+                                      MaxSum{sm[threadIdx.x + s], ss[threadIdx.x + s]});
+            sm[threadIdx.x] = x.m; ss[threadIdx.x] = x.s;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { stats[0] = sm[0]; stats[1] = ss[0]; }
+}
 
 // ---------------------------------------------------------------------------------------------
 // Base system for one design matrix.  Called by every thread of a CTA; smem scratch:
@@ -116,6 +216,7 @@ score_setup_kernel(const double *__restrict__ X, const double *__restrict__ omeg
         ws[0] = C0;
         ws[1] = 1.0 / sigma2;
         ws[2] = sigma2;
+        ws[3] = C0 - 0.5 * log(sigma2);   // base log-likelihood with the -1/2 log sigma2 of the new column folded in
         if (!s_ok && status) atomicOr(reinterpret_cast<unsigned int *>(status), MITRE_STATUS_BASE_NOT_PD);
     }
     double *q = ws + kHdr;
@@ -160,15 +261,19 @@ __device__ __forceinline__ double finish_candidate(const double (&acc)[EP], doub
 // N <= 64: thread per candidate, subset-sum table per chunk of CB subjects in shared memory.
 // Table entry (chunk c, pattern t): sum of q_i over subjects i = c*CB + j whose pattern bit
 // (CB-1-j) is set, EP doubles, added in ascending subject order.
+// STATS: additionally accumulate (max, sum exp(w - max)) of w = loglik (+ log_prior) per CTA.
 // ---------------------------------------------------------------------------------------------
-template <int EP, int CB>
+template <int EP, int CB, bool STATS>
 __global__ void __launch_bounds__(256)
 score_w1_kernel(const uint64_t *__restrict__ rows, int64_t P, const double *__restrict__ ws, int N,
-                double *__restrict__ out, int32_t *status)
+                double *__restrict__ out, int32_t *status, const double *__restrict__ log_prior,
+                double *__restrict__ stat_partials)
 {
     extern __shared__ __align__(16) double lut[];
     constexpr int PAT = 1 << CB;
     const int nchunks = (N + CB - 1) / CB;
+    double2 *logtab = reinterpret_cast<double2 *>(lut + (size_t)nchunks * PAT * EP);
+    double *exptab = reinterpret_cast<double *>(logtab + kLogTab);
     const double *q = ws + kHdr;
     for (int idx = threadIdx.x; idx < nchunks * PAT * EP; idx += blockDim.x) {
         const int e = idx % EP;
@@ -182,9 +287,11 @@ score_w1_kernel(const uint64_t *__restrict__ rows, int64_t P, const double *__re
         }
         lut[idx] = acc;
     }
+    build_math_tables(logtab, exptab);
     __syncthreads();
-    const double C0 = ws[0], inv_s2 = ws[1], s2 = ws[2];
+    const double inv_s2 = ws[1], C1 = ws[3];
     bool bad = false;
+    MaxSum run = {-INFINITY, 0.0};
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < P; k += stride) {
         const uint64_t r = ld_stream_u64(rows + k);
@@ -209,9 +316,34 @@ score_w1_kernel(const uint64_t *__restrict__ rows, int64_t P, const double *__re
                 acc[2 * j + 1] += v.y;
             }
         }
-        st_stream_f64(out + k, finish_candidate<EP>(acc, C0, inv_s2, s2, bad));
+        double ww = 0.0;
+#pragma unroll
+        for (int e = 2; e < EP; ++e) ww = fma(acc[e], acc[e], ww);
+        const double sc = (inv_s2 + acc[0]) - ww;          // Schur complement
+        const bool ok = sc > 1e-300 && sc < 1e300;
+        bad = bad || !ok;
+        double log_s, half_rcp;
+        log_and_half_rcp(ok ? sc : 1.0, logtab, log_s, half_rcp);
+        double val = fma(-0.5, log_s, C1) + (acc[1] * acc[1]) * half_rcp;
+        if (!ok) val = nan("");
+        st_stream_f64(out + k, val);
+        if (STATS) ms_push(run, log_prior ? val + log_prior[k] : val, exptab);
     }
     if (bad && status) atomicOr(reinterpret_cast<unsigned int *>(status), MITRE_STATUS_BAD_SCHUR);
+    if (STATS) {
+        __shared__ double sm[256], ss[256];
+        sm[threadIdx.x] = run.m; ss[threadIdx.x] = run.s;
+        __syncthreads();
+        for (int s = 128; s > 0; s >>= 1) {
+            if (threadIdx.x < s) {
+                const MaxSum x = ms_merge(MaxSum{sm[threadIdx.x], ss[threadIdx.x]},
+                                          MaxSum{sm[threadIdx.x + s], ss[threadIdx.x + s]});
+                sm[threadIdx.x] = x.m; ss[threadIdx.x] = x.s;
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) { stat_partials[2 * blockIdx.x] = sm[0]; stat_partials[2 * blockIdx.x + 1] = ss[0]; }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -379,22 +511,37 @@ mc_logpdf_kernel(const double *__restrict__ x, const double *__restrict__ cov, i
 // ---- launch helpers --------------------------------------------------------------------------
 
 template <int EP, int CB>
-static int launch_w1(cudaStream_t st, const uint64_t *rows, int64_t P, const double *ws, int N,
-                     double *out, int32_t *status)
+static int launch_w1(cudaStream_t st, const uint64_t *rows, int64_t P, double *ws, int N, double *out,
+                     int32_t *status, const double *log_prior, double *stats)
 {
     const int nchunks = (N + CB - 1) / CB;
-    const size_t smem = (size_t)nchunks * (1 << CB) * EP * sizeof(double);
-    auto kern = score_w1_kernel<EP, CB>;
-    MITRE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = (size_t)nchunks * (1 << CB) * EP * sizeof(double) + kLogTab * sizeof(double2) +
+                        kExpTab * sizeof(double);
     int per_sm = 1;
-    MITRE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
-    if (per_sm < 1) return MITRE_ERR_UNSUPPORTED;
-    int64_t blocks = (int64_t)sm_count() * per_sm;
-    const int64_t need = ceil_div64(P, 256);
-    if (need < blocks) blocks = need;
-    if (blocks < 1) blocks = 1;
-    kern<<<(unsigned)blocks, 256, smem, st>>>(rows, P, ws, N, out, status);
-    MITRE_LAUNCH_CHECK();
+    int64_t blocks = 0;
+    double *partials = ws + kHdr + (size_t)N * EP;
+#define MITRE_W1_LAUNCH(STATSV)                                                                          \
+    {                                                                                                    \
+        auto kern = score_w1_kernel<EP, CB, STATSV>;                                                     \
+        MITRE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        MITRE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));         \
+        if (per_sm < 1) return MITRE_ERR_UNSUPPORTED;                                                    \
+        blocks = (int64_t)sm_count() * per_sm;                                                           \
+        const int64_t need = ceil_div64(P, 256);                                                         \
+        if (need < blocks) blocks = need;                                                                \
+        if (blocks < 1) blocks = 1;                                                                      \
+        if (blocks > kMaxStatCtas) blocks = kMaxStatCtas;                                                \
+        kern<<<(unsigned)blocks, 256, smem, st>>>(rows, P, ws, N, out, status, log_prior, partials);     \
+        MITRE_LAUNCH_CHECK();                                                                            \
+    }
+    if (stats) {
+        MITRE_W1_LAUNCH(true)
+        score_stats_final_kernel<<<1, 256, 0, st>>>(partials, (int)blocks, stats);
+        MITRE_LAUNCH_CHECK();
+    } else {
+        MITRE_W1_LAUNCH(false)
+    }
+#undef MITRE_W1_LAUNCH
     return MITRE_OK;
 }
 
@@ -415,15 +562,17 @@ static int launch_wide(cudaStream_t st, const uint64_t *rows, int64_t P, int W64
 }
 
 template <int EP>
-static int launch_ep(cudaStream_t st, const uint64_t *rows, int64_t P, int W64, const double *ws, int N,
-                     double *out, int32_t *status)
+static int launch_ep(cudaStream_t st, const uint64_t *rows, int64_t P, int W64, double *ws, int N, double *out,
+                     int32_t *status, const double *log_prior, double *stats, bool *stats_done)
 {
     if (W64 == 1) {
+        *stats_done = true;
         const size_t lut8 = (size_t)((N + 7) / 8) * 256 * EP * sizeof(double);
         // keep >= 2 CTAs per SM where the byte table allows it, else fall to nibble tables
-        if (lut8 <= 100 * 1024) return launch_w1<EP, 8>(st, rows, P, ws, N, out, status);
-        return launch_w1<EP, 4>(st, rows, P, ws, N, out, status);
+        if (lut8 <= 100 * 1024) return launch_w1<EP, 8>(st, rows, P, ws, N, out, status, log_prior, stats);
+        return launch_w1<EP, 4>(st, rows, P, ws, N, out, status, log_prior, stats);
     }
+    *stats_done = false;
     return launch_wide<EP>(st, rows, P, W64, ws, N, out, status);
 }
 
@@ -434,13 +583,19 @@ using namespace mitre;
 extern "C" size_t mitre_score_workspace_bytes(int N, int p)
 {
     if (N <= 0 || p <= 0 || p > MITRE_MAX_P) return 0;
-    return sizeof(double) * ((size_t)kHdr + (size_t)N * ep_for(p));
+    return sizeof(double) * ((size_t)kHdr + (size_t)N * ep_for(p) + 2 * (size_t)kMaxStatCtas);
 }
 
-extern "C" int mitre_score_all(void *stream, const uint64_t *packed_truth, int64_t P, int W64,
-                               const uint64_t *mask, const double *X, const double *omega,
-                               const double *kappa, int N, int p, double sigma2, void *workspace,
-                               size_t workspace_bytes, double *out, int32_t *status)
+extern "C" int mitre_weight_stats(void *stream, const double *a, const double *b, int64_t P, double *stats,
+                                  void *workspace, size_t workspace_bytes);
+extern "C" size_t mitre_draw_workspace_bytes(int64_t P);
+
+extern "C" int mitre_score_all_stats(void *stream, const uint64_t *packed_truth, int64_t P, int W64,
+                                     const uint64_t *mask, const double *X, const double *omega,
+                                     const double *kappa, int N, int p, double sigma2, void *workspace,
+                                     size_t workspace_bytes, double *out, int32_t *status,
+                                     const double *log_prior, double *stats, void *stats_workspace,
+                                     size_t stats_workspace_bytes)
 {
     if (P < 0 || N <= 0 || p <= 0 || !X || !omega || !kappa || !workspace) return MITRE_ERR_INVALID;
     if (P > 0 && (!packed_truth || !out)) return MITRE_ERR_INVALID;
@@ -448,15 +603,19 @@ extern "C" int mitre_score_all(void *stream, const uint64_t *packed_truth, int64
     if (p > MITRE_MAX_P) return MITRE_ERR_UNSUPPORTED;
     if (!(sigma2 > 0.0)) return MITRE_ERR_INVALID;
     if (workspace_bytes < mitre_score_workspace_bytes(N, p)) return MITRE_ERR_WORKSPACE;
+    if (log_prior && !stats) return MITRE_ERR_INVALID;
     cudaStream_t st = as_stream(stream);
     double *ws = static_cast<double *>(workspace);
     score_setup_kernel<<<1, 256, 0, st>>>(X, omega, kappa, mask, N, p, sigma2, ws, status);
     MITRE_LAUNCH_CHECK();
     if (P == 0) return MITRE_OK;
+    bool stats_done = false;
+    int rc = MITRE_ERR_UNSUPPORTED;
     switch (ep_for(p)) {
-#define MITRE_EP_CASE(E) \
-    case E:              \
-        return launch_ep<E>(st, packed_truth, P, W64, ws, N, out, status);
+#define MITRE_EP_CASE(E)                                                                                  \
+    case E:                                                                                               \
+        rc = launch_ep<E>(st, packed_truth, P, W64, ws, N, out, status, log_prior, stats, &stats_done);   \
+        break;
         MITRE_EP_CASE(4)
         MITRE_EP_CASE(6)
         MITRE_EP_CASE(8)
@@ -471,7 +630,22 @@ extern "C" int mitre_score_all(void *stream, const uint64_t *packed_truth, int64
         MITRE_EP_CASE(26)
 #undef MITRE_EP_CASE
     }
-    return MITRE_ERR_UNSUPPORTED;
+    if (rc != MITRE_OK) return rc;
+    if (stats && !stats_done) {
+        // wide path: separate reduction over the scored slice
+        if (!stats_workspace || stats_workspace_bytes < mitre_draw_workspace_bytes(P)) return MITRE_ERR_WORKSPACE;
+        return mitre_weight_stats(stream, out, log_prior, P, stats, stats_workspace, stats_workspace_bytes);
+    }
+    return MITRE_OK;
+}
+
+extern "C" int mitre_score_all(void *stream, const uint64_t *packed_truth, int64_t P, int W64,
+                               const uint64_t *mask, const double *X, const double *omega,
+                               const double *kappa, int N, int p, double sigma2, void *workspace,
+                               size_t workspace_bytes, double *out, int32_t *status)
+{
+    return mitre_score_all_stats(stream, packed_truth, P, W64, mask, X, omega, kappa, N, p, sigma2, workspace,
+                                 workspace_bytes, out, status, nullptr, nullptr, nullptr, 0);
 }
 
 extern "C" int mitre_likelihood_z_given_X_batch(void *stream, const double *Xs, const int32_t *p_b,

@@ -135,6 +135,30 @@ def score_all(packed, N, X, omega, kappa, sigma2, mask=None, buffers=None, out=N
     return out, buffers.status
 
 
+def score_all_stats(packed, N, X, omega, kappa, sigma2, mask=None, buffers=None, out=None, log_prior=None,
+                    draw_buffers=None):
+    """score_all + (max, sum exp(w - max)) of w = out (+ log_prior) in the same launch.
+    Returns (out, status, stats float64[2])."""
+    P, W64 = packed.shape
+    X = _dev_f64(X)
+    omega = _dev_f64(omega)
+    kappa = _dev_f64(kappa)
+    p = X.shape[1]
+    if buffers is None:
+        buffers = ScoreBuffers(P, N, p)
+    if out is None:
+        out = buffers.out if buffers.out.shape[0] == P else torch.empty(P, dtype=F64, device=dev())
+    if draw_buffers is None:
+        draw_buffers = DrawBuffers(max(P, 1))
+    ws = buffers.workspace
+    check(lib().mitre_score_all_stats(_stream(), _p(packed), P, W64, _p(mask), _p(X), _p(omega), _p(kappa),
+                                      int(N), int(p), float(sigma2), _p(ws), ws.numel(), _p(out),
+                                      _p(buffers.status), _p(log_prior), _p(draw_buffers.stats),
+                                      _p(draw_buffers.workspace), draw_buffers.workspace.numel()),
+          "mitre_score_all_stats")
+    return out, buffers.status, draw_buffers.stats
+
+
 def raise_on_status(status):
     """Synchronises; maps device status flags to numpy's LinAlgError like the reference
     (efficient_likelihoods.pyx:42 -> np.linalg.cholesky)."""

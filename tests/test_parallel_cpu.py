@@ -1,0 +1,115 @@
+"""Host logic of the multi-GPU path under gloo, world_size 2, on CPU: shard
+bounds, the uneven all-gather of log-likelihood slices, the two-stage (max, sum-exp) draw."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from mitre_b200 import parallel as PL
+
+
+def free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def test_shard_bounds_cover_and_balance():
+    for P in [0, 1, 7, 64, 1000003]:
+        for ws in [1, 2, 3, 8]:
+            b = PL.all_shard_bounds(P, ws)
+            assert b[0][0] == 0 and b[-1][1] == P
+            assert all(b[i][1] == b[i + 1][0] for i in range(ws - 1))
+            sizes = [y - x for x, y in b]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_chains_for_rank_seeds():
+    got = sorted(sum([PL.chains_for_rank(64, 8, r, base_seed=100) for r in range(8)], []))
+    assert got == [(i, 100 + i) for i in range(64)]
+    assert len(PL.chains_for_rank(64, 8, 3)) == 8
+
+
+def test_owner_of_marker_matches_flat_cumsum():
+    rng = np.random.RandomState(0)
+    for trial in range(200):
+        ws = rng.randint(1, 6)
+        sizes = rng.randint(1, 50, size=ws)
+        w = [rng.normal(-80, 4, size=n) for n in sizes]
+        stats = np.array([[x.max(), np.exp(x - x.max()).sum()] for x in w])
+        flat = np.concatenate(w)
+        u = rng.rand()
+        c = np.cumsum(np.exp(flat - flat.max()))
+        want = int(np.sum(c < u * c[-1]))
+        owner, u_local, log_total = PL.owner_of_marker(stats, u)
+        starts = np.concatenate([[0], np.cumsum(sizes)])
+        cl = np.cumsum(np.exp(w[owner] - w[owner].max()))
+        got = int(starts[owner] + np.sum(cl < u_local * cl[-1]))
+        assert abs(got - want) <= 1
+        assert abs(log_total - (flat.max() + np.log(np.exp(flat - flat.max()).sum()))) < 1e-10
+
+
+def test_owner_of_marker_edge_cases():
+    # empty / all -inf ranks are skipped; the reference's raw-exp underflow gives index 0
+    stats = np.array([[-np.inf, 0.0], [-3.0, 2.0], [-np.inf, 0.0]])
+    owner, u_local, _ = PL.owner_of_marker(stats, 0.4)
+    assert owner == 1 and 0.0 <= u_local < 1.0
+    owner, u_local, lt = PL.owner_of_marker(np.array([[-4000.0, 5.0], [-4100.0, 7.0]]), 0.7, stabilise=False)
+    assert owner == 0 and lt == -np.inf
+    owner, u_local, lt = PL.owner_of_marker(np.array([[-4000.0, 5.0], [-4100.0, 7.0]]), 0.7, stabilise=True)
+    assert owner == 0 and np.isfinite(lt)
+
+
+def _worker(rank, ws, port, P, seed, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    try:
+        rng = np.random.RandomState(seed)
+        full = rng.normal(-90, 5, size=P)
+        a, b = PL.shard_bounds(P, ws, rank)
+        local = torch.as_tensor(full[a:b].copy())
+        got = PL.allgather_loglik(local, P)
+        ok_gather = bool(np.array_equal(got.numpy(), full))
+        results = []
+        for u in [0.0, 0.13, 0.5, 0.77, 0.999]:
+            x = full[a:b]
+            stats = torch.tensor([x.max(), np.exp(x - x.max()).sum()], dtype=torch.float64)
+
+            def local_draw(u_local, x=x):
+                c = np.cumsum(np.exp(x - x.max()))
+                return int(np.sum(c < u_local * c[-1]))
+            idx, log_total = PL.two_stage_draw(stats, local_draw, a, u)
+            c = np.cumsum(np.exp(full - full.max()))
+            want = int(np.sum(c < u * c[-1]))
+            results.append((idx, want, log_total))
+        q.put((rank, ok_gather, results))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("P", [7, 1000, 4097])
+def test_gloo_world2_gather_and_two_stage_draw(P):
+    ws = 2
+    port = free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, ws, port, P, 11, q)) for r in range(ws)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=120) for _ in range(ws)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    by_rank = {r: (g, res) for r, g, res in out}
+    assert by_rank[0][0] and by_rank[1][0]
+    assert [x[0] for x in by_rank[0][1]] == [x[0] for x in by_rank[1][1]]       # every rank agrees
+    for idx, want, log_total in by_rank[0][1]:
+        assert abs(idx - want) <= 1
+        assert np.isfinite(log_total)

@@ -182,3 +182,31 @@ def test_draw_index_and_stats():
     a = torch.full((5000,), -4000.0, dtype=torch.float64, device=D.dev())
     assert int(D.draw_index(a, None, 0.7).item()) == 0
     assert 0 < int(D.draw_index(a, None, 0.7, stabilise=True).item()) < 5000
+
+
+def test_score_all_stats_fused_logsumexp():
+    """mitre_score_all_stats: (max, sum-exp) of loglik (+ log prior) reduced inside the scoring
+    kernel must match a float64 log-sum-exp of the same vector, for N <= 64 and the wide path."""
+    import torch
+    from mitre_b200 import device as D
+    for N, p, P in [(35, 4, 300001), (64, 2, 5000), (130, 3, 700), (35, 4, 1)]:
+        c = MG.scoring_inputs(seed=900 + N, N=N, p=p, P=P)
+        packed = D.pack_rows(c["truth"])
+        mask = torch.as_tensor(D.pack_mask(c["mask"]), device=D.dev())
+        rng = np.random.RandomState(1)
+        prior = rng.normal(-12, 2, size=P)
+        prior[::7] = -np.inf if P > 10 else prior[::7]
+        dprior = torch.as_tensor(prior, device=D.dev())
+        out, status, stats = D.score_all_stats(packed, N, c["X"], c["omega"], c["y"] - 0.5, 100.0, mask=mask,
+                                               log_prior=dprior)
+        ll = out.cpu().numpy()
+        D.raise_on_status(status)
+        st = stats.cpu().numpy()
+        w = ll + prior
+        want = float(torch.logsumexp(torch.as_tensor(w), 0))
+        assert abs(st[0] + np.log(st[1]) - want) < 1e-11 * max(1.0, abs(want))
+        assert st[0] == w.max()
+        out2, status2, stats2 = D.score_all_stats(packed, N, c["X"], c["omega"], c["y"] - 0.5, 100.0, mask=mask)
+        st2 = stats2.cpu().numpy()
+        want2 = float(torch.logsumexp(torch.as_tensor(ll), 0))
+        assert abs(st2[0] + np.log(st2[1]) - want2) < 1e-11 * abs(want2)
