@@ -75,8 +75,12 @@ int mitre_unpack_rows_u8(void *stream, const uint64_t *packed, int64_t P, int N,
  * the rule has no other primitive).  `workspace` must hold mitre_score_workspace_bytes(N, p)
  * bytes and stay untouched until the launch has run.  `status` (device int32, caller-zeroed)
  * receives MITRE_STATUS_* flags.
+ * Kernel selection (N <= 64): tables of subset sums -- 8-subject tables in shared memory for small
+ * candidate sets, 16-subject tables in L2 for P >= 4 Mi rows (mitre_set_large_table_min_rows moves
+ * that switch point; a tuning / test hook).
  */
 size_t mitre_score_workspace_bytes(int N, int p);
+int mitre_set_large_table_min_rows(int64_t rows);
 int mitre_score_all(void *stream, const uint64_t *packed_truth, int64_t P, int W64,
                     const uint64_t *mask, const double *X, const double *omega,
                     const double *kappa, int N, int p, double sigma2, void *workspace,

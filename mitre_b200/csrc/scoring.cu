@@ -347,6 +347,266 @@ score_w1_kernel(const uint64_t *__restrict__ rows, int64_t P, const double *__re
 }
 
 // ---------------------------------------------------------------------------------------------
+// N <= 64, byte tables, FOUR consecutive candidates per thread.  The table is lexsorted
+// (rules.py:439-462), so neighbouring rows share their leading bytes almost always: the subset
+// sums of the bytes common to the four rows are fetched and added once (prefix), only the
+// trailing bytes are looked up per row.  That cuts shared-memory traffic -- the binding resource
+// of the one-candidate-per-thread kernel (240 B of table per candidate at 128 B/clk/SM) -- by
+// ~1.8x and gives every thread four independent dependency chains.
+// Requires rows / out 32-byte aligned (checked by the launcher).
+// ---------------------------------------------------------------------------------------------
+template <int EP>
+__device__ __forceinline__ void lut_add(double (&acc)[EP], const double *__restrict__ entry)
+{
+    const double2 *e = reinterpret_cast<const double2 *>(entry);
+#pragma unroll
+    for (int j = 0; j < EP / 2; ++j) {
+        const double2 v = e[j];
+        acc[2 * j] += v.x;
+        acc[2 * j + 1] += v.y;
+    }
+}
+
+template <int EP>
+__device__ __forceinline__ double finish_tab(const double (&acc)[EP], double inv_s2, double C1,
+                                             const double2 *__restrict__ logtab, bool &bad)
+{
+    double ww = 0.0;
+#pragma unroll
+    for (int e = 2; e < EP; ++e) ww = fma(acc[e], acc[e], ww);
+    const double sc = (inv_s2 + acc[0]) - ww;          // Schur complement
+    const bool ok = sc > 1e-300 && sc < 1e300;
+    bad = bad || !ok;
+    double log_s, half_rcp;
+    log_and_half_rcp(ok ? sc : 1.0, logtab, log_s, half_rcp);
+    const double val = fma(-0.5, log_s, C1) + (acc[1] * acc[1]) * half_rcp;
+    return ok ? val : nan("");
+}
+
+template <int EP, bool STATS>
+__global__ void __launch_bounds__(256)
+score_w1r4_kernel(const uint64_t *__restrict__ rows, int64_t P, const double *__restrict__ ws, int N,
+                  double *__restrict__ out, int32_t *status, const double *__restrict__ log_prior,
+                  double *__restrict__ stat_partials)
+{
+    extern __shared__ __align__(16) double lut[];
+    constexpr int CB = 8, PAT = 256;
+    const int nchunks = (N + CB - 1) / CB;
+    double2 *logtab = reinterpret_cast<double2 *>(lut + (size_t)nchunks * PAT * EP);
+    double *exptab = reinterpret_cast<double *>(logtab + kLogTab);
+    const double *q = ws + kHdr;
+    for (int idx = threadIdx.x; idx < nchunks * PAT * EP; idx += blockDim.x) {
+        const int e = idx % EP;
+        const int pat = (idx / EP) % PAT;
+        const int c = idx / (EP * PAT);
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < CB; ++j) {
+            const int i = c * CB + j;
+            if (((pat >> (CB - 1 - j)) & 1) && i < N) acc += q[(size_t)i * EP + e];
+        }
+        lut[idx] = acc;
+    }
+    build_math_tables(logtab, exptab);
+    __syncthreads();
+    const double inv_s2 = ws[1], C1 = ws[3];
+    bool bad = false;
+    MaxSum run = {-INFINITY, 0.0};
+    const int64_t quads = P >> 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const ulonglong2 *rows2 = reinterpret_cast<const ulonglong2 *>(rows);
+    double2 *out2 = reinterpret_cast<double2 *>(out);
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < quads; t += stride) {
+        const ulonglong2 ra = rows2[2 * t], rb = rows2[2 * t + 1];
+        const uint64_t r[4] = {ra.x, ra.y, rb.x, rb.y};
+        const uint64_t diff = (r[0] ^ r[1]) | (r[0] ^ r[2]) | (r[0] ^ r[3]);
+        const int shared_chunks = min(nchunks, diff ? (__clzll((long long)diff) >> 3) : 8);
+        double prefix[EP], acc[4][EP];
+#pragma unroll
+        for (int e = 0; e < EP; ++e) {
+            prefix[e] = 0.0;
+            acc[0][e] = acc[1][e] = acc[2][e] = acc[3][e] = 0.0;
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            if (c < nchunks) {
+                const int sh = 56 - 8 * c;
+                const double *tab = lut + (size_t)c * PAT * EP;
+                if (c < shared_chunks) {
+                    lut_add<EP>(prefix, tab + ((r[0] >> sh) & 255) * EP);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) lut_add<EP>(acc[i], tab + ((r[i] >> sh) & 255) * EP);
+                }
+            }
+        }
+        double val[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+            for (int e = 0; e < EP; ++e) acc[i][e] += prefix[e];
+            val[i] = finish_tab<EP>(acc[i], inv_s2, C1, logtab, bad);
+        }
+        out2[2 * t] = make_double2(val[0], val[1]);
+        out2[2 * t + 1] = make_double2(val[2], val[3]);
+        if (STATS) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ms_push(run, log_prior ? val[i] + log_prior[4 * t + i] : val[i], exptab);
+        }
+    }
+    // tail: the last P % 4 rows, one thread each
+    if (blockIdx.x == 0 && threadIdx.x < (P & 3)) {
+        const int64_t k = (quads << 2) + threadIdx.x;
+        const uint64_t r = rows[k];
+        double acc[EP];
+#pragma unroll
+        for (int e = 0; e < EP; ++e) acc[e] = 0.0;
+        for (int c = 0; c < nchunks; ++c) lut_add<EP>(acc, lut + ((size_t)c * PAT + ((r >> (56 - 8 * c)) & 255)) * EP);
+        const double val = finish_tab<EP>(acc, inv_s2, C1, logtab, bad);
+        out[k] = val;
+        if (STATS) ms_push(run, log_prior ? val + log_prior[k] : val, exptab);
+    }
+    if (bad && status) atomicOr(reinterpret_cast<unsigned int *>(status), MITRE_STATUS_BAD_SCHUR);
+    if (STATS) {
+        __shared__ double sm[256], ss[256];
+        sm[threadIdx.x] = run.m; ss[threadIdx.x] = run.s;
+        __syncthreads();
+        for (int s = 128; s > 0; s >>= 1) {
+            if (threadIdx.x < s) {
+                const MaxSum x = ms_merge(MaxSum{sm[threadIdx.x], ss[threadIdx.x]},
+                                          MaxSum{sm[threadIdx.x + s], ss[threadIdx.x + s]});
+                sm[threadIdx.x] = x.m; ss[threadIdx.x] = x.s;
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) { stat_partials[2 * blockIdx.x] = sm[0]; stat_partials[2 * blockIdx.x + 1] = ss[0]; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// N <= 64, LARGE lexsorted tables: 16-subject subset-sum tables in global memory (L2 / L1
+// resident: 65536 x EP doubles = 3 MB per table at p = 4) instead of 8-subject tables in shared
+// memory.  ceil(N/16) lookups + adds per candidate instead of ceil(N/8); and because the rows
+// are lexsorted (rules.py:439-462), the 32 candidates of a warp almost always agree on their
+// leading 32 subjects, so those lookups are warp-uniform loads served from L1 -- the
+// shared-memory bandwidth that bounds score_w1_kernel (240 B of table reads per candidate) is
+// gone.  No shared-memory table => full occupancy (48 registers/thread).
+// Costs a table build per sweep (score_build_tables16_kernel, ~3 MB written per table), so the
+// launcher only takes this path for P >= kLargeTableMinRows.
+// ---------------------------------------------------------------------------------------------
+constexpr int64_t kLargeTableMinRows = 4 << 20;
+static int64_t g_large_table_min_rows = kLargeTableMinRows;
+
+__host__ __device__ inline int n_tables16(int N) { return (N + 15) >> 4; }
+__host__ __device__ inline int table16_bits(int N, int t) { return min(16, N - 16 * t); }
+__host__ __device__ inline size_t tables16_doubles(int N, int EP)
+{
+    size_t n = 0;
+    for (int t = 0; t < n_tables16(N); ++t) n += ((size_t)1 << table16_bits(N, t)) * EP;
+    return n;
+}
+
+// entry (table t, pattern x): sum of q_i over subjects i = 16 t + j whose pattern bit (bits-1-j)
+// is set, in ascending subject order.
+__global__ void __launch_bounds__(256)
+score_build_tables16_kernel(const double *__restrict__ ws, int N, int EP, double *__restrict__ tables)
+{
+    const double *q = ws + kHdr;
+    const int nt = n_tables16(N);
+    size_t base = 0;
+    for (int t = 0; t < nt; ++t) {
+        const int bits = table16_bits(N, t);
+        const size_t count = ((size_t)1 << bits) * EP;
+        for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < count;
+             idx += (size_t)gridDim.x * blockDim.x) {
+            const int e = (int)(idx % EP);
+            const unsigned pat = (unsigned)(idx / EP);
+            double acc = 0.0;
+            for (int j = 0; j < bits; ++j)
+                if ((pat >> (bits - 1 - j)) & 1) acc += q[(size_t)(16 * t + j) * EP + e];
+            tables[base + idx] = acc;
+        }
+        base += count;
+    }
+}
+
+template <int EP, bool STATS>
+__global__ void __launch_bounds__(256)
+score_w1g_kernel(const uint64_t *__restrict__ rows, int64_t P, const double *__restrict__ ws, int N,
+                 const double *__restrict__ tables, double *__restrict__ out, int32_t *status,
+                 const double *__restrict__ log_prior, double *__restrict__ stat_partials)
+{
+    __shared__ double2 logtab[kLogTab];
+    __shared__ double exptab[kExpTab];
+    build_math_tables(logtab, exptab);
+    __syncthreads();
+    const double inv_s2 = ws[1], C1 = ws[3];
+    const int nt = n_tables16(N);
+    // table bases and shifts (nt <= 4)
+    const double *tb[4];
+    int shift[4];
+    unsigned msk[4];
+    {
+        size_t base = 0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int bits = t < nt ? table16_bits(N, t) : 0;
+            tb[t] = tables + base;
+            shift[t] = 64 - 16 * t - bits;
+            msk[t] = (1u << bits) - 1u;
+            base += ((size_t)1 << bits) * EP;
+        }
+    }
+    bool bad = false;
+    MaxSum run = {-INFINITY, 0.0};
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < P; k += stride) {
+        const uint64_t r = ld_stream_u64(rows + k);
+        double acc[EP];
+        {
+            const double2 *e = reinterpret_cast<const double2 *>(tb[0] + (size_t)((unsigned)(r >> shift[0]) & msk[0]) * EP);
+#pragma unroll
+            for (int j = 0; j < EP / 2; ++j) {
+                const double2 v = __ldg(e + j);
+                acc[2 * j] = v.x;
+                acc[2 * j + 1] = v.y;
+            }
+        }
+#pragma unroll
+        for (int t = 1; t < 4; ++t) {
+            if (t < nt) {
+                const double2 *e =
+                    reinterpret_cast<const double2 *>(tb[t] + (size_t)((unsigned)(r >> shift[t]) & msk[t]) * EP);
+#pragma unroll
+                for (int j = 0; j < EP / 2; ++j) {
+                    const double2 v = __ldg(e + j);
+                    acc[2 * j] += v.x;
+                    acc[2 * j + 1] += v.y;
+                }
+            }
+        }
+        const double val = finish_tab<EP>(acc, inv_s2, C1, logtab, bad);
+        st_stream_f64(out + k, val);
+        if (STATS) ms_push(run, log_prior ? val + log_prior[k] : val, exptab);
+    }
+    if (bad && status) atomicOr(reinterpret_cast<unsigned int *>(status), MITRE_STATUS_BAD_SCHUR);
+    if (STATS) {
+        __shared__ double sm[256], ss[256];
+        sm[threadIdx.x] = run.m; ss[threadIdx.x] = run.s;
+        __syncthreads();
+        for (int s = 128; s > 0; s >>= 1) {
+            if (threadIdx.x < s) {
+                const MaxSum x = ms_merge(MaxSum{sm[threadIdx.x], ss[threadIdx.x]},
+                                          MaxSum{sm[threadIdx.x + s], ss[threadIdx.x + s]});
+                sm[threadIdx.x] = x.m; ss[threadIdx.x] = x.s;
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) { stat_partials[2 * blockIdx.x] = sm[0]; stat_partials[2 * blockIdx.x + 1] = ss[0]; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // N > 64: warp per candidate.  Lane l owns words l, l+32, ...; q is read through L1/L2
 // (N*EP doubles, shared by every warp).  Fixed-order butterfly reduction => deterministic.
 // ---------------------------------------------------------------------------------------------
@@ -546,6 +806,77 @@ static int launch_w1(cudaStream_t st, const uint64_t *rows, int64_t P, double *w
 }
 
 template <int EP>
+static int launch_w1r4(cudaStream_t st, const uint64_t *rows, int64_t P, double *ws, int N, double *out,
+                       int32_t *status, const double *log_prior, double *stats)
+{
+    const int nchunks = (N + 7) / 8;
+    const size_t smem = (size_t)nchunks * 256 * EP * sizeof(double) + kLogTab * sizeof(double2) +
+                        kExpTab * sizeof(double);
+    int per_sm = 1;
+    int64_t blocks = 0;
+    double *partials = ws + kHdr + (size_t)N * EP;
+#define MITRE_R4_LAUNCH(STATSV)                                                                          \
+    {                                                                                                    \
+        auto kern = score_w1r4_kernel<EP, STATSV>;                                                       \
+        MITRE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        MITRE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));         \
+        if (per_sm < 1) return MITRE_ERR_UNSUPPORTED;                                                    \
+        blocks = (int64_t)sm_count() * per_sm;                                                           \
+        const int64_t need = ceil_div64(P >> 2, 256);                                                    \
+        if (need < blocks) blocks = need;                                                                \
+        if (blocks < 1) blocks = 1;                                                                      \
+        if (blocks > kMaxStatCtas) blocks = kMaxStatCtas;                                                \
+        kern<<<(unsigned)blocks, 256, smem, st>>>(rows, P, ws, N, out, status, log_prior, partials);     \
+        MITRE_LAUNCH_CHECK();                                                                            \
+    }
+    if (stats) {
+        MITRE_R4_LAUNCH(true)
+        score_stats_final_kernel<<<1, 256, 0, st>>>(partials, (int)blocks, stats);
+        MITRE_LAUNCH_CHECK();
+    } else {
+        MITRE_R4_LAUNCH(false)
+    }
+#undef MITRE_R4_LAUNCH
+    return MITRE_OK;
+}
+
+template <int EP>
+static int launch_w1g(cudaStream_t st, const uint64_t *rows, int64_t P, double *ws, int N, double *out,
+                      int32_t *status, const double *log_prior, double *stats)
+{
+    double *partials = ws + kHdr + (size_t)N * EP;
+    double *tables = partials + 2 * kMaxStatCtas;
+    const size_t entries = tables16_doubles(N, EP);
+    int64_t bblocks = ceil_div64((int64_t)entries, 256);
+    if (bblocks > 8 * sm_count()) bblocks = 8 * sm_count();
+    score_build_tables16_kernel<<<(unsigned)bblocks, 256, 0, st>>>(ws, N, EP, tables);
+    MITRE_LAUNCH_CHECK();
+    int per_sm = 1;
+    int64_t blocks = 0;
+#define MITRE_G_LAUNCH(STATSV)                                                                           \
+    {                                                                                                    \
+        auto kern = score_w1g_kernel<EP, STATSV>;                                                        \
+        MITRE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));            \
+        if (per_sm < 1) return MITRE_ERR_UNSUPPORTED;                                                    \
+        blocks = (int64_t)sm_count() * per_sm;                                                           \
+        const int64_t need = ceil_div64(P, 256);                                                         \
+        if (need < blocks) blocks = need;                                                                \
+        if (blocks > kMaxStatCtas) blocks = kMaxStatCtas;                                                \
+        kern<<<(unsigned)blocks, 256, 0, st>>>(rows, P, ws, N, tables, out, status, log_prior, partials); \
+        MITRE_LAUNCH_CHECK();                                                                            \
+    }
+    if (stats) {
+        MITRE_G_LAUNCH(true)
+        score_stats_final_kernel<<<1, 256, 0, st>>>(partials, (int)blocks, stats);
+        MITRE_LAUNCH_CHECK();
+    } else {
+        MITRE_G_LAUNCH(false)
+    }
+#undef MITRE_G_LAUNCH
+    return MITRE_OK;
+}
+
+template <int EP>
 static int launch_wide(cudaStream_t st, const uint64_t *rows, int64_t P, int W64, const double *ws,
                        int N, double *out, int32_t *status)
 {
@@ -569,6 +900,10 @@ static int launch_ep(cudaStream_t st, const uint64_t *rows, int64_t P, int W64, 
         *stats_done = true;
         const size_t lut8 = (size_t)((N + 7) / 8) * 256 * EP * sizeof(double);
         // keep >= 2 CTAs per SM where the byte table allows it, else fall to nibble tables
+        if (P >= g_large_table_min_rows) return launch_w1g<EP>(st, rows, P, ws, N, out, status, log_prior, stats);
+        const bool aligned32 = ((reinterpret_cast<uintptr_t>(rows) | reinterpret_cast<uintptr_t>(out)) & 31) == 0;
+        if (EP <= 8 && lut8 <= 100 * 1024 && aligned32 && P >= 64)
+            return launch_w1r4<EP>(st, rows, P, ws, N, out, status, log_prior, stats);
         if (lut8 <= 100 * 1024) return launch_w1<EP, 8>(st, rows, P, ws, N, out, status, log_prior, stats);
         return launch_w1<EP, 4>(st, rows, P, ws, N, out, status, log_prior, stats);
     }
@@ -583,7 +918,17 @@ using namespace mitre;
 extern "C" size_t mitre_score_workspace_bytes(int N, int p)
 {
     if (N <= 0 || p <= 0 || p > MITRE_MAX_P) return 0;
-    return sizeof(double) * ((size_t)kHdr + (size_t)N * ep_for(p) + 2 * (size_t)kMaxStatCtas);
+    size_t n = (size_t)kHdr + (size_t)N * ep_for(p) + 2 * (size_t)kMaxStatCtas;
+    if (N <= 64) n += tables16_doubles(N, ep_for(p));     // 16-subject tables of the large-table kernel
+    return sizeof(double) * n;
+}
+
+// Test / tuning hook: the candidate count from which the large-table kernel is used (default 4 Mi).
+extern "C" int mitre_set_large_table_min_rows(int64_t rows)
+{
+    if (rows < 0) return MITRE_ERR_INVALID;
+    g_large_table_min_rows = rows;
+    return MITRE_OK;
 }
 
 extern "C" int mitre_weight_stats(void *stream, const double *a, const double *b, int64_t P, double *stats,

@@ -210,3 +210,32 @@ def test_score_all_stats_fused_logsumexp():
         st2 = stats2.cpu().numpy()
         want2 = float(torch.logsumexp(torch.as_tensor(ll), 0))
         assert abs(st2[0] + np.log(st2[1]) - want2) < 1e-11 * abs(want2)
+
+
+def test_large_table_kernel_parity():
+    """The 16-subject global-table kernel (default for P >= 4 Mi rows) forced onto small cases:
+    reference golden vectors, odd shapes, masks and the fused stats."""
+    import torch
+    from mitre_b200 import device as D
+    from mitre_b200._lib import lib
+    assert lib().mitre_set_large_table_min_rows(0) == 0
+    try:
+        for name in sorted(MG.SCORING_CASES):
+            c = MG.scoring_inputs(**MG.SCORING_CASES[name])
+            gold = np.load(os.path.join(GOLD, name + ".npz"))["loglik"]
+            assert rel(gpu_score(c), gold) < RTOL, name
+        for N, p, P in [(1, 1, 9), (15, 2, 100), (16, 3, 333), (17, 1, 64), (32, 4, 1000), (33, 5, 257),
+                        (48, 2, 500), (49, 7, 300), (64, 9, 400), (35, 24, 50)]:
+            c = MG.scoring_inputs(seed=500 + N + p, N=N, p=p, P=P)
+            opts = (c["truth"] * c["mask"]).astype(np.float64)
+            want = oracle.likelihoods_of_all_options(c["X"], c["omega"], (c["y"] - 0.5) / c["omega"], opts,
+                                                     c["sigma2"])
+            assert rel(gpu_score(c), want) < RTOL, (N, p, P)
+        c = MG.scoring_inputs(seed=77, N=35, p=4, P=50000)
+        packed = D.pack_rows(c["truth"])
+        out, status, stats = D.score_all_stats(packed, 35, c["X"], c["omega"], c["y"] - 0.5, 100.0)
+        st = stats.cpu().numpy()
+        want = float(torch.logsumexp(out, 0))
+        assert abs(st[0] + np.log(st[1]) - want) < 1e-11 * abs(want)
+    finally:
+        lib().mitre_set_large_table_min_rows(4 << 20)
