@@ -135,6 +135,17 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def fp64_roofline(D, P, kernel_ms):
+    """Scoring is fp64-pipe work (north_star): algorithmic fp64 operations per candidate of the
+    table kernel at p = 4 -- 12 adds (two 6-vector table sums) + 28 (|w|^2, Schur complement, table
+    log, table reciprocal, assembly) = 40 -- over the measured DFMA rate of this device."""
+    ops = 40.0
+    peak = D.probe_fp64_tflops()
+    achieved = ops * P / (kernel_ms * 1e-3) / 1e12
+    return {"ops_per_candidate": ops, "achieved_tops": achieved, "peak_dfma_tflops": peak,
+            "peak_instr_tops": peak / 2.0, "frac_of_instr_peak": achieved / (peak / 2.0)}
+
+
 def ncu_traffic_per_launch(P):
     """dram bytes per launch of score_w1_kernel from the committed ncu capture, scaled to P."""
     path = os.path.join(ROOT, "profiles", "score_w1_traffic.json")
@@ -370,10 +381,13 @@ def run_b200(args):
     empty_rows = packed[:0]
 
     def sweep():
-        out, _ = D.score_all(packed, N, dX, dom, dka, SIGMA2, mask=dmask, buffers=buffers)
         if world > 1:
-            st = D.weight_stats(out, None, buffers=draw)
+            # (max, sum-exp) of the slice reduced in the scoring kernel's epilogue, then the 16-byte exchange
+            out, _, st = D.score_all_stats(packed, N, dX, dom, dka, SIGMA2, mask=dmask, buffers=buffers,
+                                           draw_buffers=draw)
             dist.all_gather_into_tensor(gathered, st)
+        else:
+            out, _ = D.score_all(packed, N, dX, dom, dka, SIGMA2, mask=dmask, buffers=buffers)
         return out
 
     def setup_only():
@@ -449,12 +463,13 @@ def run_b200(args):
             "e2e": {"value": P_total / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(n_small * 8), "d2h_bytes_per_step": int(P * 8),
                     "ms_per_step": e2e_ms},
-            "gpu_launches": int(args.steps * (2 + (2 if world > 1 else 0))),
+            "gpu_launches": int(args.steps * (3 + (1 if world > 1 else 0))),
             "clocks": clocks.summary(),
-            "roofline": {"kernel": "score_w1_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "roofline": {"kernel": "score_w1g4_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                          "traffic": ncu_traffic_per_launch(P), "kernel_ms": kernel_ms,
-                         "setup_ms": setup_ms, "algorithmic_bytes_per_candidate": 16},
+                         "setup_ms": setup_ms, "algorithmic_bytes_per_candidate": 16,
+                         "fp64": fp64_roofline(D, P, kernel_ms)},
             "detector_eval": {"groups": int(pop._G), "algorithmic_bytes": det_bytes,
                               "ms": det_ms, "achieved_gbs": det_bytes / (det_ms * 1e-3) / 1e9,
                               "frac_of_hbm_peak": det_bytes / (det_ms * 1e-3) / 1e9 / peak,

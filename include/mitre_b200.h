@@ -51,6 +51,11 @@ const char *mitre_error_string(int code);
 /* sm count, compute capability and opt-in shared memory of the current device. */
 int mitre_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *smem_optin);
 
+/* Measurement aid: launches a pure DFMA kernel (8 independent chains per thread); the caller times
+ * it with stream events.  *flops_launched_host receives the flop count of the launch.  Gives the
+ * fp64-pipe denominator for the scoring kernel (MEASURED_PEAKS.json has no fp64 entry). */
+int mitre_probe_fp64(void *stream, int iters, double *sink, double *flops_launched_host);
+
 /* ---- packing (layout conversion at the boundary) ------------------------------------------ */
 
 /* float64[P, N] (non-zero = True; the array the reference passes as `list_of_truth_vectors`,

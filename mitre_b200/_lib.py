@@ -27,6 +27,7 @@ SIGNATURES = {
     "mitre_version": (ctypes.c_char_p, []),
     "mitre_error_string": (ctypes.c_char_p, [c_int]),
     "mitre_device_info": (c_int, [ctypes.POINTER(c_int)] * 3 + [ctypes.POINTER(c_size_t)]),
+    "mitre_probe_fp64": (c_int, [c_void_p, c_int, c_void_p, ctypes.POINTER(c_double)]),
     "mitre_pack_rows_f64": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p]),
     "mitre_pack_rows_u8": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p]),
     "mitre_unpack_rows_u8": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p]),

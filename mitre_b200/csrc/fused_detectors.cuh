@@ -68,7 +68,7 @@ struct NetHolder {
 __device__ __forceinline__ void cmp_exchange(double &x, double &y, int &ix, int &iy)
 {
     const bool sw = x > y;
-    const double lo = fmin(x, y), hi = fmax(x, y);     // DMNMX: values are never NaN here
+    const double lo = sw ? y : x, hi = sw ? x : y;
     const int ilo = sw ? iy : ix, ihi = sw ? ix : iy;
     x = lo; y = hi; ix = ilo; iy = ihi;
 }

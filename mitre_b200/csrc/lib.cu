@@ -70,6 +70,22 @@ unpack_rows_kernel(const uint64_t *__restrict__ packed, int64_t P, int N, uint8_
     }
 }
 
+// fp64 pipe probe: 8 independent DFMA chains per thread (the denominator for the scoring kernel's
+// fp64 roofline; MEASURED_PEAKS.json carries no fp64 figure).
+__global__ void __launch_bounds__(256)
+fp64_probe_kernel(int iters, double seed, double *__restrict__ sink)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+           a7 = a0 + 7;
+    const double m = 0.999999, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 123.456) sink[0] = r;      // never true: keeps the chains alive
+}
+
 static unsigned grid_for(int64_t work_items, int threads)
 {
     int64_t blocks = ceil_div64(work_items, threads);
@@ -239,4 +255,15 @@ cleanup:
     cudaFree(d_status);
     free(h_kappa);
     return rc;
+}
+
+// Launches the DFMA probe; *flops_launched = 2 * 8 * iters * threads.  Time it with stream events.
+extern "C" int mitre_probe_fp64(void *stream, int iters, double *sink, double *flops_launched)
+{
+    if (iters <= 0 || !sink) return MITRE_ERR_INVALID;
+    const int blocks = sm_count() * 8;
+    fp64_probe_kernel<<<blocks, 256, 0, as_stream(stream)>>>(iters, 1.0, sink);
+    MITRE_LAUNCH_CHECK();
+    if (flops_launched) *flops_launched = 2.0 * 8.0 * (double)iters * 256.0 * (double)blocks;
+    return MITRE_OK;
 }

@@ -59,6 +59,23 @@ def device_info():
     return dict(sm_count=sm.value, cc=(ma.value, mi.value), smem_optin=smem.value)
 
 
+def probe_fp64_tflops(iters=20000, reps=3):
+    """Measured fp64 FMA throughput of the current device (TFLOP/s), CUDA-event timed."""
+    sink = torch.zeros(1, dtype=F64, device=dev())
+    flops = ctypes.c_double(0.0)
+    check(lib().mitre_probe_fp64(_stream(), iters, _p(sink), ctypes.byref(flops)), "mitre_probe_fp64")
+    torch.cuda.synchronize()
+    best = 0.0
+    for _ in range(reps):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        check(lib().mitre_probe_fp64(_stream(), iters, _p(sink), ctypes.byref(flops)), "mitre_probe_fp64")
+        e.record()
+        torch.cuda.synchronize()
+        best = max(best, flops.value / (s.elapsed_time(e) * 1e-3) / 1e12)
+    return best
+
+
 # ---- packing ---------------------------------------------------------------------------------
 
 def pack_mask(mask_bool):
