@@ -481,6 +481,9 @@ def run_b200(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, pop, state, N, P, torch, D)
+            del pop, packed
+            torch.cuda.empty_cache()
+            line["mcmc"] = mcmc_samples_per_sec(args)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -524,6 +527,56 @@ def cpu_baseline(args, pop, state, N, P, torch, D):
                       "bool->float64 marshal (logit_rules.py:214-217, %.0f%% of the time) + the "
                       "efficient_likelihoods kernel" % (done, chunk, 100.0 * marshal / spent),
             "kernel_only_value": done / (spent - marshal), "max_rel_diff_vs_gpu": check_rel}
+
+
+def mcmc_samples_per_sec(args):
+    """BASELINE.json's second metric: MCMC samples/s of the Bokulich-shaped problem (S2: N=35,
+    V=200, 12 intervals, t in [1,180]) with the B200 likelihood path vs the same host sampler
+    calling the reference's compiled Cython kernel on the host (same seed, same PG sampler)."""
+    import torch
+    from mitre_b200 import chains, logit_rules as LR
+    from oracle import build_ref
+    import oracle
+    data, model = chains.build_model("S2", seed=args.seed)
+    r0 = chains.initial_rule_list(model)
+    chains.run_chain(model, 1, 3, r0)                      # warm-up
+    torch.cuda.synchronize()
+    steps = 40
+    t0 = time.perf_counter()
+    chains.run_chain(model, 2, steps, r0)
+    gpu = steps / (time.perf_counter() - t0)
+    try:
+        ref = build_ref.load()
+        kind = "reference"
+    except Exception:
+        ref, kind = oracle, "port"
+    flat_truth = model.rule_population.flat_truth                   # host bool[P, N], like the reference keeps it
+
+    class ReferenceKernelModel(LR.LogisticRuleModel):
+        """The reference's data flow for the two likelihood calls (logit_rules.py:171-229)."""
+        def __init__(self, base):
+            self.__dict__.update(base.__dict__)
+
+        def likelihoods_z_given_Xs(self, omega, Xs):
+            return np.array([oracle.likelihood_z_given_X(omega, X, self.data.y, self.prior_coefficient_variance)
+                             for X in Xs])
+
+        def likelihoods_of_all_options(self, rl, current_omega, i, j, N_workers=None):
+            X, mask = self._sweep_inputs(rl, i, j)
+            opts = (flat_truth * mask).astype(np.float64)
+            z = (self.data.y - 0.5) / current_omega
+            return ref.likelihoods_of_all_options(X.astype(np.float64), current_omega, z, opts,
+                                                  np.float64(self.prior_coefficient_variance))
+
+    cpu_model = ReferenceKernelModel(model)
+    cpu_steps = 8
+    t0 = time.perf_counter()
+    chains.run_chain(cpu_model, 2, cpu_steps, r0)
+    cpu = cpu_steps / (time.perf_counter() - t0)
+    return {"workload": "S2 Bokulich-shape", "candidates": len(model.rule_population),
+            "b200_samples_per_sec": gpu, "b200_steps": steps,
+            "cpu_samples_per_sec": cpu, "cpu_steps": cpu_steps, "cpu_kernel": kind, "cpu_cores": 1,
+            "note": "same host sampler, seed and Polya-Gamma sampler; only the likelihood calls differ"}
 
 
 def main():

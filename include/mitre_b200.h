@@ -261,6 +261,22 @@ int mitre_draw_index(void *stream, const double *a, const double *b, int64_t P, 
                      int stabilise, double *stats, int64_t *index_out, void *workspace,
                      size_t workspace_bytes);
 
+/* ---- primitive prior on the device: replaces the O(P) host evaluation of flat_prior ------------
+ *
+ * Reference: LogisticRuleModel.flat_prior (logit_rules.py:424-457): log-prior of every primitive =
+ * Normal logpdf of its variable's log-weight + Beta logpdf of its window's relative duration,
+ * minus the log-sum-exp over all primitives.  Both terms depend only on the primitive's
+ * (variable, window), i.e. on its group, so the host evaluates V + W scalars and
+ *   mitre_row_groups  maps every lexsorted row to its group once per population
+ *                     (binary search of perm[i] in row_offsets int64[G+1]);
+ *   mitre_row_prior   writes out[i] = by_variable[group_variable[g]] + by_window[group_window[g]] - norm.
+ */
+int mitre_row_groups(void *stream, const int64_t *perm, int64_t P, const int64_t *row_offsets,
+                     int64_t G, int32_t *row_group);
+int mitre_row_prior(void *stream, const int32_t *row_group, int64_t P, const int32_t *group_variable,
+                    const int32_t *group_window, const double *by_variable, const double *by_window,
+                    double norm, double *out);
+
 #ifdef __cplusplus
 }
 #endif

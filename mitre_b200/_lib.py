@@ -66,6 +66,9 @@ SIGNATURES = {
                               [c_i64] + [c_void_p] * 4 + [c_int] + [c_void_p] * 4),
     "mitre_selftest_divide": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p]),
     "mitre_densify_perm": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p]),
+    "mitre_row_groups": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_void_p]),
+    "mitre_row_prior": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_double, c_void_p]),
     "mitre_draw_workspace_bytes": (c_size_t, [c_i64]),
     "mitre_weight_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p,
                                    c_size_t]),

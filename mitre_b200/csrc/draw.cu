@@ -184,6 +184,38 @@ draw_select_kernel(const double *__restrict__ a, const double *__restrict__ b, i
     if (threadIdx.x == 0) *index_out = sel * kDrawTile + scount[0];
 }
 
+// ---- primitive prior on the device (flat_prior, logit_rules.py:424-457) ---------------------------
+// row -> group by binary search of the row's enumeration index in the group row offsets
+__global__ void __launch_bounds__(256)
+row_groups_kernel(const int64_t *__restrict__ perm, int64_t P, const int64_t *__restrict__ row_offsets,
+                  int64_t G, int32_t *__restrict__ row_group)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += stride) {
+        const int64_t r = perm[i];
+        int64_t lo = 0, hi = G;          // last g with row_offsets[g] <= r
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (row_offsets[mid] <= r) lo = mid;
+            else hi = mid;
+        }
+        row_group[i] = (int32_t)lo;
+    }
+}
+
+// out[i] = by_variable[gvar[g]] + by_window[gwin[g]] - norm,  g = row_group[i]
+__global__ void __launch_bounds__(256)
+row_prior_kernel(const int32_t *__restrict__ row_group, int64_t P, const int32_t *__restrict__ gvar,
+                 const int32_t *__restrict__ gwin, const double *__restrict__ by_variable,
+                 const double *__restrict__ by_window, double norm, double *__restrict__ out)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += stride) {
+        const int g = row_group[i];
+        out[i] = (__ldg(by_variable + __ldg(gvar + g)) + __ldg(by_window + __ldg(gwin + g))) - norm;
+    }
+}
+
 constexpr int kStatsBlocks = 592;   // 148 SMs x 4
 
 }  // namespace mitre
@@ -231,6 +263,35 @@ extern "C" int mitre_draw_index(void *stream, const double *a, const double *b, 
     draw_tile_sums_kernel<<<(unsigned)ntiles, 256, 0, st>>>(a, b, P, stats, stabilise, tile_sums);
     MITRE_LAUNCH_CHECK();
     draw_select_kernel<<<1, 256, 0, st>>>(a, b, P, stats, stabilise, tile_sums, ntiles, u, index_out);
+    MITRE_LAUNCH_CHECK();
+    return MITRE_OK;
+}
+
+extern "C" int mitre_row_groups(void *stream, const int64_t *perm, int64_t P, const int64_t *row_offsets,
+                                int64_t G, int32_t *row_group)
+{
+    if (P < 0 || G <= 0) return MITRE_ERR_INVALID;
+    if (P == 0) return MITRE_OK;
+    if (!perm || !row_offsets || !row_group) return MITRE_ERR_INVALID;
+    int64_t blocks = ceil_div64(P, 256);
+    if (blocks > 16 * sm_count()) blocks = 16 * sm_count();
+    row_groups_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(perm, P, row_offsets, G, row_group);
+    MITRE_LAUNCH_CHECK();
+    return MITRE_OK;
+}
+
+extern "C" int mitre_row_prior(void *stream, const int32_t *row_group, int64_t P, const int32_t *group_variable,
+                               const int32_t *group_window, const double *by_variable, const double *by_window,
+                               double norm, double *out)
+{
+    if (P < 0) return MITRE_ERR_INVALID;
+    if (P == 0) return MITRE_OK;
+    if (!row_group || !group_variable || !group_window || !by_variable || !by_window || !out)
+        return MITRE_ERR_INVALID;
+    int64_t blocks = ceil_div64(P, 256);
+    if (blocks > 16 * sm_count()) blocks = 16 * sm_count();
+    row_prior_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(row_group, P, group_variable, group_window,
+                                                                      by_variable, by_window, norm, out);
     MITRE_LAUNCH_CHECK();
     return MITRE_OK;
 }

@@ -359,3 +359,24 @@ def draw_index(a, b, u, stabilise=False, buffers=None):
                                  _p(buffers.stats), _p(buffers.index), _p(buffers.workspace),
                                  buffers.workspace.numel()), "mitre_draw_index")
     return buffers.index
+
+
+# ---- primitive prior ---------------------------------------------------------------------------
+
+def row_groups(perm, row_offsets):
+    """int32[P]: the group of every lexsorted row."""
+    P = perm.shape[0]
+    G = row_offsets.shape[0] - 1
+    out = torch.empty(P, dtype=I32, device=dev())
+    check(lib().mitre_row_groups(_stream(), _p(perm), P, _p(row_offsets), G, _p(out)), "mitre_row_groups")
+    return out
+
+
+def row_prior(row_group, group_variable, group_window, by_variable, by_window, norm, out=None):
+    """out[i] = by_variable[gvar[g_i]] + by_window[gwin[g_i]] - norm (flat_prior, logit_rules.py:424-457)."""
+    P = row_group.shape[0]
+    if out is None:
+        out = torch.empty(P, dtype=F64, device=dev())
+    check(lib().mitre_row_prior(_stream(), _p(row_group), P, _p(group_variable), _p(group_window),
+                                _p(by_variable), _p(by_window), float(norm), _p(out)), "mitre_row_prior")
+    return out

@@ -103,6 +103,9 @@ class LogisticRuleModel(object):
         state = dict(self.__dict__)
         state['_device_state'] = None
         state.pop('_flat_prior_cache', None)
+        state.pop('_prior_table_cache', None)
+        state.pop('_structure_terms', None)
+        state.pop('_prior_device_cache', None)
         return state
 
     def _dev(self):
@@ -251,13 +254,18 @@ class LogisticRuleModel(object):
 
     def structure_prior(self, rule_list, empty_probability):
         """logit_rules.py:337-402."""
-        length_distribution = nbinom(self.hyperparameter_alpha_m,
-                                     self.hyperparameter_beta_m / (1.0 + self.hyperparameter_beta_m))
-        log_rule_normalization = length_distribution.logcdf(self.max_rules - 1)
-        sublength_distribution = nbinom(
-            self.hyperparameter_alpha_primitives,
-            self.hyperparameter_beta_primitives / (1.0 + self.hyperparameter_beta_primitives))
-        log_primitive_normalization = sublength_distribution.logcdf(self.max_primitives - 1)
+        frozen = self.__dict__.get('_structure_terms')
+        if frozen is None:      # pure functions of the model constants: freeze once
+            length_distribution = nbinom(self.hyperparameter_alpha_m,
+                                         self.hyperparameter_beta_m / (1.0 + self.hyperparameter_beta_m))
+            sublength_distribution = nbinom(
+                self.hyperparameter_alpha_primitives,
+                self.hyperparameter_beta_primitives / (1.0 + self.hyperparameter_beta_primitives))
+            frozen = (length_distribution, length_distribution.logcdf(self.max_rules - 1),
+                      sublength_distribution, sublength_distribution.logcdf(self.max_primitives - 1))
+            self._structure_terms = frozen
+        length_distribution, log_rule_normalization, sublength_distribution, \
+            log_primitive_normalization = frozen
         rules = rule_list.rules
         if len(rules) == 0:
             return np.log(empty_probability)
@@ -273,9 +281,73 @@ class LogisticRuleModel(object):
         return l0 + l1 + l2
 
     def prior_contribution_from_primitives(self, state):
+        if getattr(self, 'fast_prior', False):
+            # factored form: no P-long vector (see _prior_tables)
+            bv, bw, norm = self._prior_tables(state)
+            lookup = self.rule_population._window_lookup
+            return sum([(bv[p.variable] + bw[lookup[(float(p.window[0]), float(p.window[1]))]]) - norm
+                        for rule in state.rl for p in rule])
         flat_prior = self.flat_prior(state)
         return sum([flat_prior[self.rule_population.get_primitive_index(p)]
                     for rule in state.rl for p in rule])
+
+    def _prior_tables(self, state):
+        """flat_prior in factored form: (by_variable[V], by_window[W], normalisation).  A primitive's
+        log-prior depends only on its (variable, window); the normalisation is the log-sum-exp over
+        the G groups weighted by their primitive counts instead of over the P primitives
+        (identical up to summation order)."""
+        pop = self.rule_population
+        key = (state.phylogeny_mean, state.phylogeny_std, state.window_concentration,
+               state.window_typical_fraction, id(pop._filter_map), pop.n_primitives)
+        cache = self.__dict__.setdefault('_prior_table_cache', [])
+        for k, v in cache:
+            if k == key:
+                return v
+        log_vw = np.log(np.asarray(self.data.variable_weights, dtype=np.float64))
+        by_variable = scipy.stats.norm.logpdf(log_vw, loc=state.phylogeny_mean, scale=state.phylogeny_std)
+        total_duration = float(self.data.experiment_end - self.data.experiment_start)
+        durations = pop._durations_by_window / ((1.0 + self.window_duration_epsilon) * total_duration)
+        window_a = state.window_concentration * state.window_typical_fraction
+        window_b = state.window_concentration * (1.0 - state.window_typical_fraction)
+        by_window = scipy.stats.beta.logpdf(durations, window_a, window_b)
+        counts = pop.group_counts()
+        terms = by_variable[pop._group_variable] + by_window[pop._group_window]
+        live = counts > 0
+        normalization = logsumexp(terms[live], b=counts[live]) if live.any() else 0.0
+        result = (by_variable, by_window, float(normalization))
+        cache.append((key, result))
+        del cache[:-6]
+        return result
+
+    def flat_prior_device(self, state):
+        """flat_prior as a float64[P] CUDA tensor (mitre_row_prior), cached per hyperparameter state."""
+        import torch
+        from . import device as D
+        pop = self.rule_population
+        key = (state.phylogeny_mean, state.phylogeny_std, state.window_concentration,
+               state.window_typical_fraction, id(pop._filter_map), pop.n_primitives)
+        cached = self.__dict__.get('_prior_device_cache')
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        bv, bw, norm = self._prior_tables(state)
+        gvar, gwin = pop.group_tables_device()
+        out = cached[1] if cached is not None and cached[1].shape[0] == pop.n_primitives else None
+        d = D.row_prior(pop.row_group_device(), gvar, gwin, torch.as_tensor(bv, device=D.dev()),
+                        torch.as_tensor(bw, device=D.dev()), norm, out=out)
+        self._prior_device_cache = (key, d)
+        return d
+
+    def likelihoods_with_stats_device(self, rl, current_omega, i, j, log_prior):
+        """One launch: log-likelihoods of all options (device) + (max, sum-exp) of lik + log_prior."""
+        from . import device as D
+        X, mask = self._sweep_inputs(rl, i, j)
+        dX, dom, dka, dmask = self._stage_sweep_inputs(X, current_omega, mask)
+        st = self._dev()
+        if 'draw' not in st:
+            st['draw'] = D.DrawBuffers(max(len(self.rule_population), 1))
+        return D.score_all_stats(self.rule_population.packed_truth, st['N'], dX, dom, dka,
+                                 self.prior_coefficient_variance, mask=dmask, buffers=st['buffers'],
+                                 log_prior=log_prior, draw_buffers=st['draw'])
 
     def multinomial_prior(self, rule_list):
         return sum([log_multinomial_coefficient(subrule) for subrule in rule_list.rules])
@@ -350,8 +422,16 @@ class LogisticRuleState:
 class LogisticRuleSampler(RuleListSampler):
     """logit_rules.py:503-1420."""
 
-    def __init__(self, model, r0, local_updates_per_structure_update=10):
+    def __init__(self, model, r0, local_updates_per_structure_update=10, device_draw=False):
+        """device_draw=False walks the reference's arithmetic exactly (log-likelihoods copied to the
+        host, numpy cumsum draw).  device_draw=True keeps the P-long vectors on the GPU: factored
+        prior (model._prior_tables / flat_prior_device), log-sum-exp reduced in the scoring kernel,
+        proposal drawn by mitre_draw_index -- same np.random consumption, same chain except where a
+        uniform draw lands within rounding of a partial sum."""
         self.model = model
+        self.device_draw = device_draw
+        if device_draw:
+            model.fast_prior = True
         r0 = r0.copy()
         for i in range(len(r0)):
             model.rule_population.sort_list_of_primitives(r0[i])
@@ -492,7 +572,7 @@ class LogisticRuleSampler(RuleListSampler):
         """logit_rules.py:794-881."""
         population = self.model.rule_population
         primitives = population.flat_rules
-        primitive_priors = self.model.flat_prior(self.current_state)
+        primitive_priors = None if self.device_draw else self.model.flat_prior(self.current_state)
         rule_list = self.current_state.rl
         positions = []
         counts = []
@@ -514,8 +594,9 @@ class LogisticRuleSampler(RuleListSampler):
             i, j = positions[choice_index]
             primitive = rule_list[i][j]
             k0 = population.get_primitive_index(primitive)
-            multinomial_priors = np.zeros(len(primitives))
-            relative_rates = np.ones(len(primitives))
+            if not self.device_draw:
+                multinomial_priors = np.zeros(len(primitives))
+                relative_rates = np.ones(len(primitives))
             base_counts = counts[i].copy()
             if k0 is not None:
                 base_counts[k0] -= 1
@@ -523,12 +604,17 @@ class LogisticRuleSampler(RuleListSampler):
                 k0 = -1
                 logger.warning('Not decrementing base counts of atypical detector')
             for k, n in base_counts.items():
+                if self.device_draw:
+                    break
                 multinomial_priors[k] = -1.0 * gammaln(n + 1 + 1)
                 relative_rates[k] += n
-            likelihoods = self.model.likelihoods_of_all_options(rule_list, self.current_state.omega, i, j)
-            posteriors = likelihoods + primitive_priors + multinomial_priors
-            weights = posteriors + np.log(relative_rates)
-            k = choose_from_relative_probabilities(np.exp(weights))
+            if self.device_draw:
+                k = self._device_gibbs_draw(rule_list, i, j, base_counts)
+            else:
+                likelihoods = self.model.likelihoods_of_all_options(rule_list, self.current_state.omega, i, j)
+                posteriors = likelihoods + primitive_priors + multinomial_priors
+                weights = posteriors + np.log(relative_rates)
+                k = choose_from_relative_probabilities(np.exp(weights))
             rule_list[i][j] = PrimitiveRule(*primitives[k])
             logger.info('At (%d,%d) replacing %d with %d' % (i, j, k0, k))
             self.comments.append('At (%d,%d) replacing %d with %d' % (i, j, k0, k))
@@ -540,6 +626,49 @@ class LogisticRuleSampler(RuleListSampler):
                 counts[i].pop(k0)
         self.ensure_current_rl_sorted()
         self.current_X = self.model.data.covariate_matrix(rule_list)
+
+    # ---- device-resident weight assembly + draw (device_draw=True) ------------------------------------
+    def _with_sparse(self, d_vec, deltas):
+        """Context helper: add sparse {index: delta} to a device vector, return the restore info."""
+        import torch
+        idx = [k for k in deltas if k is not None and k >= 0]
+        if not idx:
+            return None
+        t_idx = torch.as_tensor(idx, device=d_vec.device)
+        saved = d_vec[t_idx].clone()
+        d_vec[t_idx] = saved + torch.as_tensor([deltas[k] for k in idx], dtype=d_vec.dtype,
+                                               device=d_vec.device)
+        return (t_idx, saved)
+
+    @staticmethod
+    def _restore(d_vec, token):
+        if token is not None:
+            d_vec[token[0]] = token[1]
+
+    def _device_draw(self, d_a, d_b, deltas=None):
+        """index = #{cumsum(exp(a + b + sparse)) < u * total} with u = np.random.rand()
+        (choose_from_relative_probabilities, rules.py:1261-1264) on the device."""
+        from . import device as D
+        st = self.model._dev()
+        if 'draw' not in st:
+            st['draw'] = D.DrawBuffers(max(len(self.model.rule_population), 1))
+        token = self._with_sparse(d_b, deltas) if deltas else None
+        u = np.random.rand()
+        k = int(D.draw_index(d_a, d_b, u, stabilise=False, buffers=st['draw']).item())
+        self._restore(d_b, token)
+        return min(k, d_a.shape[0] - 1)
+
+    def _device_gibbs_draw(self, rule_list, i, j, base_counts):
+        """update_primitives' weights = lik + prior + multinomial + log(relative_rates)
+        (logit_rules.py:861-862) assembled and drawn on the device."""
+        from . import device as D
+        d_prior = self.model.flat_prior_device(self.current_state)
+        out, status = self.model.likelihoods_of_all_options_device(rule_list, self.current_state.omega, i, j)
+        deltas = {k: -1.0 * gammaln(n + 1 + 1) + np.log(1.0 + n) for k, n in base_counts.items()
+                  if k is not None and k >= 0}
+        k = self._device_draw(out, d_prior, deltas)
+        D.raise_on_status(status)
+        return k
 
     def add_remove(self):
         if np.random.rand() < 0.5:
@@ -562,11 +691,21 @@ class LogisticRuleSampler(RuleListSampler):
         log_relative_prior = (structure_contributions[1] - structure_contributions[0])
         old_X = self.model.data.covariate_matrix(base_rule)
         old_likelihood = self.model.likelihood_z_given_X(self.current_state.omega, old_X)
-        priors = self.model.flat_prior(self.current_state)
-        likelihoods = self.model.likelihoods_of_all_options(new_rl, self.current_state.omega,
-                                                            position_to_add_at, 0)
-        primitive_distribution = priors + likelihoods
-        log_marginalized_likelihood = logsumexp(primitive_distribution)
+        if self.device_draw:
+            from . import device as D
+            d_prior = self.model.flat_prior_device(self.current_state)
+            out, status, stats = self.model.likelihoods_with_stats_device(
+                new_rl, self.current_state.omega, position_to_add_at, 0, d_prior)
+            st = stats.cpu().numpy()
+            D.raise_on_status(status)
+            log_marginalized_likelihood = st[0] + np.log(st[1])
+            primitive_distribution = ('device', out, d_prior, None)
+        else:
+            priors = self.model.flat_prior(self.current_state)
+            likelihoods = self.model.likelihoods_of_all_options(new_rl, self.current_state.omega,
+                                                                position_to_add_at, 0)
+            primitive_distribution = priors + likelihoods
+            log_marginalized_likelihood = logsumexp(primitive_distribution)
         log_likelihood_ratio = (log_marginalized_likelihood - old_likelihood)
         new_total_n_primitives = sum(map(len, new_rl))
         probability_remove_proposal = 1.0 / new_total_n_primitives
@@ -582,6 +721,9 @@ class LogisticRuleSampler(RuleListSampler):
         for primitive in base_subrule:
             k = population.get_primitive_index(primitive)
             base_rule_counts[k] = base_rule_counts.get(k, 0) + 1
+        if self.device_draw:
+            return self._consider_addition_to_existing_rule_device(base_rule, position_to_add_to,
+                                                                   base_n_istar, base_rule_counts)
         log_relative_multinomial_coefficient = (np.log(base_n_istar + 1) +
                                                 np.zeros(len(population.flat_rules)))
         for k, n in base_rule_counts.items():
@@ -614,6 +756,46 @@ class LogisticRuleSampler(RuleListSampler):
         return (new_rl, log_relative_prior, log_likelihood_ratio, primitive_distribution,
                 probability_remove_proposal)
 
+    def _consider_addition_to_existing_rule_device(self, base_rule, position_to_add_to, base_n_istar,
+                                                   base_rule_counts):
+        """consider_addition_to_existing_rule with every P-long quantity reduced on the device.
+        log_relative_multinomial_coefficient = c0 + sparse deltas (logit_rules.py:1005-1013)."""
+        from . import device as D
+        c0 = np.log(base_n_istar + 1)
+        deltas = {k: -1.0 * np.log(n + 1) for k, n in base_rule_counts.items() if k is not None}
+        new_rl = base_rule.copy()
+        new_rl[position_to_add_to].append(self._placeholder())
+        structure_contributions = [
+            self.model.structure_prior(rl, empty_probability=self.current_state.empty_probability)
+            for rl in [base_rule, new_rl]]
+        log_relative_structure_prior = (structure_contributions[1] - structure_contributions[0])
+        d_prior = self.model.flat_prior_device(self.current_state)
+        st = self.model._dev()
+        if 'draw' not in st:
+            st['draw'] = D.DrawBuffers(max(len(self.model.rule_population), 1))
+        old_X = self.model.data.covariate_matrix(base_rule)
+        old_likelihood = self.model.likelihood_z_given_X(self.current_state.omega, old_X)
+        # C = logsumexp(prior + lik) with the unmodified prior, in the scoring launch
+        out, status, stats = self.model.likelihoods_with_stats_device(
+            new_rl, self.current_state.omega, position_to_add_to, base_n_istar, d_prior)
+        sC = stats.cpu().numpy().copy()
+        D.raise_on_status(status)
+        token = self._with_sparse(d_prior, deltas)
+        sA = D.weight_stats(d_prior, None, buffers=st['draw']).cpu().numpy().copy()     # prior + deltas
+        sB = D.weight_stats(out, d_prior, buffers=st['draw']).cpu().numpy().copy()      # + lik
+        self._restore(d_prior, token)
+        lse = lambda s: s[0] + np.log(s[1])
+        log_relative_prior_primitive_piece = c0 + lse(sA)
+        log_relative_prior = (log_relative_prior_primitive_piece + log_relative_structure_prior)
+        log_marginalized_likelihood = (c0 + lse(sB)) - log_relative_prior_primitive_piece
+        log_likelihood_ratio = (log_marginalized_likelihood - old_likelihood)
+        new_total_n_primitives = sum(map(len, new_rl))
+        T_sstar_prefactor = (base_n_istar + 1.0) / (new_total_n_primitives)
+        T_sstar_other_factor = np.exp(lse(sC) - (c0 + lse(sB)))
+        probability_remove_proposal = (T_sstar_prefactor * T_sstar_other_factor)
+        return (new_rl, log_relative_prior, log_likelihood_ratio, ('device', out, d_prior, deltas),
+                probability_remove_proposal)
+
     def add(self, force_acceptance=False):
         """logit_rules.py:1097-1192."""
         current_rl = self.current_state.rl
@@ -640,7 +822,11 @@ class LogisticRuleSampler(RuleListSampler):
         if (np.random.rand() < acceptance_ratio) or force_acceptance:
             comment += ': accepted (ratio %.3g)' % acceptance_ratio
             self.successes['add'] = self.successes.get('add', 0) + 1
-            k = choose_from_relative_probabilities(np.exp(candidate_distribution))
+            if isinstance(candidate_distribution, tuple):
+                _tag, d_out, d_prior, deltas = candidate_distribution
+                k = self._device_draw(d_out, d_prior, deltas)
+            else:
+                k = choose_from_relative_probabilities(np.exp(candidate_distribution))
             comment += ': adds detector %d' % k
             primitives = self.model.rule_population.flat_rules
             new_rl[rule_index][primitive_index] = PrimitiveRule(*primitives[k])

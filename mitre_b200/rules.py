@@ -554,6 +554,45 @@ class DiscreteRulePopulation:
     def filter_thresholds(self, *args, **kwargs):
         raise NotImplementedError('filter_thresholds (rules.py:631-791) is outside the device hot path')
 
+    # -- device-side descriptors for the on-device prior / draw ------------------------------------------
+    def row_group_device(self):
+        """int32[P] CUDA tensor: group of every active lexsorted row."""
+        from . import device as D
+        import torch
+        c = self._host_cache
+        key = ('row_group_dev', id(self._filter_map))
+        if key not in c:
+            if self._P == 0:
+                base = torch.empty(0, dtype=torch.int32, device=D.dev())
+            else:
+                base = D.row_groups(self._perm, self._row_offsets)
+            if self._filter_map is not None:
+                base = base.index_select(0, torch.as_tensor(self._filter_map, device=base.device))
+            c[key] = base
+        return c[key]
+
+    def group_tables_device(self):
+        """(group_variable, group_window) int32[G] CUDA tensors."""
+        from . import device as D
+        import torch
+        c = self._host_cache
+        if 'group_tables_dev' not in c:
+            c['group_tables_dev'] = (
+                torch.as_tensor(np.ascontiguousarray(self._group_variable, dtype=np.int32), device=D.dev()),
+                torch.as_tensor(np.ascontiguousarray(self._group_window, dtype=np.int32), device=D.dev()))
+        return c['group_tables_dev']
+
+    def group_counts(self):
+        """int64[G]: number of active primitives in every group (2 K_g unless filtered)."""
+        c = self._host_cache
+        key = ('group_counts', id(self._filter_map))
+        if key not in c:
+            if self._filter_map is None:
+                c[key] = 2 * self._K_host.astype(np.int64)
+            else:
+                c[key] = np.bincount(self._flat_groups(), minlength=self._G).astype(np.int64)
+        return c[key]
+
     # -- flat arrays the priors consume (rules.py:453-454, 606-608) ---------------------------------
     def _flat_groups(self):
         rg = self._row_group_host()

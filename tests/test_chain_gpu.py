@@ -27,8 +27,9 @@ def same_rule_list(got, want):
                 assert abs(g[4] - w[4]) <= 1e-9 * abs(w[4]) + 1e-300
 
 
+@pytest.mark.parametrize("device_draw", [False, True])
 @pytest.mark.parametrize("name", sorted(MC.CHAIN_CASES))
-def test_chain_matches_reference_trace(name):
+def test_chain_matches_reference_trace(name, device_draw):
     from mitre_b200 import logit_rules as LR, polyagamma, rules as R
     from mitre_b200.posterior import PosteriorSummary
     cfg = MC.CHAIN_CASES[name]
@@ -42,7 +43,8 @@ def test_chain_matches_reference_trace(name):
     assert len(model.rule_population) == gold["n_primitives"]
     np.random.seed(cfg["seed"])
     LR.ppg = polyagamma.PyPolyaGamma(cfg["seed"])
-    sampler = LR.LogisticRuleSampler(model, MC.initial_rule_list(R, model))
+    model.fast_prior = False
+    sampler = LR.LogisticRuleSampler(model, MC.initial_rule_list(R, model), device_draw=device_draw)
     sampler.sample(cfg["steps"])
     assert sampler.comments == gold["comments"]
     for s, want in zip(sampler.states, gold["rule_lists"]):
