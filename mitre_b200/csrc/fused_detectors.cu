@@ -3,6 +3,7 @@
 #include "fused_detectors.cuh"
 
 namespace mitre {
+int g_fused_packed = 0;   // measured: the value + id network at 8 warps/SM beats the packed-key one at 11
 int launch_fused_nb4(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
                      const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
                      const double *winv_n, const double *winv_sxx, const int32_t *widx,
@@ -176,6 +177,13 @@ extern "C" int mitre_densify_perm(void *stream, const int64_t *perm_padded, int6
     densify_perm_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(perm_padded, P, 2 * (N - 1), row_offsets,
                                                                          perm);
     MITRE_LAUNCH_CHECK();
+    return MITRE_OK;
+}
+
+// Test / tuning hook: 1 = packed-key sorting network (default), 0 = value + id network.
+extern "C" int mitre_set_fused_packed(int enable)
+{
+    g_fused_packed = enable ? 1 : 0;
     return MITRE_OK;
 }
 

@@ -15,8 +15,12 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
 def build_gpu_population(d, pop_cfg, fused=True):
-    """fused=True: single-launch thread-per-group kernel (N <= 63); False: phase-by-phase kernels."""
+    """fused=True: single-launch thread-per-group kernel (N <= 63), value + id network (default);
+    "packed": same kernel with the packed-key network (N <= 40); False: phase-by-phase kernels."""
     from mitre_b200 import rules as R
+    from mitre_b200._lib import lib
+    lib().mitre_set_fused_packed(1 if fused == "packed" else 0)
+    fused = bool(fused)
     V = d["X"][0].shape[0]
     data = R.Dataset(d["X"], d["T"], d["y"], ["v%d" % i for i in range(V)], d["variable_weights"],
                      d["experiment_start"], d["experiment_end"])
@@ -63,7 +67,7 @@ def check_population(pop, gold_windows, gold_ok, gold_groups, gold_values, gold_
         assert np.array_equal(pop.truth_table[t], DO.unpack_rows(gold_packed[i:i + 1], N)[0])
 
 
-@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("fused", [True, "packed", False])
 @pytest.mark.parametrize("name", sorted(MG.DETECTOR_CASES))
 def test_population_vs_reference_golden(name, fused):
     cfg = MG.DETECTOR_CASES[name]
@@ -80,7 +84,7 @@ def test_population_vs_reference_golden(name, fused):
     assert np.array_equal(pop.flat_truth, DO.unpack_rows(gold["sorted_truth_packed"], N))
 
 
-@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("fused", [True, "packed", False])
 @pytest.mark.parametrize("N,V,T,nint", [(2, 3, (2, 3), 1), (3, 2, (2, 4), 2), (8, 40, (3, 6), 3), (9, 33, (3, 6), 3),
                                         (16, 3, (2, 5), 2), (24, 2, (3, 5), 2), (33, 5, (3, 20), 6),
                                         (40, 70, (3, 7), 2), (41, 2, (3, 7), 2), (48, 3, (3, 7), 2),
@@ -205,3 +209,40 @@ def test_exact_division_selftest():
     fast, exact = fast.cpu().numpy(), exact.cpu().numpy()
     assert np.array_equal(fast, exact)
     assert np.array_equal(exact, a / n)
+
+
+@pytest.mark.parametrize("fused", [True, "packed", False])
+def test_near_ties_below_key_resolution_take_the_exact_path(fused):
+    """Values that differ only in their lowest mantissa bits collide in the packed sort key (value
+    bits with the subject id in the low 6 bits); the kernel must detect the mis-ordered neighbours
+    and fall back to the exact comparison path.  Constant series with 4 samples have exact means."""
+    from mitre_b200 import rules as R
+    rng = np.random.RandomState(5)
+    N, V = 20, 34
+    base = 0.3
+    X, T = [], []
+    for s in range(N):
+        t = np.array([1.0, 2.0])
+        x = rng.rand(V, 2)
+        delta = 2.0 ** -10 * (s + 1)          # distinct, well separated slopes; exact two-sample means
+        # variable 0: the mean of subject s is base advanced by (N - s) ulps -> DEcreasing with the id,
+        # so ordering by (truncated key, id) is exactly wrong; variable 1: a mix of ties and near-ties
+        v0 = base
+        for _ in range(N - s):
+            v0 = np.nextafter(v0, 1.0)
+        x[0, :] = [v0 - delta, v0 + delta]
+        v1 = np.nextafter(base, 1.0) if s % 3 == 0 else (base if s % 3 == 1 else np.nextafter(base, 0.0))
+        x[1, :] = [v1 - delta, v1 + delta]
+        assert (x[0, 0] + x[0, 1]) / 2 == v0 and (x[1, 0] + x[1, 1]) / 2 == v1
+        X.append(x)
+        T.append(t)
+    y = np.arange(N) % 2 == 0
+    ref = DO.build_population(X, T, 0.0, 5.0, 1, 1.0, None)
+    o = ref["order"]
+    d = dict(X=X, T=T, y=y, variable_weights=np.ones(V), experiment_start=0.0, experiment_end=5.0)
+    data, pop = build_gpu_population(d, dict(tmin=1.0, N_intervals=1, tmax=None), fused)
+    is_mean = ref["group_type"] == 1
+    assert np.array_equal(pop._values.cpu().numpy()[is_mean], ref["values"][is_mean])
+    assert np.array_equal(pop._K_host[is_mean], ref["K"][is_mean]), (pop._K_host[is_mean][:4], ref["K"][is_mean][:4])
+    assert np.array_equal(pop.packed_truth.cpu().numpy().view(np.uint64), DO.pack_rows(ref["truth"][o]))
+    assert np.array_equal(pop._perm_host(), o)
