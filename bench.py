@@ -545,6 +545,11 @@ def mcmc_samples_per_sec(args):
     t0 = time.perf_counter()
     chains.run_chain(model, 2, steps, r0)
     gpu = steps / (time.perf_counter() - t0)
+    chains.run_chain(model, 1, 3, r0, device_gibbs=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    chains.run_chain(model, 2, steps, r0, device_gibbs=True)
+    gpu_gibbs = steps / (time.perf_counter() - t0)
     try:
         ref = build_ref.load()
         kind = "reference"
@@ -576,6 +581,7 @@ def mcmc_samples_per_sec(args):
     cpu = cpu_steps / (time.perf_counter() - t0)
     return {"workload": "S2 Bokulich-shape", "candidates": len(model.rule_population),
             "b200_samples_per_sec": gpu, "b200_steps": steps,
+            "b200_device_gibbs_samples_per_sec": gpu_gibbs,
             "cpu_samples_per_sec": cpu, "cpu_steps": cpu_steps, "cpu_kernel": kind, "cpu_cores": 1,
             "note": "same host sampler, seed and Polya-Gamma sampler; the CPU arm follows the reference's data "
                     "flow (O(P) flat_prior, bool->float64 marshal, Cython kernel, numpy cumsum draw), the B200 "

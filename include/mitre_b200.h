@@ -278,6 +278,21 @@ int mitre_row_prior(void *stream, const int32_t *row_group, int64_t P, const int
                     const int32_t *group_window, const double *by_variable, const double *by_window,
                     double norm, double *out);
 
+/* ---- omega / beta Gibbs inner loop on the device ----------------------------------------------------
+ *
+ * Reference: LogisticRuleSampler.update_omega (logit_rules.py:753-760, pypolyagamma.pgdrawv) and
+ * update_beta (762-787), run 10x per step (567-573).  One single-CTA launch:
+ *   mode 0: n_iters x { omega_i ~ PG(1, (X beta)_i);  beta ~ N(V X'kappa, V), V = (I/v + X' Omega X)^-1 }
+ *   mode 1: n_iters independent beta draws for the omega passed in `omega` (input)
+ * X float64[N, p]; beta_io float64[p] (start value in, last draw out); omega float64[N];
+ * betas_out float64[n_iters, p].  Philox4x32-10 keyed by `seed`.  Distributionally (not
+ * stream-for-stream) equivalent to the host samplers.  mitre_pg_draw: out[i] ~ PG(1, z[i]).
+ */
+int mitre_gibbs_omega_beta(void *stream, const double *X, const double *kappa, int N, int p,
+                           double prior_variance, int n_iters, int mode, uint64_t seed,
+                           double *beta_io, double *omega, double *betas_out, int32_t *status);
+int mitre_pg_draw(void *stream, const double *z, int64_t n, uint64_t seed, double *out);
+
 #ifdef __cplusplus
 }
 #endif

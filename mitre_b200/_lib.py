@@ -70,6 +70,9 @@ SIGNATURES = {
     "mitre_row_groups": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_void_p]),
     "mitre_row_prior": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_double, c_void_p]),
+    "mitre_gibbs_omega_beta": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_int, c_int,
+                                       ctypes.c_uint64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mitre_pg_draw": (c_int, [c_void_p, c_void_p, c_i64, ctypes.c_uint64, c_void_p]),
     "mitre_draw_workspace_bytes": (c_size_t, [c_i64]),
     "mitre_weight_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p,
                                    c_size_t]),

@@ -36,13 +36,13 @@ def initial_rule_list(model):
     return R.RuleList([[model.rule_population.flat_rules[int(np.argmin(dist))]]])
 
 
-def run_chain(model, seed, steps, r0=None, device_draw=True):
+def run_chain(model, seed, steps, r0=None, device_draw=True, device_gibbs=False):
     """One chain: numpy's global RNG and the Polya-Gamma sampler are seeded with `seed`."""
     from . import logit_rules as LR, polyagamma
     np.random.seed(seed)
     LR.ppg = polyagamma.PyPolyaGamma(seed)
     sampler = LR.LogisticRuleSampler(model, r0 if r0 is not None else initial_rule_list(model),
-                                     device_draw=device_draw)
+                                     device_draw=device_draw, device_gibbs=device_gibbs)
     sampler.sample(steps)
     return sampler
 
@@ -61,6 +61,8 @@ def main():
     ap.add_argument("--shape", default="S2")
     ap.add_argument("--variables", type=int, default=None)
     ap.add_argument("--base-seed", type=int, default=0)
+    ap.add_argument("--host-gibbs", action="store_true",
+                    help="omega/beta updates on the host (reference RNG stream) instead of the device kernel")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -77,7 +79,7 @@ def main():
     t0 = time.perf_counter()
     results = []
     for i, seed in mine:
-        sampler = run_chain(model, seed, args.steps, r0)
+        sampler = run_chain(model, seed, args.steps, r0, device_gibbs=not args.host_gibbs)
         results.append(dict(chain=i, seed=seed, point=summarize(sampler),
                             final_length=len(sampler.current_state.rl)))
     dt = time.perf_counter() - t0

@@ -380,3 +380,31 @@ def row_prior(row_group, group_variable, group_window, by_variable, by_window, n
     check(lib().mitre_row_prior(_stream(), _p(row_group), P, _p(group_variable), _p(group_window),
                                 _p(by_variable), _p(by_window), float(norm), _p(out)), "mitre_row_prior")
     return out
+
+
+# ---- omega / beta Gibbs loop ---------------------------------------------------------------------
+
+def gibbs_omega_beta(X, kappa, prior_variance, beta, n_iters, seed, omega=None):
+    """n_iters x (omega ~ PG(1, X beta), beta | omega) in one launch (omega=None), or n_iters beta
+    draws for a given omega.  Returns (omega float64[N], beta float64[p], betas float64[n_iters, p],
+    status) as CUDA tensors."""
+    X = _dev_f64(X)
+    kappa = _dev_f64(kappa)
+    N, p = X.shape
+    beta_io = _dev_f64(beta).clone()
+    mode = 0 if omega is None else 1
+    om = torch.empty(N, dtype=F64, device=dev()) if omega is None else _dev_f64(omega).clone()
+    betas = torch.empty((n_iters, p), dtype=F64, device=dev())
+    status = torch.zeros(1, dtype=I32, device=dev())
+    check(lib().mitre_gibbs_omega_beta(_stream(), _p(X), _p(kappa), N, p, float(prior_variance), int(n_iters),
+                                       mode, int(seed) & 0xFFFFFFFFFFFFFFFF, _p(beta_io), _p(om), _p(betas),
+                                       _p(status)), "mitre_gibbs_omega_beta")
+    return om, beta_io, betas, status
+
+
+def pg_draw(z, seed):
+    z = _dev_f64(z)
+    out = torch.empty_like(z)
+    check(lib().mitre_pg_draw(_stream(), _p(z), z.shape[0], int(seed) & 0xFFFFFFFFFFFFFFFF, _p(out)),
+          "mitre_pg_draw")
+    return out

@@ -422,7 +422,8 @@ class LogisticRuleState:
 class LogisticRuleSampler(RuleListSampler):
     """logit_rules.py:503-1420."""
 
-    def __init__(self, model, r0, local_updates_per_structure_update=10, device_draw=False):
+    def __init__(self, model, r0, local_updates_per_structure_update=10, device_draw=False,
+                 device_gibbs=False):
         """device_draw=False walks the reference's arithmetic exactly (log-likelihoods copied to the
         host, numpy cumsum draw).  device_draw=True keeps the P-long vectors on the GPU: factored
         prior (model._prior_tables / flat_prior_device), log-sum-exp reduced in the scoring kernel,
@@ -430,6 +431,10 @@ class LogisticRuleSampler(RuleListSampler):
         uniform draw lands within rounding of a partial sum."""
         self.model = model
         self.device_draw = device_draw
+        # device_gibbs=True: the 10 x (omega, beta) Gibbs updates of a step are one kernel launch
+        # (mitre_gibbs_omega_beta: Polya-Gamma + posterior draw on the device, Philox stream keyed
+        # from np.random) -- same conditionals, different random stream than the host samplers.
+        self.device_gibbs = device_gibbs
         if device_draw:
             model.fast_prior = True
         r0 = r0.copy()
@@ -463,11 +468,14 @@ class LogisticRuleSampler(RuleListSampler):
 
     def step(self):
         """logit_rules.py:567-596."""
-        beta_values = []
-        for _ in range(self.local_updates_per_structure_update):
-            self.update_omega()
-            self.update_beta()
-            beta_values.append(self.current_state.beta)
+        if self.device_gibbs:
+            beta_values = self._device_gibbs_sweeps(self.local_updates_per_structure_update)
+        else:
+            beta_values = []
+            for _ in range(self.local_updates_per_structure_update):
+                self.update_omega()
+                self.update_beta()
+                beta_values.append(self.current_state.beta)
         self.additional_beta_values.append(beta_values)
         move_type_indicator = np.random.rand()
         if move_type_indicator < 0.45:
@@ -546,6 +554,21 @@ class LogisticRuleSampler(RuleListSampler):
             logger.info('Step %d' % i)
             self.step()
             i += 1
+
+    def _device_gibbs_sweeps(self, n):
+        """n x (update_omega, update_beta) (logit_rules.py:567-573) in one launch."""
+        from . import device as D
+        state = self.current_state
+        p = self.current_X.shape[1]
+        beta0 = state.beta if len(state.beta) == p else np.zeros(p)
+        seed = int(np.random.randint(0, 2 ** 62))
+        omega, beta, betas, status = D.gibbs_omega_beta(
+            self.current_X, self.model.data.y - 0.5, self.model.prior_coefficient_variance, beta0, n, seed)
+        betas_h = betas.cpu().numpy()
+        D.raise_on_status(status)
+        state.omega = omega.cpu().numpy()
+        state.beta = betas_h[-1].copy()
+        return [betas_h[i].copy() for i in range(n)]
 
     def update_omega(self):
         """logit_rules.py:753-760."""
