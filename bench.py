@@ -313,7 +313,12 @@ def build_population(args, rank, torch):
     if pop._fused_args is not None:
         D.detectors_fused(*pop._fused_args)
         marks["detector_kernel_ms"] = cuda_time_ms(torch, lambda: D.detectors_fused(*pop._fused_args), 3)
-        marks["detector_kernel"] = "fused_detectors_kernel"
+        marks["detector_kernel"] = "values_resident_kernel + sort_emit_staged_kernel"
+        from mitre_b200._lib import lib
+        lib().mitre_set_detector_split(0)      # the single fused kernel, for comparison
+        D.detectors_fused(*pop._fused_args)
+        marks["detector_single_kernel_ms"] = cuda_time_ms(torch, lambda: D.detectors_fused(*pop._fused_args), 3)
+        lib().mitre_set_detector_split(1)
     torch.cuda.empty_cache()
     return data, pop, marks
 
@@ -474,6 +479,7 @@ def run_b200(args):
                               "ms": det_ms, "achieved_gbs": det_bytes / (det_ms * 1e-3) / 1e9,
                               "frac_of_hbm_peak": det_bytes / (det_ms * 1e-3) / 1e9 / peak,
                               "kernel": build_marks.get("detector_kernel", "phase-by-phase kernels + host"),
+                              "single_fused_kernel_ms": build_marks.get("detector_single_kernel_ms"),
                               "host_phase_ms": {"values": build_marks["values"],
                                                 "thresholds_rows": build_marks["thresholds_rows"],
                                                 "lexsort": build_marks["lexsort"]},

@@ -196,11 +196,21 @@ int mitre_lexsort_rows(void *stream, const uint64_t *rows, int64_t P, int W64, i
                        int64_t *perm, uint64_t *sorted_rows, void *workspace,
                        size_t workspace_bytes);
 
-/* ---- fused detector evaluation (N <= 63): values + thresholds + truth rows in ONE launch --------
+/* ---- fused detector evaluation (N <= 63): values + thresholds + truth rows, no host round trip --
  *
- * Same outputs as mitre_detector_values / _thresholds / _rows, but one thread owns one
- * (window, variable, type) group end to end (register-resident sorting network), so HBM sees only
- * the algorithmic output.
+ * Same outputs as mitre_detector_values / _thresholds / _rows.  Default: two launches.
+ *   values      block = 32 variables x a run of windows; the tile's samples sit in shared memory for
+ *               the whole block (series_t is read from HBM once), both detector types come out of
+ *               one pass over a window's samples, finished tiles leave as contiguous ranges.  When
+ *               the sample axis does not fit in shared memory: block = window x 32 variables,
+ *               samples read through L2.
+ *   sort/emit   one thread owns one (window, variable, type) group: register-resident sorting
+ *               network, then thresholds and both truth rows of every threshold; the block's slices
+ *               of values / thresholds / rows move between HBM and shared memory as TMA bulk copies.
+ * mitre_set_detector_split selects other variants for tests and timing: 0 = the earlier single
+ * kernel that does all of it per thread; 1 = default; 2 = values with one thread per value;
+ * 3 = values through L2 even when the resident kernel fits; 4 = sort/emit with direct global
+ * accesses instead of staged tiles.
  *
  * mitre_window_lists precomputes, once per window set, everything that does not depend on the
  * variable (ld = row stride of the per-sample lists, >= S):
@@ -214,6 +224,7 @@ int mitre_lexsort_rows(void *stream, const uint64_t *rows, int64_t P, int W64, i
  *                vstride >= V), so the 32 lanes of a warp read 32 consecutive variables of one sample
  *   task_window / task_type  int32 / int8 [n_tasks_wt]: the (window, type) pairs to evaluate
  *                (type 0 = slope, only for windows with slope_ok; 1 = average)
+ *   n_windows    W, the number of windows behind the lists; G = number of groups (rows of values)
  *   rows_padded  uint64[G, 2(N-1)]: group g's first 2*K[g] slots hold its (above, below) row pairs
  *                in threshold order; unused slots hold the sentinel ~0.  A stable lexsort of this
  *                padded table with N+1 significant bits (mitre_lexsort_rows(..., N + 1, ...)) leaves
@@ -232,10 +243,11 @@ int mitre_detectors_fused(void *stream, const double *series_t, int64_t vstride,
                           const double *winv_n, const double *winv_sxx, const int32_t *widx,
                           const double *wdt, int64_t ld, const int64_t *group_base,
                           const uint8_t *slope_ok, const int32_t *task_window,
-                          const int8_t *task_type, int n_tasks_wt, double *values,
-                          double *thresholds, int32_t *K, uint64_t *rows_padded);
+                          const int8_t *task_type, int n_tasks_wt, int n_windows, int64_t G,
+                          double *values, double *thresholds, int32_t *K, uint64_t *rows_padded);
 int mitre_densify_perm(void *stream, const int64_t *perm_padded, int64_t P, int N,
                        const int64_t *row_offsets, int64_t *perm);
+int mitre_set_detector_split(int enable); /* tuning/test hook, see above */
 int mitre_set_fused_packed(int enable);   /* tuning/test hook: packed-key (1) or value+id (0, default) sort */
 int mitre_selftest_divide(void *stream, const double *a, const int32_t *n, int64_t count,
                           double *fast, double *exact);

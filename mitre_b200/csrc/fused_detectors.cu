@@ -1,105 +1,107 @@
 // fused_detectors.cu -- C ABI entry points of the fused detector path (kernel: fused_detectors.cuh,
 // instantiated per sorting-network size in fused_inst.cu).
+#define MITRE_FUSED_MAIN 1
 #include "fused_detectors.cuh"
 
 namespace mitre {
+int g_detector_split = 1;
 int g_fused_packed = 0;   // measured: the value + id network at 8 warps/SM beats the packed-key one at 11
 int launch_fused_nb4(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
                      const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
                      const double *winv_n, const double *winv_sxx, const int32_t *widx,
                      const double *wdt, int64_t ld, const int64_t *group_base,
                      const uint8_t *slope_ok, const int32_t *task_window, const int8_t *task_type,
-                     int n_wt, double *values, double *thresholds, int32_t *K, uint64_t *rows);
+                     int n_wt, int64_t G, double *values, double *thresholds, int32_t *K, uint64_t *rows);
 int launch_fused_nb8(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
                      const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
                      const double *winv_n, const double *winv_sxx, const int32_t *widx,
                      const double *wdt, int64_t ld, const int64_t *group_base,
                      const uint8_t *slope_ok, const int32_t *task_window, const int8_t *task_type,
-                     int n_wt, double *values, double *thresholds, int32_t *K, uint64_t *rows);
+                     int n_wt, int64_t G, double *values, double *thresholds, int32_t *K, uint64_t *rows);
 int launch_fused_nb12(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
                      const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
                      const double *winv_n, const double *winv_sxx, const int32_t *widx,
                      const double *wdt, int64_t ld, const int64_t *group_base,
                      const uint8_t *slope_ok, const int32_t *task_window, const int8_t *task_type,
-                     int n_wt, double *values, double *thresholds, int32_t *K, uint64_t *rows);
+                     int n_wt, int64_t G, double *values, double *thresholds, int32_t *K, uint64_t *rows);
 int launch_fused_nb16(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
                      const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
                      const double *winv_n, const double *winv_sxx, const int32_t *widx,
                      const double *wdt, int64_t ld, const int64_t *group_base,
                      const uint8_t *slope_ok, const int32_t *task_window, const int8_t *task_type,
-                     int n_wt, double *values, double *thresholds, int32_t *K, uint64_t *rows);
+                     int n_wt, int64_t G, double *values, double *thresholds, int32_t *K, uint64_t *rows);
 int launch_fused_nb20(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
                      const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
                      const double *winv_n, const double *winv_sxx, const int32_t *widx,
                      const double *wdt, int64_t ld, const int64_t *group_base,
                      const uint8_t *slope_ok, const int32_t *task_window, const int8_t *task_type,
-                     int n_wt, double *values, double *thresholds, int32_t *K, uint64_t *rows);
+                     int n_wt, int64_t G, double *values, double *thresholds, int32_t *K, uint64_t *rows);
 int launch_fused_nb24(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
                      const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
                      const double *winv_n, const double *winv_sxx, const int32_t *widx,
                      const double *wdt, int64_t ld, const int64_t *group_base,
                      const uint8_t *slope_ok, const int32_t *task_window, const int8_t *task_type,
-                     int n_wt, double *values, double *thresholds, int32_t *K, uint64_t *rows);
+                     int n_wt, int64_t G, double *values, double *thresholds, int32_t *K, uint64_t *rows);
 int launch_fused_nb28(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
                      const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
                      const double *winv_n, const double *winv_sxx, const int32_t *widx,
                      const double *wdt, int64_t ld, const int64_t *group_base,
                      const uint8_t *slope_ok, const int32_t *task_window, const int8_t *task_type,
-                     int n_wt, double *values, double *thresholds, int32_t *K, uint64_t *rows);
+                     int n_wt, int64_t G, double *values, double *thresholds, int32_t *K, uint64_t *rows);
 int launch_fused_nb32(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
                      const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
                      const double *winv_n, const double *winv_sxx, const int32_t *widx,
                      const double *wdt, int64_t ld, const int64_t *group_base,
                      const uint8_t *slope_ok, const int32_t *task_window, const int8_t *task_type,
-                     int n_wt, double *values, double *thresholds, int32_t *K, uint64_t *rows);
+                     int n_wt, int64_t G, double *values, double *thresholds, int32_t *K, uint64_t *rows);
 int launch_fused_nb36(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
                      const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
                      const double *winv_n, const double *winv_sxx, const int32_t *widx,
                      const double *wdt, int64_t ld, const int64_t *group_base,
                      const uint8_t *slope_ok, const int32_t *task_window, const int8_t *task_type,
-                     int n_wt, double *values, double *thresholds, int32_t *K, uint64_t *rows);
+                     int n_wt, int64_t G, double *values, double *thresholds, int32_t *K, uint64_t *rows);
 int launch_fused_nb40(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
                      const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
                      const double *winv_n, const double *winv_sxx, const int32_t *widx,
                      const double *wdt, int64_t ld, const int64_t *group_base,
                      const uint8_t *slope_ok, const int32_t *task_window, const int8_t *task_type,
-                     int n_wt, double *values, double *thresholds, int32_t *K, uint64_t *rows);
+                     int n_wt, int64_t G, double *values, double *thresholds, int32_t *K, uint64_t *rows);
 int launch_fused_nb44(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
                      const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
                      const double *winv_n, const double *winv_sxx, const int32_t *widx,
                      const double *wdt, int64_t ld, const int64_t *group_base,
                      const uint8_t *slope_ok, const int32_t *task_window, const int8_t *task_type,
-                     int n_wt, double *values, double *thresholds, int32_t *K, uint64_t *rows);
+                     int n_wt, int64_t G, double *values, double *thresholds, int32_t *K, uint64_t *rows);
 int launch_fused_nb48(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
                      const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
                      const double *winv_n, const double *winv_sxx, const int32_t *widx,
                      const double *wdt, int64_t ld, const int64_t *group_base,
                      const uint8_t *slope_ok, const int32_t *task_window, const int8_t *task_type,
-                     int n_wt, double *values, double *thresholds, int32_t *K, uint64_t *rows);
+                     int n_wt, int64_t G, double *values, double *thresholds, int32_t *K, uint64_t *rows);
 int launch_fused_nb52(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
                      const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
                      const double *winv_n, const double *winv_sxx, const int32_t *widx,
                      const double *wdt, int64_t ld, const int64_t *group_base,
                      const uint8_t *slope_ok, const int32_t *task_window, const int8_t *task_type,
-                     int n_wt, double *values, double *thresholds, int32_t *K, uint64_t *rows);
+                     int n_wt, int64_t G, double *values, double *thresholds, int32_t *K, uint64_t *rows);
 int launch_fused_nb56(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
                      const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
                      const double *winv_n, const double *winv_sxx, const int32_t *widx,
                      const double *wdt, int64_t ld, const int64_t *group_base,
                      const uint8_t *slope_ok, const int32_t *task_window, const int8_t *task_type,
-                     int n_wt, double *values, double *thresholds, int32_t *K, uint64_t *rows);
+                     int n_wt, int64_t G, double *values, double *thresholds, int32_t *K, uint64_t *rows);
 int launch_fused_nb60(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
                      const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
                      const double *winv_n, const double *winv_sxx, const int32_t *widx,
                      const double *wdt, int64_t ld, const int64_t *group_base,
                      const uint8_t *slope_ok, const int32_t *task_window, const int8_t *task_type,
-                     int n_wt, double *values, double *thresholds, int32_t *K, uint64_t *rows);
+                     int n_wt, int64_t G, double *values, double *thresholds, int32_t *K, uint64_t *rows);
 int launch_fused_nb64(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
                      const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
                      const double *winv_n, const double *winv_sxx, const int32_t *widx,
                      const double *wdt, int64_t ld, const int64_t *group_base,
                      const uint8_t *slope_ok, const int32_t *task_window, const int8_t *task_type,
-                     int n_wt, double *values, double *thresholds, int32_t *K, uint64_t *rows);
+                     int n_wt, int64_t G, double *values, double *thresholds, int32_t *K, uint64_t *rows);
 
 // padded slot index -> dense enumeration index (the reference's _reordering_cache values)
 __global__ void __launch_bounds__(256)
@@ -138,8 +140,8 @@ extern "C" int mitre_detectors_fused(void *stream, const double *series_t, int64
                                      const double *winv_n, const double *winv_sxx, const int32_t *widx,
                                      const double *wdt, int64_t ld, const int64_t *group_base,
                                      const uint8_t *slope_ok, const int32_t *task_window,
-                                     const int8_t *task_type, int n_tasks_wt, double *values,
-                                     double *thresholds, int32_t *K, uint64_t *rows_padded)
+                                     const int8_t *task_type, int n_tasks_wt, int n_windows, int64_t G,
+                                     double *values, double *thresholds, int32_t *K, uint64_t *rows_padded)
 {
     if (N < 2 || N > 63) return MITRE_ERR_UNSUPPORTED;
     if (V <= 0 || n_tasks_wt < 0 || vstride < V || ld <= 0) return MITRE_ERR_INVALID;
@@ -147,22 +149,70 @@ extern "C" int mitre_detectors_fused(void *stream, const double *series_t, int64
     if (!series_t || !wlo || !wcnt || !wstart || !winv_n || !winv_sxx || !widx || !wdt || !group_base ||
         !slope_ok || !task_window || !task_type || !values || !thresholds || !K || !rows_padded)
         return MITRE_ERR_INVALID;
-    if (N <= 4) return launch_fused_nb4(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, values, thresholds, K, rows_padded);
-    if (N <= 8) return launch_fused_nb8(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, values, thresholds, K, rows_padded);
-    if (N <= 12) return launch_fused_nb12(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, values, thresholds, K, rows_padded);
-    if (N <= 16) return launch_fused_nb16(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, values, thresholds, K, rows_padded);
-    if (N <= 20) return launch_fused_nb20(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, values, thresholds, K, rows_padded);
-    if (N <= 24) return launch_fused_nb24(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, values, thresholds, K, rows_padded);
-    if (N <= 28) return launch_fused_nb28(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, values, thresholds, K, rows_padded);
-    if (N <= 32) return launch_fused_nb32(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, values, thresholds, K, rows_padded);
-    if (N <= 36) return launch_fused_nb36(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, values, thresholds, K, rows_padded);
-    if (N <= 40) return launch_fused_nb40(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, values, thresholds, K, rows_padded);
-    if (N <= 44) return launch_fused_nb44(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, values, thresholds, K, rows_padded);
-    if (N <= 48) return launch_fused_nb48(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, values, thresholds, K, rows_padded);
-    if (N <= 52) return launch_fused_nb52(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, values, thresholds, K, rows_padded);
-    if (N <= 56) return launch_fused_nb56(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, values, thresholds, K, rows_padded);
-    if (N <= 60) return launch_fused_nb60(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, values, thresholds, K, rows_padded);
-    if (N <= 64) return launch_fused_nb64(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, values, thresholds, K, rows_padded);
+    if (g_detector_split) {
+        if (G <= 0) return MITRE_ERR_INVALID;
+        if (n_windows <= 0) return MITRE_ERR_INVALID;
+        if (g_detector_split == 2) {
+            const int64_t bx = (int64_t)n_tasks_wt * N;
+            if (bx > 0x7fffffffll) return MITRE_ERR_UNSUPPORTED;
+            int by = (V + 2047) / 2048;   // up to 8 variables per thread along y
+            if (by > 65535) by = 65535;
+            values_flat_kernel<<<dim3((unsigned)bx, (unsigned)by), 256, 0, as_stream(stream)>>>(
+                series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, wdt, ld, group_base, slope_ok,
+                task_window, task_type, values);
+        } else if (g_detector_split != 3 &&
+                   (size_t)ld * 256 + sizeof(double) * 128 * (size_t)(N | 1) + 2 * resident_meta_bytes(N, ld) <=
+                       smem_optin()) {
+            // the whole sample axis of a 32-variable tile fits in shared memory
+            const size_t smem = (size_t)ld * 256 + sizeof(double) * 128 * (size_t)(N | 1) +
+                                2 * resident_meta_bytes(N, ld);
+            const int n_warps = N < 16 ? N : 16;                // warps take subjects dynamically
+            MITRE_CUDA_TRY(cudaFuncSetAttribute(values_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)smem));
+            const uint32_t magic_n = (uint32_t)((0x100000000ull + (uint64_t)N - 1) / (uint64_t)N);
+            // split the windows over blockIdx.y so that the grid fills whole waves of one block per SM
+            const int tiles = (V + 31) / 32, sms = sm_count();
+            int chunks = 1;
+            double best = 0.0;
+            for (int k = 1; k <= 16 && n_windows / k >= 8; ++k) {
+                const int64_t blocks = (int64_t)tiles * k;
+                const double fill = (double)blocks / (double)(ceil_div64(blocks, sms) * sms) - 0.004 * k;
+                if (fill > best) { best = fill; chunks = k; }
+            }
+            const int per_block = (n_windows + chunks - 1) / chunks;
+            chunks = (n_windows + per_block - 1) / per_block;
+            values_resident_kernel<<<dim3((unsigned)tiles, (unsigned)chunks), 32 * n_warps, smem, as_stream(stream)>>>(
+                series_t, vstride, N, V, n_windows, wlo, wcnt, wstart, winv_n, winv_sxx, wdt, ld, group_base,
+                slope_ok, magic_n, per_block, values);
+        } else {
+            const int n_vtiles = (V + 31) / 32;
+            const int64_t blocks = (int64_t)n_windows * n_vtiles;
+            if (blocks > 0x7fffffffll) return MITRE_ERR_UNSUPPORTED;
+            const int rounds = (N + 7) / 8;                     // subjects per warp
+            const int n_warps = (N + rounds - 1) / rounds;      // <= 8, so that the warps finish together
+            const size_t smem = sizeof(double) * 64 * (size_t)(N | 1);
+            values_tile_kernel<<<(unsigned)blocks, 32 * n_warps, smem, as_stream(stream)>>>(
+                series_t, vstride, N, V, n_vtiles, wlo, wcnt, wstart, winv_n, winv_sxx, wdt, ld, group_base,
+                slope_ok, values);
+        }
+        MITRE_LAUNCH_CHECK();
+    }
+    if (N <= 4) return launch_fused_nb4(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
+    if (N <= 8) return launch_fused_nb8(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
+    if (N <= 12) return launch_fused_nb12(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
+    if (N <= 16) return launch_fused_nb16(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
+    if (N <= 20) return launch_fused_nb20(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
+    if (N <= 24) return launch_fused_nb24(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
+    if (N <= 28) return launch_fused_nb28(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
+    if (N <= 32) return launch_fused_nb32(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
+    if (N <= 36) return launch_fused_nb36(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
+    if (N <= 40) return launch_fused_nb40(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
+    if (N <= 44) return launch_fused_nb44(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
+    if (N <= 48) return launch_fused_nb48(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
+    if (N <= 52) return launch_fused_nb52(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
+    if (N <= 56) return launch_fused_nb56(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
+    if (N <= 60) return launch_fused_nb60(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
+    if (N <= 64) return launch_fused_nb64(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
     return MITRE_ERR_UNSUPPORTED;
 }
 
@@ -180,7 +230,14 @@ extern "C" int mitre_densify_perm(void *stream, const int64_t *perm_padded, int6
     return MITRE_OK;
 }
 
-// Test / tuning hook: 1 = packed-key sorting network (default), 0 = value + id network.
+// Test / tuning hook: 1 = values kernel + sort/emit kernel (default), 0 = the single fused kernel.
+extern "C" int mitre_set_detector_split(int enable)
+{
+    g_detector_split = (enable >= 0 && enable <= 4) ? enable : 1;
+    return MITRE_OK;
+}
+
+// Test / tuning hook: 1 = packed-key sorting network, 0 = value + id network (default).
 extern "C" int mitre_set_fused_packed(int enable)
 {
     g_fused_packed = enable ? 1 : 0;

@@ -33,6 +33,7 @@
 namespace mitre {
 
 extern int g_fused_packed;   // 1: packed-key sorting network where it is instantiated (NB <= 40)
+extern int g_detector_split;  // see mitre_set_detector_split
 
 // ---- compile-time Batcher merge-exchange network for n inputs ------------------------------------
 template <int N>
@@ -230,7 +231,8 @@ struct Column {
     __device__ __forceinline__ double operator()(int j) const { return __ldg(base + (int64_t)j * stride); }
 };
 
-__device__ __forceinline__ double pw_leaf_col(const Column &x, int off, int n)
+template <class Col>
+__device__ __forceinline__ double pw_leaf_col(const Col &x, int off, int n)
 {
     if (n < 8) {
         double res = -0.0;
@@ -257,7 +259,8 @@ __device__ __forceinline__ double pw_leaf_col(const Column &x, int off, int n)
     return res;
 }
 
-static __device__ __noinline__ double pw_tree_col(const Column &x, int n)
+template <class Col>
+static __device__ __noinline__ double pw_tree_col(const Col &x, int n)
 {
     int st_off[40], st_n[40];
     bool st_open[40];
@@ -285,7 +288,8 @@ static __device__ __noinline__ double pw_tree_col(const Column &x, int n)
     return vals[0];
 }
 
-__device__ __forceinline__ double pairwise_sum_col(const Column &x, int n)
+template <class Col>
+__device__ __forceinline__ double pairwise_sum_col(const Col &x, int n)
 {
     return n <= 128 ? pw_leaf_col(x, 0, n) : pw_tree_col(x, n);
 }
@@ -583,6 +587,533 @@ fused_detectors_kernel(const double *__restrict__ series_t, int64_t vstride, int
                 for (int k2 = kcount; k2 < N - 1; ++k2) rg[k2] = make_ulonglong2(~0ull, ~0ull);
         }
     }
+}
+
+// =================================================================================================
+// Split path: (1) values with one thread per (window, type, subject, variable), (2) sort + emit
+// with one thread per group.  The value reduction is a short, occupancy-friendly kernel (no shared
+// memory, ~40 registers, coalesced reads of series_t with the 32 lanes on consecutive variables);
+// the sorting network then runs in a kernel that holds nothing but the group's values and ids.
+// Costs one re-read of values[G, N] (an output anyway) in exchange for much better latency hiding
+// than the single fused kernel, whose 220-register threads also carried the staging loop.
+// =================================================================================================
+#ifdef MITRE_FUSED_MAIN
+static __global__ void __launch_bounds__(256)
+values_flat_kernel(const double *__restrict__ series_t, int64_t vstride, int N, int V,
+                   const int32_t *__restrict__ wlo, const int32_t *__restrict__ wcnt,
+                   const int32_t *__restrict__ wstart, const double *__restrict__ winv_n,
+                   const double *__restrict__ winv_sxx, const double *__restrict__ wdt, int64_t ld,
+                   const int64_t *__restrict__ group_base, const uint8_t *__restrict__ slope_ok,
+                   const int32_t *__restrict__ task_window, const int8_t *__restrict__ task_type,
+                   double *__restrict__ values)
+{
+    // block = (window-type pair, subject, slab of variables)
+    const int wt = blockIdx.x / N, s = blockIdx.x % N;
+    const int w = task_window[wt];
+    const int type = task_type[wt];
+    const int nt = 1 + slope_ok[w];
+    const int n = wcnt[w * N + s];
+    const int lo_s = wlo[w * N + s];
+    const double inv_n = winv_n[w * N + s], inv_sxx = winv_sxx[w * N + s];
+    const double *dts = wdt + (int64_t)w * ld + wstart[w * N + s];
+    const int64_t gb = group_base[w] + (nt == 2 ? type : 0);
+    const double nd = (double)n;
+    for (int v = blockIdx.y * blockDim.x + threadIdx.x; v < V; v += gridDim.y * blockDim.x) {
+        const Column x{series_t + (int64_t)lo_s * vstride + v, vstride};
+        double val;
+        if (type == 1) {
+            val = div_small_int(pairwise_sum_col(x, n), nd, inv_n);
+        } else {
+            double sx = 0.0;
+            for (int j = 0; j < n; ++j) sx += x(j);
+            const double xb = sx * inv_n;
+            double sxy = 0.0;
+            for (int j = 0; j < n; ++j) sxy = fma(__ldg(dts + j), x(j) - xb, sxy);
+            val = sxy * inv_sxx;
+        }
+        values[(gb + (int64_t)v * nt) * N + s] = val;
+    }
+}
+
+
+// Tile variant of the values kernel: block = (window, tile of 32 variables), both detector types of
+// the window in one pass over the samples.  A warp takes one subject at a time with its 32 lanes on
+// consecutive variables (256-byte coalesced reads of series_t); results go through a shared-memory
+// tile [32 * nt][N] so that the block's slice of values -- which is one contiguous range of
+// 32 * nt * N doubles -- is written with full-line stores.  Windows of up to kTileCap samples keep
+// the samples in registers (all loads in flight at once); longer ones walk the column.
+constexpr int kTileCap = 16;
+
+// Mean (numpy pairwise order, pw_leaf_col for n <= 16) and centred least-squares slope of NN samples
+// held in registers; NN is a compile-time constant so that nothing is predicated off at run time.
+template <int NN, class Col, class Dt>
+__device__ __forceinline__ void window_stats(const Col &x, const Dt &dt, double inv_n, double inv_sxx,
+                                             bool with_slope, double &mean, double &slope)
+{
+    double xr[NN];
+#pragma unroll
+    for (int j = 0; j < NN; ++j) xr[j] = x(j);
+    double sum;
+    if (NN < 8) {
+        sum = -0.0;
+#pragma unroll
+        for (int j = 0; j < NN; ++j) sum = __dadd_rn(sum, xr[j]);
+    } else {
+        double r[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = (NN == 16) ? __dadd_rn(xr[k], xr[(8 + k) % NN]) : xr[k];
+        sum = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                        __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+        if (NN < 16) {
+#pragma unroll
+            for (int j = 8; j < NN; ++j) sum = __dadd_rn(sum, xr[j]);
+        }
+    }
+    mean = div_small_int(sum, (double)NN, inv_n);
+    if (with_slope) {
+        // sequential sum from +0.0; for NN < 8 that is the mean's sum except for the sign of a zero
+        double sx;
+        if (NN < 8) {
+            sx = __dadd_rn(sum, 0.0);
+        } else {
+            sx = 0.0;
+#pragma unroll
+            for (int j = 0; j < NN; ++j) sx = __dadd_rn(sx, xr[j]);
+        }
+        const double xb = __dmul_rn(sx, inv_n);
+        double sxy = 0.0;
+#pragma unroll
+        for (int j = 0; j < NN; ++j) sxy = __fma_rn(dt(j), __dadd_rn(xr[j], -xb), sxy);
+        slope = __dmul_rn(sxy, inv_sxx);
+    }
+}
+
+// all sample counts: compile-time specialisations up to kTileCap, the column walk beyond
+template <class Col, class Dt>
+__device__ __forceinline__ void window_stats_any(int n, const Col &x, const Dt &dt, double inv_n, double inv_sxx,
+                                                 bool ws, double &mean, double &slope)
+{
+#define MITRE_WS(NN) case NN: window_stats<NN>(x, dt, inv_n, inv_sxx, ws, mean, slope); break;
+    if (n >= 1 && n <= kTileCap) {
+        switch (n) {
+            MITRE_WS(1) MITRE_WS(2) MITRE_WS(3) MITRE_WS(4) MITRE_WS(5) MITRE_WS(6) MITRE_WS(7) MITRE_WS(8)
+            MITRE_WS(9) MITRE_WS(10) MITRE_WS(11) MITRE_WS(12) MITRE_WS(13) MITRE_WS(14) MITRE_WS(15)
+            MITRE_WS(16)
+        default: break;
+        }
+    } else {
+        mean = div_small_int(pairwise_sum_col(x, n), (double)n, inv_n);
+        if (ws) {
+            double sx = 0.0;
+            for (int j = 0; j < n; ++j) sx = __dadd_rn(sx, x(j));
+            const double xb = __dmul_rn(sx, inv_n);
+            double sxy = 0.0;
+            for (int j = 0; j < n; ++j) sxy = __fma_rn(dt(j), __dadd_rn(x(j), -xb), sxy);
+            slope = __dmul_rn(sxy, inv_sxx);
+        }
+    }
+#undef MITRE_WS
+}
+
+struct LdgVec {
+    const double *p;
+    __device__ __forceinline__ double operator()(int j) const { return __ldg(p + j); }
+};
+struct SmemCol32 {   // column of a [rows][32] shared-memory tile
+    const double *p;
+    __device__ __forceinline__ double operator()(int j) const { return p[j * 32]; }
+};
+struct SmemVec {
+    const double *p;
+    __device__ __forceinline__ double operator()(int j) const { return p[j]; }
+};
+
+static __global__ void __launch_bounds__(256)
+values_tile_kernel(const double *__restrict__ series_t, int64_t vstride, int N, int V, int n_vtiles,
+                   const int32_t *__restrict__ wlo, const int32_t *__restrict__ wcnt,
+                   const int32_t *__restrict__ wstart, const double *__restrict__ winv_n,
+                   const double *__restrict__ winv_sxx, const double *__restrict__ wdt, int64_t ld,
+                   const int64_t *__restrict__ group_base, const uint8_t *__restrict__ slope_ok,
+                   double *__restrict__ values)
+{
+    extern __shared__ double tile[];   // [32 * nt][Np], Np = N | 1
+    const int w = blockIdx.x / n_vtiles, vt = blockIdx.x % n_vtiles;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const int Np = N | 1;
+    const int nt = 1 + slope_ok[w];
+    const int v0 = vt * 32;
+    const int v = min(v0 + lane, V - 1);   // lanes past V recompute the last variable; never stored
+    for (int s = warp; s < N; s += n_warps) {
+        const int n = __ldg(wcnt + w * N + s);
+        const int lo_s = __ldg(wlo + w * N + s);
+        const double inv_n = __ldg(winv_n + w * N + s);
+        const double *px = series_t + (int64_t)lo_s * vstride + v;
+        const double *dts = wdt + (int64_t)w * ld + __ldg(wstart + w * N + s);
+        double mean = 0.0, slope = 0.0;
+        window_stats_any(n, Column{px, vstride}, LdgVec{dts}, inv_n, __ldg(winv_sxx + w * N + s), nt == 2, mean,
+                         slope);
+        tile[(lane * nt + (nt - 1)) * Np + s] = mean;
+        if (nt == 2) tile[(lane * 2) * Np + s] = slope;
+    }
+    __syncthreads();
+    const int n_rows = min(32, V - v0) * nt;
+    double *out = values + (group_base[w] + (int64_t)v0 * nt) * N;
+    for (int r = warp; r < n_rows; r += n_warps)
+        for (int s = lane; s < N; s += 32) out[(int64_t)r * N + s] = tile[r * Np + s];
+}
+
+// Resident variant: block = tile of 32 variables for ALL windows.  The tile's samples
+// [S rows][32 variables] are loaded into shared memory once, so series_t is read from HBM exactly
+// once; windows then run back to back out of shared memory.  Per window, the warps split the
+// subjects, results go to one of two staging tiles, and after the single barrier of the iteration
+// the block streams the finished tile (a contiguous range of values) to HBM.  The per-window
+// tables (lo, cnt, start, 1/n, 1/sxx, centred times) are prefetched one window ahead with cp.async.
+__device__ __forceinline__ void cp_async4(void *dst_smem, const void *src_gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem));
+}
+
+struct ResidentMeta {
+    double *inv_n, *inv_sxx, *dt;
+    int32_t *lo, *cnt, *start;
+};
+
+__device__ __forceinline__ ResidentMeta resident_meta(char *base, int N, int64_t ld)
+{
+    ResidentMeta m;
+    m.inv_n = reinterpret_cast<double *>(base);
+    m.inv_sxx = m.inv_n + N;
+    m.dt = m.inv_sxx + N;
+    m.lo = reinterpret_cast<int32_t *>(m.dt + ld);
+    m.cnt = m.lo + N;
+    m.start = m.cnt + N;
+    return m;
+}
+
+__host__ __device__ inline size_t resident_meta_bytes(int N, int64_t ld)
+{
+    return (sizeof(double) * (2 * (size_t)N + (size_t)ld) + sizeof(int32_t) * 3 * (size_t)N + 15) & ~(size_t)15;
+}
+
+__device__ __forceinline__ void resident_prefetch(const ResidentMeta m, int w, int N, int S, int64_t ld,
+                                                  const int32_t *__restrict__ wlo, const int32_t *__restrict__ wcnt,
+                                                  const int32_t *__restrict__ wstart,
+                                                  const double *__restrict__ winv_n,
+                                                  const double *__restrict__ winv_sxx, const double *__restrict__ wdt)
+{
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int64_t o = (int64_t)w * N;
+    for (int i = tid; i < N; i += nthr) {
+        cp_async8(m.inv_n + i, winv_n + o + i);
+        cp_async8(m.inv_sxx + i, winv_sxx + o + i);
+        cp_async4(m.lo + i, wlo + o + i);
+        cp_async4(m.cnt + i, wcnt + o + i);
+        cp_async4(m.start + i, wstart + o + i);
+    }
+    const double *src = wdt + (int64_t)w * ld;
+    for (int i = tid; i < S; i += nthr) cp_async8(m.dt + i, src + i);
+}
+
+static __global__ void __launch_bounds__(512, 1)
+values_resident_kernel(const double *__restrict__ series_t, int64_t vstride, int N, int V, int W,
+                       const int32_t *__restrict__ wlo, const int32_t *__restrict__ wcnt,
+                       const int32_t *__restrict__ wstart, const double *__restrict__ winv_n,
+                       const double *__restrict__ winv_sxx, const double *__restrict__ wdt, int64_t ld,
+                       const int64_t *__restrict__ group_base, const uint8_t *__restrict__ slope_ok,
+                       uint32_t magic_n, int windows_per_block, double *__restrict__ values)
+{
+    extern __shared__ __align__(16) double rsm[];
+    __shared__ int next_subject[2];
+    const int S = (int)ld;
+    const int Np = N | 1;
+    double *ser = rsm;                                   // [S][32]
+    double *stage = ser + (size_t)S * 32;                // [2][64 * Np]
+    char *meta_base = reinterpret_cast<char *>(stage + 2 * 64 * Np);
+    const size_t meta_bytes = resident_meta_bytes(N, ld);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = blockDim.x >> 5;
+    const int v0 = blockIdx.x * 32;
+    const int vc = min(v0 + lane, V - 1);
+
+    const int w_begin = blockIdx.y * windows_per_block, w_end = min(W, w_begin + windows_per_block);
+    if (tid < 2) next_subject[tid] = 0;
+    resident_prefetch(resident_meta(meta_base, N, ld), w_begin, N, S, ld, wlo, wcnt, wstart, winv_n, winv_sxx, wdt);
+    for (int r = warp; r < S; r += n_warps) cp_async8(ser + r * 32 + lane, series_t + (int64_t)r * vstride + vc);
+    cp_async_wait_all();
+    __syncthreads();
+
+    for (int w = w_begin; w < w_end; ++w) {
+        const int b = (w - w_begin) & 1;
+        if (w + 1 < w_end)
+            resident_prefetch(resident_meta(meta_base + (b ^ 1) * meta_bytes, N, ld), w + 1, N, S, ld, wlo, wcnt,
+                              wstart, winv_n, winv_sxx, wdt);
+        if (tid == 0) next_subject[b ^ 1] = 0;   // last used two barriers ago
+        const ResidentMeta m = resident_meta(meta_base + b * meta_bytes, N, ld);
+        double *st = stage + b * 64 * Np;
+        const int nt = 1 + slope_ok[w];
+        // warps take subjects as they come free: sample counts differ a lot between subjects
+        for (;;) {
+            int s = 0;
+            if (lane == 0) s = atomicAdd(&next_subject[b], 1);
+            s = __shfl_sync(0xffffffffu, s, 0);
+            if (s >= N) break;
+            const int n = m.cnt[s];
+            double mean = 0.0, slope = 0.0;
+            window_stats_any(n, SmemCol32{ser + m.lo[s] * 32 + lane}, SmemVec{m.dt + m.start[s]}, m.inv_n[s],
+                             m.inv_sxx[s], nt == 2, mean, slope);
+            st[(lane * nt + (nt - 1)) * Np + s] = mean;
+            if (nt == 2) st[(lane * 2) * Np + s] = slope;
+        }
+        cp_async_wait_all();
+        __syncthreads();
+        // stream the finished tile out: rows [0, n_rows) x N of the staging tile are one contiguous
+        // range of values
+        const int n_out = min(32, V - v0) * nt * N;
+        double *out = values + (group_base[w] + (int64_t)v0 * nt) * N;
+        for (int i = tid; i < n_out; i += blockDim.x) {
+            const int r = (int)__umulhi((uint32_t)i, magic_n);   // i / N
+            out[i] = st[r * Np + (i - r * N)];
+        }
+    }
+}
+#endif  // MITRE_FUSED_MAIN
+
+template <int NB, int THREADS, int MINB, bool SYNC>
+__global__ void __launch_bounds__(THREADS, MINB)
+sort_emit_kernel(const double *__restrict__ values, int64_t G, int N, double *__restrict__ thresholds,
+                 int32_t *__restrict__ K, uint64_t *__restrict__ rows)
+{
+    const int L = 2 * (N - 1);
+    const uint64_t valid = ~0ull << (64 - N);
+    const int64_t stride = (int64_t)gridDim.x * THREADS;
+    for (int64_t base = (int64_t)blockIdx.x * THREADS; base < G; base += stride) {
+        if (SYNC) __syncthreads();   // keeps the block's warps on the same stretch of this long code
+        const int64_t g = base + threadIdx.x;
+        if (g >= G) continue;
+        const double *vg = values + g * N;
+        double val[NB];
+        int id[NB];
+#pragma unroll
+        for (int s = 0; s < NB; ++s) {
+            id[s] = s;
+            val[s] = (s < N) ? __ldg(vg + s) : INFINITY;
+        }
+        run_network<NB>(val, id, std::make_index_sequence<NetHolder<NB>::net.count>{});
+        int kcount = 0;
+        {
+            double *tg = thresholds + g * (N - 1);
+            double prev = 0.0;
+#pragma unroll
+            for (int k = 0; k < NB - 1; ++k) {
+                if (k < N - 1) {
+                    const double m = __dmul_rn(0.5, __dadd_rn(val[k], val[k + 1]));
+                    const bool u = (k == 0) || (m != prev);
+                    if (u) tg[kcount] = m;
+                    kcount += u;
+                    prev = m;
+                }
+            }
+            for (int k2 = kcount; k2 < N - 1; ++k2) tg[k2] = 0.0;
+            K[g] = kcount;
+        }
+        {
+            ulonglong2 *rg = reinterpret_cast<ulonglong2 *>(rows + g * L);
+            uint64_t acc = 0, Tn = 0;
+            int pos = kcount - 1;
+#pragma unroll
+            for (int k = NB - 1; k >= 0; --k) {
+                if (k == N - 1) {
+                    acc = 1ull << (63 - id[k]);
+                    Tn = 0;
+                } else if (k < N - 1) {
+                    const double m = __dmul_rn(0.5, __dadd_rn(val[k], val[k + 1]));
+                    bool uniq = true;
+                    if (k > 0) uniq = m != __dmul_rn(0.5, __dadd_rn(val[k - 1], val[k]));
+                    const uint64_t above = (m == val[k + 1]) ? Tn : acc;
+                    if (uniq) rg[pos] = make_ulonglong2(above, ~above & valid);
+                    pos -= uniq;
+                    Tn = (val[k] == val[k + 1]) ? Tn : acc;
+                    acc |= 1ull << (63 - id[k]);
+                }
+            }
+            for (int k2 = kcount; k2 < N - 1; ++k2) rg[k2] = make_ulonglong2(~0ull, ~0ull);
+        }
+    }
+}
+
+// Staged variant of sort_emit_kernel: one thread still owns one group, but nothing it reads or
+// writes goes to global memory directly.  A block of kStageThreads groups bulk-loads its slice of
+// values (one contiguous range) into shared memory through the TMA unit, every thread sorts and
+// emits into its own rows of two shared-memory tiles, and thread 0 hands the finished tiles --
+// again contiguous ranges of thresholds[] and rows[] -- back to the TMA unit as two bulk stores
+// that drain while the block's next tile is loaded and sorted.  Per-thread strided 8/16-byte
+// global accesses (32 sectors per warp instruction, the L2 request rate that bounded the direct
+// version) become full-line transfers.
+constexpr int kStageThreads = 128;
+
+__host__ __device__ inline size_t sort_emit_stage_bytes(int N)
+{
+    return (size_t)kStageThreads * 3 * (size_t)(N - 1) * 8;
+}
+
+template <int NB>
+__global__ void __launch_bounds__(kStageThreads, (NB <= 40) ? 2 : 1)
+sort_emit_staged_kernel(const double *__restrict__ values, int64_t G, int N, double *__restrict__ thresholds,
+                        int32_t *__restrict__ K, uint64_t *__restrict__ rows)
+{
+    extern __shared__ __align__(128) unsigned char stage_smem[];
+    __shared__ uint64_t bar;
+    constexpr int T = kStageThreads;
+    const int L = 2 * (N - 1);
+    const int tid = threadIdx.x;
+    uint64_t *srow = reinterpret_cast<uint64_t *>(stage_smem);      // [T][L]; the values tile on the way in
+    double *sthr = reinterpret_cast<double *>(srow + (size_t)T * L);   // [T][N-1]
+    const uint64_t valid = ~0ull << (64 - N);
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+    const int64_t n_tiles = ceil_div64(G, T);
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t g0 = tile * T;
+        const int cnt = (int)((G - g0 < T) ? (G - g0) : T);
+        const bool full = cnt == T;
+        // ---- values tile -> shared memory ----
+        if (full) {
+            if (tid == 0) {
+                bulk_wait_read0();   // the previous tile's stores have let go of the buffers
+                mbar_arrive_expect_tx(&bar, (uint32_t)(T * N * 8));
+                bulk_g2s(srow, values + g0 * N, (uint32_t)(T * N * 8), &bar);
+            }
+            mbar_wait(&bar, phase);
+            phase ^= 1;
+        } else {
+            if (tid == 0) bulk_wait_read0();
+            __syncthreads();
+            double *vin_all = reinterpret_cast<double *>(srow);
+            for (int i = tid; i < cnt * N; i += T) vin_all[i] = values[g0 * N + i];
+            __syncthreads();
+        }
+        double val[NB];
+        int id[NB];
+        {
+            const double *vin = reinterpret_cast<const double *>(srow) + tid * N;
+#pragma unroll
+            for (int s = 0; s < NB; ++s) {
+                id[s] = s;
+                val[s] = (s < N && tid < cnt) ? vin[s] : INFINITY;
+            }
+        }
+        __syncthreads();   // every thread holds its values: the tile may be overwritten with rows
+        run_network<NB>(val, id, std::make_index_sequence<NetHolder<NB>::net.count>{});
+        int kcount = 0;
+        {
+            double *tg = sthr + tid * (N - 1);
+            double prev = 0.0;
+#pragma unroll
+            for (int k = 0; k < NB - 1; ++k) {
+                if (k < N - 1) {
+                    const double m = __dmul_rn(0.5, __dadd_rn(val[k], val[k + 1]));
+                    const bool u = (k == 0) || (m != prev);
+                    if (u) tg[kcount] = m;
+                    kcount += u;
+                    prev = m;
+                }
+            }
+            for (int k2 = kcount; k2 < N - 1; ++k2) tg[k2] = 0.0;
+            if (tid < cnt) K[g0 + tid] = kcount;
+        }
+        {
+            ulonglong2 *rg = reinterpret_cast<ulonglong2 *>(srow + (size_t)tid * L);
+            uint64_t acc = 0, Tn = 0;
+            int pos = kcount - 1;
+#pragma unroll
+            for (int k = NB - 1; k >= 0; --k) {
+                if (k == N - 1) {
+                    acc = 1ull << (63 - id[k]);
+                    Tn = 0;
+                } else if (k < N - 1) {
+                    const double m = __dmul_rn(0.5, __dadd_rn(val[k], val[k + 1]));
+                    bool uniq = true;
+                    if (k > 0) uniq = m != __dmul_rn(0.5, __dadd_rn(val[k - 1], val[k]));
+                    const uint64_t above = (m == val[k + 1]) ? Tn : acc;
+                    if (uniq) rg[pos] = make_ulonglong2(above, ~above & valid);
+                    pos -= uniq;
+                    Tn = (val[k] == val[k + 1]) ? Tn : acc;
+                    acc |= 1ull << (63 - id[k]);
+                }
+            }
+            for (int k2 = kcount; k2 < N - 1; ++k2) rg[k2] = make_ulonglong2(~0ull, ~0ull);
+        }
+        // ---- finished tiles -> global ----
+        if (full) {
+            fence_async_smem();
+            __syncthreads();
+            if (tid == 0) {
+                bulk_s2g(rows + g0 * L, srow, (uint32_t)(T * L * 8));
+                bulk_s2g(thresholds + g0 * (N - 1), sthr, (uint32_t)(T * (N - 1) * 8));
+                bulk_commit();
+            }
+        } else {
+            __syncthreads();
+            for (int i = tid; i < cnt * L; i += T) rows[g0 * L + i] = srow[i];
+            for (int i = tid; i < cnt * (N - 1); i += T) thresholds[g0 * (N - 1) + i] = sthr[i];
+        }
+    }
+    if (tid == 0) bulk_wait0();
+}
+
+template <int NB>
+static int launch_sort_emit_staged(cudaStream_t st, const double *values, int64_t G, int N, double *thresholds,
+                                   int32_t *K, uint64_t *rows)
+{
+    auto kern = sort_emit_staged_kernel<NB>;
+    const size_t smem = sort_emit_stage_bytes(N);
+    MITRE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    MITRE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kStageThreads, smem));
+    if (per_sm < 1) return MITRE_ERR_UNSUPPORTED;
+    int64_t blocks = (int64_t)sm_count() * per_sm;
+    const int64_t need = ceil_div64(G, kStageThreads);
+    if (need < blocks) blocks = need;
+    if (blocks < 1) blocks = 1;
+    kern<<<(unsigned)blocks, kStageThreads, smem, st>>>(values, G, N, thresholds, K, rows);
+    MITRE_LAUNCH_CHECK();
+    return MITRE_OK;
+}
+
+template <int NB, int THREADS, int MINB, bool SYNC>
+static int launch_sort_emit(cudaStream_t st, const double *values, int64_t G, int N, double *thresholds,
+                            int32_t *K, uint64_t *rows)
+{
+    auto kern = sort_emit_kernel<NB, THREADS, MINB, SYNC>;
+    int per_sm = 1;
+    MITRE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, 0));
+    if (per_sm < 1) return MITRE_ERR_UNSUPPORTED;
+    int64_t blocks = (int64_t)sm_count() * per_sm;
+    const int64_t need = ceil_div64(G, THREADS);
+    if (need < blocks) blocks = need;
+    if (blocks < 1) blocks = 1;
+    kern<<<(unsigned)blocks, THREADS, 0, st>>>(values, G, N, thresholds, K, rows);
+    MITRE_LAUNCH_CHECK();
+    return MITRE_OK;
+}
+
+template <int NB>
+static int launch_split_impl(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
+                             const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
+                             const double *winv_n, const double *winv_sxx, const int32_t *widx,
+                             const double *wdt, int64_t ld, const int64_t *group_base,
+                             const uint8_t *slope_ok, const int32_t *task_window, const int8_t *task_type,
+                             int n_wt, int64_t G, double *values, double *thresholds, int32_t *K,
+                             uint64_t *rows)
+{
+    (void)widx;
+    (void)series_t; (void)vstride; (void)V; (void)wlo; (void)wcnt; (void)wstart; (void)winv_n; (void)winv_sxx;
+    (void)wdt; (void)ld; (void)group_base; (void)slope_ok; (void)task_window; (void)task_type; (void)n_wt;
+    if (g_detector_split == 4) return launch_sort_emit<NB, 256, 1, false>(st, values, G, N, thresholds, K, rows);
+    return launch_sort_emit_staged<NB>(st, values, G, N, thresholds, K, rows);
 }
 
 template <int NB, bool PACKED>

@@ -295,7 +295,8 @@ def detectors_fused(series_t, N, V, lists, group_base, slope_ok, task_window, ta
                                       _p(lists['lo']), _p(lists['cnt']), _p(lists['start']),
                                       _p(lists['inv_n']), _p(lists['inv_sxx']), _p(lists['idx']),
                                       _p(lists['dt']), lists['ld'], _p(group_base), _p(slope_ok),
-                                      _p(task_window), _p(task_type), task_window.shape[0], _p(values),
+                                      _p(task_window), _p(task_type), task_window.shape[0],
+                                      lists['lo'].shape[0], int(G), _p(values),
                                       _p(thresholds), _p(K), _p(rows)), "mitre_detectors_fused")
     return values, thresholds, K, rows
 

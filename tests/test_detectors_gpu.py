@@ -15,11 +15,14 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
 def build_gpu_population(d, pop_cfg, fused=True):
-    """fused=True: single-launch thread-per-group kernel (N <= 63), value + id network (default);
-    "packed": same kernel with the packed-key network (N <= 40); False: phase-by-phase kernels."""
+    """fused=True: the default device path (N <= 63): values kernel + staged sort/emit kernel;
+    "tile" / "flat": other values kernels; "direct": sort/emit without shared-memory staging;
+    "single": the one-kernel variant; "packed": that kernel with the packed-key network (N <= 40);
+    False: phase-by-phase kernels (any N)."""
     from mitre_b200 import rules as R
     from mitre_b200._lib import lib
     lib().mitre_set_fused_packed(1 if fused == "packed" else 0)
+    lib().mitre_set_detector_split({"single": 0, "packed": 0, "flat": 2, "tile": 3, "direct": 4}.get(fused, 1))
     fused = bool(fused)
     V = d["X"][0].shape[0]
     data = R.Dataset(d["X"], d["T"], d["y"], ["v%d" % i for i in range(V)], d["variable_weights"],
@@ -67,7 +70,7 @@ def check_population(pop, gold_windows, gold_ok, gold_groups, gold_values, gold_
         assert np.array_equal(pop.truth_table[t], DO.unpack_rows(gold_packed[i:i + 1], N)[0])
 
 
-@pytest.mark.parametrize("fused", [True, "packed", False])
+@pytest.mark.parametrize("fused", [True, "tile", "flat", "direct", "single", "packed", False])
 @pytest.mark.parametrize("name", sorted(MG.DETECTOR_CASES))
 def test_population_vs_reference_golden(name, fused):
     cfg = MG.DETECTOR_CASES[name]
@@ -84,7 +87,7 @@ def test_population_vs_reference_golden(name, fused):
     assert np.array_equal(pop.flat_truth, DO.unpack_rows(gold["sorted_truth_packed"], N))
 
 
-@pytest.mark.parametrize("fused", [True, "packed", False])
+@pytest.mark.parametrize("fused", [True, "tile", "flat", "direct", "single", "packed", False])
 @pytest.mark.parametrize("N,V,T,nint", [(2, 3, (2, 3), 1), (3, 2, (2, 4), 2), (8, 40, (3, 6), 3), (9, 33, (3, 6), 3),
                                         (16, 3, (2, 5), 2), (24, 2, (3, 5), 2), (33, 5, (3, 20), 6),
                                         (40, 70, (3, 7), 2), (41, 2, (3, 7), 2), (48, 3, (3, 7), 2),
@@ -211,7 +214,7 @@ def test_exact_division_selftest():
     assert np.array_equal(exact, a / n)
 
 
-@pytest.mark.parametrize("fused", [True, "packed", False])
+@pytest.mark.parametrize("fused", [True, "tile", "flat", "direct", "single", "packed", False])
 def test_near_ties_below_key_resolution_take_the_exact_path(fused):
     """Values that differ only in their lowest mantissa bits collide in the packed sort key (value
     bits with the subject id in the low 6 bits); the kernel must detect the mis-ordered neighbours

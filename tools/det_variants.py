@@ -1,0 +1,42 @@
+"""Times the detector-evaluation launch variants on the S5 bench population (GPU box only).
+usage: python tools/det_variants.py [V]"""
+import sys
+import types
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+import bench  # noqa: E402
+from mitre_b200 import device as D  # noqa: E402
+from mitre_b200._lib import lib  # noqa: E402
+
+
+def main():
+    V = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
+    sys.argv = sys.argv[:1]
+    args = bench.parse_args()
+    args.variables = V
+    data, pop, marks = bench.build_population(args, 0, torch)
+    fa = pop._fused_args
+
+    def run(split):
+        lib().mitre_set_detector_split(split)
+        out = D.detectors_fused(*fa)
+        ms = min(bench.cuda_time_ms(torch, lambda: D.detectors_fused(*fa), 10) for _ in range(3))
+        return out, ms
+
+    for _ in range(100):    # clocks up
+        D.detectors_fused(*fa)
+    ref, ms0 = run(0)
+    print("single fused kernel: %.3f ms" % ms0)
+    for split, name in ((2, "flat values + staged sort/emit"), (3, "tile values + staged sort/emit"),
+                        (4, "default values + direct sort/emit"), (1, "default")):
+        out, ms = run(split)
+        same = all(torch.equal(a, b) for a, b in zip(ref, out))
+        print("%-36s %.3f ms  identical=%s" % (name, ms, same))
+    lib().mitre_set_detector_split(1)
+
+
+if __name__ == "__main__":
+    main()
