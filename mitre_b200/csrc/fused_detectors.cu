@@ -233,7 +233,7 @@ extern "C" int mitre_densify_perm(void *stream, const int64_t *perm_padded, int6
 // Test / tuning hook: 1 = values kernel + sort/emit kernel (default), 0 = the single fused kernel.
 extern "C" int mitre_set_detector_split(int enable)
 {
-    g_detector_split = (enable >= 0 && enable <= 4) ? enable : 1;
+    g_detector_split = (enable >= 0 && enable <= 5) ? enable : 1;
     return MITRE_OK;
 }
 

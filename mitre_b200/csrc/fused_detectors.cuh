@@ -102,6 +102,61 @@ __device__ __forceinline__ void run_network_u64(uint64_t (&k)[N], std::index_seq
     (cmp_exchange_u64(k[NetHolder<N>::net.a[I]], k[NetHolder<N>::net.b[I]]), ...);
 }
 
+// ---- 32-bit key variant: sort keys = order-preserving bits of the value rounded toward zero to
+// float32, with the subject id in the low 6 bits.  A compare-exchange is one unsigned min and one
+// max (2 instructions instead of 7, one register per element instead of three).  The key orders
+// every pair whose float32 images differ above their 6 lowest mantissa bits; exact values are then
+// fetched by id and the few groups with a mis-ordered near-tie are repaired by odd-even
+// transposition passes on the exact (value, id) pairs.
+__device__ __forceinline__ uint32_t sort_key32(double v, int s)
+{
+    uint32_t u = __float_as_uint(__double2float_rz(v));
+    u ^= (uint32_t)((int32_t)u >> 31) | 0x80000000u;
+    return (u & ~63u) | (uint32_t)s;
+}
+
+__device__ __forceinline__ void cmp_exchange_u32(uint32_t &x, uint32_t &y)
+{
+    const uint32_t lo = min(x, y), hi = max(x, y);
+    x = lo; y = hi;
+}
+
+template <int N, size_t... I>
+__device__ __forceinline__ void run_network_u32(uint32_t (&k)[N], std::index_sequence<I...>)
+{
+    (cmp_exchange_u32(k[NetHolder<N>::net.a[I]], k[NetHolder<N>::net.b[I]]), ...);
+}
+
+// Sorted (value, id) pairs of one group from its values row `vin` (shared memory, N doubles).
+template <int NB>
+__device__ __forceinline__ void sort_group_key32(const double *vin, int N, double (&val)[NB], int (&id)[NB])
+{
+    uint32_t key[NB];
+#pragma unroll
+    for (int s = 0; s < NB; ++s) key[s] = (s < N) ? sort_key32(vin[s], s) : (0xFFFFFFC0u | (uint32_t)s);
+    run_network_u32<NB>(key, std::make_index_sequence<NetHolder<NB>::net.count>{});
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+        id[k] = (int)(key[k] & 63u);
+        val[k] = (k < N) ? vin[id[k]] : INFINITY;
+        if (k > 0 && k < N) bad |= val[k - 1] > val[k];
+    }
+    while (bad) {   // rare: near-ties below the key's resolution
+        bad = false;
+#pragma unroll
+        for (int par = 0; par < 2; ++par) {
+#pragma unroll
+            for (int k = par; k + 1 < NB; k += 2) {
+                if (k + 1 < N) {
+                    bad |= val[k] > val[k + 1];
+                    cmp_exchange(val[k], val[k + 1], id[k], id[k + 1]);
+                }
+            }
+        }
+    }
+}
+
 // Generic (any N <= 64) thresholds + rows for one group from its values column in shared memory
 // and a scratch column of subject ids, presorted or not: insertion sort by exact value, then the
 // same two passes as the register path.  Rare path; correctness over speed.
@@ -941,32 +996,35 @@ sort_emit_kernel(const double *__restrict__ values, int64_t G, int N, double *__
 }
 
 // Staged variant of sort_emit_kernel: one thread still owns one group, but nothing it reads or
-// writes goes to global memory directly.  A block of kStageThreads groups bulk-loads its slice of
-// values (one contiguous range) into shared memory through the TMA unit, every thread sorts and
-// emits into its own rows of two shared-memory tiles, and thread 0 hands the finished tiles --
-// again contiguous ranges of thresholds[] and rows[] -- back to the TMA unit as two bulk stores
-// that drain while the block's next tile is loaded and sorted.  Per-thread strided 8/16-byte
-// global accesses (32 sectors per warp instruction, the L2 request rate that bounded the direct
-// version) become full-line transfers.
-constexpr int kStageThreads = 128;
+// writes goes to global memory with a per-thread stride.  A block of kStageThreads groups
+// bulk-loads its slice of values (one contiguous range) into shared memory through the TMA unit;
+// every thread sorts its group by 32-bit keys, re-reads the exact values in sorted order and emits
+// thresholds and the `above` row of every threshold into its own rows of two shared-memory tiles.
+// The thresholds tile goes back as one bulk store; the rows tile is expanded to (above, below)
+// pairs on the way out, 16 bytes per thread with consecutive threads on consecutive addresses.
+// Per-thread strided 8/16-byte global accesses (32 sectors per warp instruction -- the L2 request
+// rate that bounded the direct version) become full-line transfers, and keeping only one row of
+// each pair on chip leaves room for six blocks per SM.
+constexpr int kStageThreads = 64;
 
 __host__ __device__ inline size_t sort_emit_stage_bytes(int N)
 {
-    return (size_t)kStageThreads * 3 * (size_t)(N - 1) * 8;
+    return (size_t)kStageThreads * (2 * (size_t)N - 1) * 8;   // [T][N] values / above rows + [T][N-1] thresholds
 }
 
 template <int NB>
-__global__ void __launch_bounds__(kStageThreads, (NB <= 40) ? 2 : 1)
+__global__ void __launch_bounds__(kStageThreads, (NB <= 40) ? 6 : 3)
 sort_emit_staged_kernel(const double *__restrict__ values, int64_t G, int N, double *__restrict__ thresholds,
-                        int32_t *__restrict__ K, uint64_t *__restrict__ rows)
+                        int32_t *__restrict__ K, uint64_t *__restrict__ rows, int dry)
 {
     extern __shared__ __align__(128) unsigned char stage_smem[];
     __shared__ uint64_t bar;
     constexpr int T = kStageThreads;
-    const int L = 2 * (N - 1);
+    const int M = N - 1;
     const int tid = threadIdx.x;
-    uint64_t *srow = reinterpret_cast<uint64_t *>(stage_smem);      // [T][L]; the values tile on the way in
-    double *sthr = reinterpret_cast<double *>(srow + (size_t)T * L);   // [T][N-1]
+    double *sval = reinterpret_cast<double *>(stage_smem);            // [T][N] on the way in
+    uint64_t *sabove = reinterpret_cast<uint64_t *>(stage_smem);      // [T][M] on the way out (same bytes)
+    double *sthr = sval + (size_t)T * N;                              // [T][M]
     const uint64_t valid = ~0ull << (64 - N);
     if (tid == 0) {
         mbar_init(&bar, 1);
@@ -982,84 +1040,82 @@ sort_emit_staged_kernel(const double *__restrict__ values, int64_t G, int N, dou
         // ---- values tile -> shared memory ----
         if (full) {
             if (tid == 0) {
-                bulk_wait_read0();   // the previous tile's stores have let go of the buffers
                 mbar_arrive_expect_tx(&bar, (uint32_t)(T * N * 8));
-                bulk_g2s(srow, values + g0 * N, (uint32_t)(T * N * 8), &bar);
+                bulk_g2s(sval, values + g0 * N, (uint32_t)(T * N * 8), &bar);
             }
             mbar_wait(&bar, phase);
             phase ^= 1;
         } else {
-            if (tid == 0) bulk_wait_read0();
-            __syncthreads();
-            double *vin_all = reinterpret_cast<double *>(srow);
-            for (int i = tid; i < cnt * N; i += T) vin_all[i] = values[g0 * N + i];
+            for (int i = tid; i < cnt * N; i += T) sval[i] = values[g0 * N + i];
             __syncthreads();
         }
         double val[NB];
         int id[NB];
-        {
-            const double *vin = reinterpret_cast<const double *>(srow) + tid * N;
-#pragma unroll
-            for (int s = 0; s < NB; ++s) {
-                id[s] = s;
-                val[s] = (s < N && tid < cnt) ? vin[s] : INFINITY;
-            }
-        }
-        __syncthreads();   // every thread holds its values: the tile may be overwritten with rows
-        run_network<NB>(val, id, std::make_index_sequence<NetHolder<NB>::net.count>{});
+        // threads past the end of the last tile sort whatever the buffer holds; nothing of it is stored
+        sort_group_key32<NB>(sval + tid * N, N, val, id);
+        if (tid == 0) bulk_wait_read0();   // the previous tile's thresholds have left their buffer
+        __syncthreads();                   // every thread holds its values: their tile becomes the rows tile
+        if (!dry) {
         int kcount = 0;
         {
-            double *tg = sthr + tid * (N - 1);
+            double *tg = sthr + tid * M;
             double prev = 0.0;
 #pragma unroll
             for (int k = 0; k < NB - 1; ++k) {
-                if (k < N - 1) {
+                if (k < M) {
                     const double m = __dmul_rn(0.5, __dadd_rn(val[k], val[k + 1]));
                     const bool u = (k == 0) || (m != prev);
-                    if (u) tg[kcount] = m;
+                    tg[kcount] = m;   // a repeated midpoint is overwritten by its successor
                     kcount += u;
                     prev = m;
                 }
             }
-            for (int k2 = kcount; k2 < N - 1; ++k2) tg[k2] = 0.0;
+            for (int k2 = kcount; k2 < M; ++k2) tg[k2] = 0.0;
             if (tid < cnt) K[g0 + tid] = kcount;
         }
         {
-            ulonglong2 *rg = reinterpret_cast<ulonglong2 *>(srow + (size_t)tid * L);
+            uint64_t *rg = sabove + (size_t)tid * M;
             uint64_t acc = 0, Tn = 0;
             int pos = kcount - 1;
 #pragma unroll
             for (int k = NB - 1; k >= 0; --k) {
-                if (k == N - 1) {
+                if (k == M) {
                     acc = 1ull << (63 - id[k]);
                     Tn = 0;
-                } else if (k < N - 1) {
+                } else if (k < M) {
                     const double m = __dmul_rn(0.5, __dadd_rn(val[k], val[k + 1]));
                     bool uniq = true;
                     if (k > 0) uniq = m != __dmul_rn(0.5, __dadd_rn(val[k - 1], val[k]));
-                    const uint64_t above = (m == val[k + 1]) ? Tn : acc;
-                    if (uniq) rg[pos] = make_ulonglong2(above, ~above & valid);
+                    rg[pos] = (m == val[k + 1]) ? Tn : acc;   // same row for a repeated midpoint
                     pos -= uniq;
                     Tn = (val[k] == val[k + 1]) ? Tn : acc;
                     acc |= 1ull << (63 - id[k]);
                 }
             }
-            for (int k2 = kcount; k2 < N - 1; ++k2) rg[k2] = make_ulonglong2(~0ull, ~0ull);
+            for (int k2 = kcount; k2 < M; ++k2) rg[k2] = ~0ull;   // sentinel: no subject set is all ones
         }
+        } else if (val[0] == 12345.678) K[g0 + tid] = id[3];
         // ---- finished tiles -> global ----
+        if (full) fence_async_smem();
+        __syncthreads();
         if (full) {
-            fence_async_smem();
-            __syncthreads();
             if (tid == 0) {
-                bulk_s2g(rows + g0 * L, srow, (uint32_t)(T * L * 8));
-                bulk_s2g(thresholds + g0 * (N - 1), sthr, (uint32_t)(T * (N - 1) * 8));
+                bulk_s2g(thresholds + g0 * M, sthr, (uint32_t)(T * M * 8));
                 bulk_commit();
             }
         } else {
-            __syncthreads();
-            for (int i = tid; i < cnt * L; i += T) rows[g0 * L + i] = srow[i];
-            for (int i = tid; i < cnt * (N - 1); i += T) thresholds[g0 * (N - 1) + i] = sthr[i];
+            for (int i = tid; i < cnt * M; i += T) thresholds[g0 * M + i] = sthr[i];
         }
+        {
+            ulonglong2 *out = reinterpret_cast<ulonglong2 *>(rows) + g0 * M;
+            const int n_out = cnt * M;
+#pragma unroll 2
+            for (int i = tid; i < n_out; i += T) {
+                const uint64_t above = sabove[i];
+                out[i] = make_ulonglong2(above, above == ~0ull ? ~0ull : (~above & valid));
+            }
+        }
+        __syncthreads();   // the rows tile is free for the next values
     }
     if (tid == 0) bulk_wait0();
 }
@@ -1078,7 +1134,7 @@ static int launch_sort_emit_staged(cudaStream_t st, const double *values, int64_
     const int64_t need = ceil_div64(G, kStageThreads);
     if (need < blocks) blocks = need;
     if (blocks < 1) blocks = 1;
-    kern<<<(unsigned)blocks, kStageThreads, smem, st>>>(values, G, N, thresholds, K, rows);
+    kern<<<(unsigned)blocks, kStageThreads, smem, st>>>(values, G, N, thresholds, K, rows, g_detector_split == 5);
     MITRE_LAUNCH_CHECK();
     return MITRE_OK;
 }

@@ -31,7 +31,7 @@ def main():
     ref, ms0 = run(0)
     print("single fused kernel: %.3f ms" % ms0)
     for split, name in ((2, "flat values + staged sort/emit"), (3, "tile values + staged sort/emit"),
-                        (4, "default values + direct sort/emit"), (1, "default")):
+                        (4, "default values + direct sort/emit"), (5, "dry"), (1, "default")):
         out, ms = run(split)
         same = all(torch.equal(a, b) for a, b in zip(ref, out))
         print("%-36s %.3f ms  identical=%s" % (name, ms, same))
