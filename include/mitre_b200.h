@@ -210,7 +210,8 @@ int mitre_lexsort_rows(void *stream, const uint64_t *rows, int64_t P, int W64, i
  * mitre_set_detector_split selects other variants for tests and timing: 0 = the earlier single
  * kernel that does all of it per thread; 1 = default; 2 = values with one thread per value;
  * 3 = values through L2 even when the resident kernel fits; 4 = sort/emit with direct global
- * accesses instead of staged tiles.
+ * accesses instead of staged tiles; 5 = timing probe: sort/emit moves its tiles but skips the
+ * sort and the emission (outputs undefined) -- the kernel's data-movement floor.
  *
  * mitre_window_lists precomputes, once per window set, everything that does not depend on the
  * variable (ld = row stride of the per-sample lists, >= S):

@@ -161,15 +161,14 @@ extern "C" int mitre_detectors_fused(void *stream, const double *series_t, int64
                 series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, wdt, ld, group_base, slope_ok,
                 task_window, task_type, values);
         } else if (g_detector_split != 3 &&
-                   (size_t)ld * 256 + sizeof(double) * 128 * (size_t)(N | 1) + 2 * resident_meta_bytes(N, ld) <=
+                   (size_t)ld * 256 + sizeof(double) * 128 * (size_t)N + 2 * resident_meta_bytes(N, ld) <=
                        smem_optin()) {
             // the whole sample axis of a 32-variable tile fits in shared memory
-            const size_t smem = (size_t)ld * 256 + sizeof(double) * 128 * (size_t)(N | 1) +
+            const size_t smem = (size_t)ld * 256 + sizeof(double) * 128 * (size_t)N +
                                 2 * resident_meta_bytes(N, ld);
             const int n_warps = N < 16 ? N : 16;                // warps take subjects dynamically
             MITRE_CUDA_TRY(cudaFuncSetAttribute(values_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int)smem));
-            const uint32_t magic_n = (uint32_t)((0x100000000ull + (uint64_t)N - 1) / (uint64_t)N);
             // split the windows over blockIdx.y so that the grid fills whole waves of one block per SM
             const int tiles = (V + 31) / 32, sms = sm_count();
             int chunks = 1;
@@ -183,7 +182,7 @@ extern "C" int mitre_detectors_fused(void *stream, const double *series_t, int64
             chunks = (n_windows + per_block - 1) / per_block;
             values_resident_kernel<<<dim3((unsigned)tiles, (unsigned)chunks), 32 * n_warps, smem, as_stream(stream)>>>(
                 series_t, vstride, N, V, n_windows, wlo, wcnt, wstart, winv_n, winv_sxx, wdt, ld, group_base,
-                slope_ok, magic_n, per_block, values);
+                slope_ok, per_block, values);
         } else {
             const int n_vtiles = (V + 31) / 32;
             const int64_t blocks = (int64_t)n_windows * n_vtiles;

@@ -828,45 +828,45 @@ __device__ __forceinline__ void cp_async4(void *dst_smem, const void *src_gmem)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem));
 }
 
-struct ResidentMeta {
-    double *inv_n, *inv_sxx, *dt;
-    int32_t *lo, *cnt, *start;
+struct alignas(16) SubjectRec {   // one subject's share of a window, as the kernel wants to read it
+    int32_t lo, cnt, start, pad;
+    double inv_n, inv_sxx;
 };
 
-__device__ __forceinline__ ResidentMeta resident_meta(char *base, int N, int64_t ld)
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src_gmem)
 {
-    ResidentMeta m;
-    m.inv_n = reinterpret_cast<double *>(base);
-    m.inv_sxx = m.inv_n + N;
-    m.dt = m.inv_sxx + N;
-    m.lo = reinterpret_cast<int32_t *>(m.dt + ld);
-    m.cnt = m.lo + N;
-    m.start = m.cnt + N;
-    return m;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem));
 }
 
 __host__ __device__ inline size_t resident_meta_bytes(int N, int64_t ld)
 {
-    return (sizeof(double) * (2 * (size_t)N + (size_t)ld) + sizeof(int32_t) * 3 * (size_t)N + 15) & ~(size_t)15;
+    return sizeof(SubjectRec) * (size_t)N + sizeof(double) * (size_t)ld;   // ld is even: a multiple of 16
 }
 
-__device__ __forceinline__ void resident_prefetch(const ResidentMeta m, int w, int N, int S, int64_t ld,
+// window w's tables -> one of the two shared-memory copies; dt16: the centred times may move 16 bytes at a time
+__device__ __forceinline__ void resident_prefetch(char *dst, int w, int N, int S, int64_t ld, bool dt16,
                                                   const int32_t *__restrict__ wlo, const int32_t *__restrict__ wcnt,
                                                   const int32_t *__restrict__ wstart,
                                                   const double *__restrict__ winv_n,
                                                   const double *__restrict__ winv_sxx, const double *__restrict__ wdt)
 {
     const int tid = threadIdx.x, nthr = blockDim.x;
+    SubjectRec *rec = reinterpret_cast<SubjectRec *>(dst);
+    double *dt = reinterpret_cast<double *>(rec + N);
     const int64_t o = (int64_t)w * N;
-    for (int i = tid; i < N; i += nthr) {
-        cp_async8(m.inv_n + i, winv_n + o + i);
-        cp_async8(m.inv_sxx + i, winv_sxx + o + i);
-        cp_async4(m.lo + i, wlo + o + i);
-        cp_async4(m.cnt + i, wcnt + o + i);
-        cp_async4(m.start + i, wstart + o + i);
+    if (tid < N) {
+        cp_async4(&rec[tid].lo, wlo + o + tid);
+        cp_async4(&rec[tid].cnt, wcnt + o + tid);
+        cp_async4(&rec[tid].start, wstart + o + tid);
+        cp_async8(&rec[tid].inv_n, winv_n + o + tid);
+        cp_async8(&rec[tid].inv_sxx, winv_sxx + o + tid);
     }
     const double *src = wdt + (int64_t)w * ld;
-    for (int i = tid; i < S; i += nthr) cp_async8(m.dt + i, src + i);
+    if (dt16) {
+        for (int i = tid; 2 * i < S; i += nthr) cp_async16(dt + 2 * i, src + 2 * i);
+    } else {
+        for (int i = tid; i < S; i += nthr) cp_async8(dt + i, src + i);
+    }
 }
 
 static __global__ void __launch_bounds__(512, 1)
@@ -875,58 +875,72 @@ values_resident_kernel(const double *__restrict__ series_t, int64_t vstride, int
                        const int32_t *__restrict__ wstart, const double *__restrict__ winv_n,
                        const double *__restrict__ winv_sxx, const double *__restrict__ wdt, int64_t ld,
                        const int64_t *__restrict__ group_base, const uint8_t *__restrict__ slope_ok,
-                       uint32_t magic_n, int windows_per_block, double *__restrict__ values)
+                       int windows_per_block, double *__restrict__ values)
 {
     extern __shared__ __align__(16) double rsm[];
     __shared__ int next_subject[2];
     const int S = (int)ld;
-    const int Np = N | 1;
     double *ser = rsm;                                   // [S][32]
-    double *stage = ser + (size_t)S * 32;                // [2][64 * Np]
-    char *meta_base = reinterpret_cast<char *>(stage + 2 * 64 * Np);
+    double *stage = ser + (size_t)S * 32;                // [2][64 * N]
+    char *meta_base = reinterpret_cast<char *>(stage + 2 * 64 * N);
     const size_t meta_bytes = resident_meta_bytes(N, ld);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = blockDim.x >> 5;
     const int v0 = blockIdx.x * 32;
     const int vc = min(v0 + lane, V - 1);
-
+    const bool dt16 = (reinterpret_cast<uintptr_t>(wdt) & 15) == 0 && (ld & 1) == 0;
     const int w_begin = blockIdx.y * windows_per_block, w_end = min(W, w_begin + windows_per_block);
+    if (w_begin >= w_end) return;
     if (tid < 2) next_subject[tid] = 0;
-    resident_prefetch(resident_meta(meta_base, N, ld), w_begin, N, S, ld, wlo, wcnt, wstart, winv_n, winv_sxx, wdt);
+    resident_prefetch(meta_base, w_begin, N, S, ld, dt16, wlo, wcnt, wstart, winv_n, winv_sxx, wdt);
     for (int r = warp; r < S; r += n_warps) cp_async8(ser + r * 32 + lane, series_t + (int64_t)r * vstride + vc);
+    int nt_next = 1 + slope_ok[w_begin];
+    int64_t gb_next = group_base[w_begin];
     cp_async_wait_all();
     __syncthreads();
 
     for (int w = w_begin; w < w_end; ++w) {
         const int b = (w - w_begin) & 1;
-        if (w + 1 < w_end)
-            resident_prefetch(resident_meta(meta_base + (b ^ 1) * meta_bytes, N, ld), w + 1, N, S, ld, wlo, wcnt,
-                              wstart, winv_n, winv_sxx, wdt);
+        const int nt = nt_next;
+        const int64_t gb = gb_next;
+        if (w + 1 < w_end) {
+            resident_prefetch(meta_base + (b ^ 1) * meta_bytes, w + 1, N, S, ld, dt16, wlo, wcnt, wstart, winv_n,
+                              winv_sxx, wdt);
+            nt_next = 1 + slope_ok[w + 1];   // consumed one barrier from now
+            gb_next = group_base[w + 1];
+        }
         if (tid == 0) next_subject[b ^ 1] = 0;   // last used two barriers ago
-        const ResidentMeta m = resident_meta(meta_base + b * meta_bytes, N, ld);
-        double *st = stage + b * 64 * Np;
-        const int nt = 1 + slope_ok[w];
+        const SubjectRec *rec = reinterpret_cast<const SubjectRec *>(meta_base + b * meta_bytes);
+        const double *dt = reinterpret_cast<const double *>(rec + N);
+        double *st = stage + b * 64 * N;
+        double *st_lane = st + lane * nt * N;
+        const uint32_t ctr_addr = smem_u32(&next_subject[b]);
         // warps take subjects as they come free: sample counts differ a lot between subjects
         for (;;) {
             int s = 0;
-            if (lane == 0) s = atomicAdd(&next_subject[b], 1);
+            if (lane == 0)   // plain PTX: the compiler's warp-aggregated atomicAdd costs three times as much here
+                asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(s) : "r"(ctr_addr) : "memory");
             s = __shfl_sync(0xffffffffu, s, 0);
             if (s >= N) break;
-            const int n = m.cnt[s];
+            const int4 ri = *reinterpret_cast<const int4 *>(&rec[s].lo);          // lo, cnt, start
+            const double2 rd = *reinterpret_cast<const double2 *>(&rec[s].inv_n);  // 1/n, 1/sxx
             double mean = 0.0, slope = 0.0;
-            window_stats_any(n, SmemCol32{ser + m.lo[s] * 32 + lane}, SmemVec{m.dt + m.start[s]}, m.inv_n[s],
-                             m.inv_sxx[s], nt == 2, mean, slope);
-            st[(lane * nt + (nt - 1)) * Np + s] = mean;
-            if (nt == 2) st[(lane * 2) * Np + s] = slope;
+            window_stats_any(ri.y, SmemCol32{ser + ri.x * 32 + lane}, SmemVec{dt + ri.z}, rd.x, rd.y, nt == 2, mean,
+                             slope);
+            st_lane[(nt - 1) * N + s] = mean;
+            if (nt == 2) st_lane[s] = slope;
         }
         cp_async_wait_all();
         __syncthreads();
         // stream the finished tile out: rows [0, n_rows) x N of the staging tile are one contiguous
         // range of values
         const int n_out = min(32, V - v0) * nt * N;
-        double *out = values + (group_base[w] + (int64_t)v0 * nt) * N;
-        for (int i = tid; i < n_out; i += blockDim.x) {
-            const int r = (int)__umulhi((uint32_t)i, magic_n);   // i / N
-            out[i] = st[r * Np + (i - r * N)];
+        double *out = values + (gb + (int64_t)v0 * nt) * N;
+        if (((reinterpret_cast<uintptr_t>(out) | (uintptr_t)(n_out & 1) * 8) & 15) == 0) {
+            double2 *out2 = reinterpret_cast<double2 *>(out);
+            const double2 *st2 = reinterpret_cast<const double2 *>(st);
+            for (int i = tid; 2 * i < n_out; i += blockDim.x) out2[i] = st2[i];
+        } else {
+            for (int i = tid; i < n_out; i += blockDim.x) out[i] = st[i];
         }
     }
 }
