@@ -386,13 +386,17 @@ def run_b200(args):
     empty_rows = packed[:0]
 
     def sweep():
+        # the timed step is the same at every N: each rank scores its own shard, nothing is exchanged
+        out, _ = D.score_all(packed, N, dX, dom, dka, SIGMA2, mask=dmask, buffers=buffers)
+        return out
+
+    def sweep_with_exchange():
+        # what the sampler's two-stage draw adds (parallel.py): (max, sum-exp) of the shard reduced in the
+        # scoring kernel's epilogue, then a 16-byte-per-rank all-gather
+        out, _, st = D.score_all_stats(packed, N, dX, dom, dka, SIGMA2, mask=dmask, buffers=buffers,
+                                       draw_buffers=draw)
         if world > 1:
-            # (max, sum-exp) of the slice reduced in the scoring kernel's epilogue, then the 16-byte exchange
-            out, _, st = D.score_all_stats(packed, N, dX, dom, dka, SIGMA2, mask=dmask, buffers=buffers,
-                                           draw_buffers=draw)
             dist.all_gather_into_tensor(gathered, st)
-        else:
-            out, _ = D.score_all(packed, N, dX, dom, dka, SIGMA2, mask=dmask, buffers=buffers)
         return out
 
     def setup_only():
@@ -440,14 +444,19 @@ def run_b200(args):
     kernel_ms = cuda_time_ms(torch, lambda: D.score_all(packed, N, dX, dom, dka, SIGMA2, mask=dmask,
                                                         buffers=buffers), max(args.steps, 5)) - setup_ms
 
+    # the sampler's exchange step, timed apart from the headline (same CUDA-event recipe)
+    barrier()
+    exch_ms = cuda_time_ms(torch, sweep_with_exchange, max(args.steps, 5))
+    barrier()
+
     # ---- max over ranks, totals ----
-    t = torch.tensor([ms_step, e2e_ms, float(P)], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_step, e2e_ms, float(P), exch_ms], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms_step, e2e_ms, P_total = float(tmax[0]), float(tmax[1]), float(tsum[2])
+        ms_step, e2e_ms, P_total, exch_ms = float(tmax[0]), float(tmax[1]), float(tsum[2]), float(tmax[3])
     else:
         P_total = float(P)
 
@@ -464,11 +473,15 @@ def run_b200(args):
             "config": {"workload": "S5-primitive-sweep", "subjects": N, "variables_per_gpu": args.variables,
                        "windows": len(pop.windows), "candidates_per_gpu": int(P),
                        "base_columns_p": p, "l2_policy": "inputs (3.3 GB/GPU) exceed the 126 MB L2",
-                       "exchange": "all-gather of (max, sum-exp) pairs" if world > 1 else "none"},
+                       "exchange": "none: candidate shards are independent (see sampler_exchange)"},
+            "sampler_exchange": {"what": "scoring with the (max, sum-exp) reduction fused into the epilogue + "
+                                         "all-gather of one 16-byte pair per rank (two-stage draw)",
+                                 "ms_per_step": exch_ms, "value": P_total / (exch_ms * 1e-3), "unit": UNIT,
+                                 "bytes_on_wire_per_rank": 16 if world > 1 else 0},
             "e2e": {"value": P_total / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(n_small * 8), "d2h_bytes_per_step": int(P * 8),
                     "ms_per_step": e2e_ms},
-            "gpu_launches": int(args.steps * (3 + (1 if world > 1 else 0))),
+            "gpu_launches": int(args.steps * 3),
             "clocks": clocks.summary(),
             "roofline": {"kernel": "score_w1g4_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
