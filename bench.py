@@ -27,6 +27,7 @@ fresh omega.
 """
 import argparse
 import json
+import math
 import os
 import sys
 import threading
@@ -439,6 +440,33 @@ def run_b200(args):
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
 
+    # ---- the sampler's own end-to-end sweep (logit_rules.py:1052-1066 with device_draw=True): the P-long
+    # vectors never leave the device; host buffers in, the drawn candidate index and log-total out ----
+    g = torch.Generator(device=dev)
+    g.manual_seed(args.seed + 7)
+    d_prior = torch.randn(P, dtype=torch.float64, device=dev, generator=g) - math.log(max(P, 1))
+    h_idx = torch.empty(1, dtype=torch.int64).pin_memory()
+    h_stats = torch.empty(2, dtype=torch.float64).pin_memory()
+
+    def e2e_draw_step(u=0.37):
+        d_small.copy_(h_small, non_blocking=True)
+        out, _, st = D.score_all_stats(packed, N, dX, dom, dka, SIGMA2, mask=dmask, buffers=buffers,
+                                       log_prior=d_prior, draw_buffers=draw)
+        idx = D.draw_index(out, d_prior, u, stabilise=True, buffers=draw, reuse_stats=True)
+        h_idx.copy_(idx, non_blocking=True)
+        h_stats.copy_(st, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(2):
+        e2e_draw_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_draw_step()
+    barrier()
+    e2e_draw_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
+    del d_prior
+
     # kernel-only time of the dominant kernel: the step minus the (tiny) setup launch
     setup_ms = cuda_time_ms(torch, setup_only, 50)
     kernel_ms = cuda_time_ms(torch, lambda: D.score_all(packed, N, dX, dom, dka, SIGMA2, mask=dmask,
@@ -450,13 +478,14 @@ def run_b200(args):
     barrier()
 
     # ---- max over ranks, totals ----
-    t = torch.tensor([ms_step, e2e_ms, float(P), exch_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_step, e2e_ms, float(P), exch_ms, e2e_draw_ms], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         ms_step, e2e_ms, P_total, exch_ms = float(tmax[0]), float(tmax[1]), float(tsum[2]), float(tmax[3])
+        e2e_draw_ms = float(tmax[4])
     else:
         P_total = float(P)
 
@@ -481,6 +510,11 @@ def run_b200(args):
             "e2e": {"value": P_total / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(n_small * 8), "d2h_bytes_per_step": int(P * 8),
                     "ms_per_step": e2e_ms},
+            "e2e_sampler_sweep": {"what": "host inputs -> scoring + log-prior + (max, sum-exp) -> on-device draw -> "
+                                          "drawn index and stats back to pinned host memory (the sampler's "
+                                          "device_draw sweep; the P-long vectors stay in HBM)",
+                                  "value": P_total / (e2e_draw_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_draw_ms,
+                                  "h2d_bytes_per_step": int(n_small * 8), "d2h_bytes_per_step": 24},
             "gpu_launches": int(args.steps * 3),
             "clocks": clocks.summary(),
             "roofline": {"kernel": "score_w1g4_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,

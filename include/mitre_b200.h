@@ -264,7 +264,9 @@ int mitre_selftest_divide(void *stream, const double *a, const int32_t *n, int64
  *   all-gather for the two-stage multi-GPU draw.
  * mitre_draw_index: index_out[0] = #{ i : cumsum(exp(w - shift))[i] < u * total }.
  *   stabilise = 0: shift = 0, i.e. the reference's raw np.exp(weights) including its underflow
- *   behaviour; stabilise = 1: shift = max w (stats is then computed first and must be non-NULL).
+ *   behaviour; stabilise = 1: shift = max w (stats is then computed first and must be non-NULL);
+ *   stabilise = 2: shift = stats[0] as the caller left it (mitre_score_all_stats / mitre_weight_stats
+ *   over the same weights), saving the extra pass.
  *   The cumulative sum is hierarchical, not np.cumsum's strict left-to-right order: the drawn
  *   index can differ from the reference only when u*total is within rounding of a partial sum.
  */

@@ -164,6 +164,7 @@ class ShardedScorer:
         stats = D.weight_stats(local_out, local_prior, buffers=self.draw_buffers).clone()
 
         def local_draw(u_local):
+            # draw_buffers.stats still holds this slice's (max, sum-exp) from weight_stats above
             return int(D.draw_index(local_out, local_prior, u_local, stabilise=True,
-                                    buffers=self.draw_buffers).item())
+                                    buffers=self.draw_buffers, reuse_stats=True).item())
         return two_stage_draw(stats, local_draw, self.start, u, self.group, stabilise)

@@ -146,6 +146,30 @@ def test_update_truths_rebuilds_identically():
     assert np.array_equal(pop.packed_truth.cpu().numpy(), before)
 
 
+@pytest.mark.parametrize("held_out", [0, 7, 19])
+def test_update_truths_on_a_cross_validation_fold(held_out):
+    """SURVEY 8f-4 (main.py:1192-1194, rules.py:300-323): leave-one-out keeps the population's windows
+    (and their slope flags) and re-evaluates everything else on the training subjects."""
+    from mitre_b200 import rules as R
+    d = synthetic.make_series(N=20, V=3, T=(5, 9), span=(0.0, 40.0), seed=5)
+    data, pop = build_gpu_population(d, dict(tmin=1.0, N_intervals=4, tmax=None))
+    keep = [s for s in range(20) if s != held_out]
+    X = [d["X"][s] for s in keep]
+    T = [d["T"][s] for s in keep]
+    train = R.Dataset(X, T, d["y"][keep], ["v%d" % i for i in range(3)], d["variable_weights"],
+                      d["experiment_start"], d["experiment_end"])
+    windows, ok = list(pop.windows), list(pop.windows_ok_for_slope)
+    pop.data = train
+    pop._update_truths()
+    assert list(pop.windows) == windows and list(pop.windows_ok_for_slope) == ok
+    groups = DO.calculate_values(X, T, windows, ok)
+    ref = DO.enumerate_primitives(groups, len(keep))
+    order = DO.lexsort_rows(ref["truth"])
+    assert np.array_equal(pop.packed_truth.cpu().numpy().view(np.uint64), DO.pack_rows(ref["truth"][order]))
+    assert pop.flat_truth.shape == (len(order), len(keep))
+    assert train._primitive_result_cache is pop.truth_table
+
+
 def test_constant_series_slope_divergence_is_confined_to_slope_rows():
     """DESIGN.md "slope parity": a constant non-zero series has slope exactly 0 in closed form and
     ~1e-20 LAPACK noise in the reference, which changes the tie structure of that slope group only.
