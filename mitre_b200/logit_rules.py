@@ -22,7 +22,9 @@ import time
 import numpy as np
 import scipy.stats
 from scipy.special import gammaln, logsumexp
-from scipy.stats import nbinom
+from scipy.stats import nbinom  # noqa: F401  (kept for pickles of older models)
+
+from . import fastdist
 
 from . import polyagamma
 from .rules import (PrimitiveRule, RuleList, DiscreteRulePopulation, Dataset, RuleListSampler,
@@ -229,16 +231,15 @@ class LogisticRuleModel(object):
         return np.sum(terms)
 
     def prior_contribution_empty_probability(self, state):
-        return scipy.stats.beta.logpdf(state.empty_probability, self.hyperparameter_a_empty,
-                                       self.hyperparameter_b_empty)
+        return fastdist.beta_logpdf(state.empty_probability, self.hyperparameter_a_empty,
+                                    self.hyperparameter_b_empty)
 
     def prior_contribution_window_parameters(self, state):
-        return scipy.stats.expon.logpdf(state.window_concentration,
-                                        scale=self.window_concentration_typical)
+        return fastdist.expon_logpdf(state.window_concentration, self.window_concentration_typical)
 
     def prior_contribution_phylogeny_parameters(self, state):
-        mean_prior = scipy.stats.norm.logpdf(state.phylogeny_mean, loc=self.phylogeny_lambda_l,
-                                             scale=np.sqrt(self.phylogeny_mean_hyperprior_variance))
+        mean_prior = fastdist.norm_logpdf(state.phylogeny_mean, self.phylogeny_lambda_l,
+                                          np.sqrt(self.phylogeny_mean_hyperprior_variance))
         if (0. <= state.phylogeny_std and state.phylogeny_std <= self.phylogeny_std_upper_bound):
             std_prior = -1.0 * np.log(self.phylogeny_std_upper_bound)
         else:
@@ -256,9 +257,9 @@ class LogisticRuleModel(object):
         """logit_rules.py:337-402."""
         frozen = self.__dict__.get('_structure_terms')
         if frozen is None:      # pure functions of the model constants: freeze once
-            length_distribution = nbinom(self.hyperparameter_alpha_m,
-                                         self.hyperparameter_beta_m / (1.0 + self.hyperparameter_beta_m))
-            sublength_distribution = nbinom(
+            length_distribution = fastdist.NegativeBinomial(
+                self.hyperparameter_alpha_m, self.hyperparameter_beta_m / (1.0 + self.hyperparameter_beta_m))
+            sublength_distribution = fastdist.NegativeBinomial(
                 self.hyperparameter_alpha_primitives,
                 self.hyperparameter_beta_primitives / (1.0 + self.hyperparameter_beta_primitives))
             frozen = (length_distribution, length_distribution.logcdf(self.max_rules - 1),
@@ -304,16 +305,16 @@ class LogisticRuleModel(object):
             if k == key:
                 return v
         log_vw = np.log(np.asarray(self.data.variable_weights, dtype=np.float64))
-        by_variable = scipy.stats.norm.logpdf(log_vw, loc=state.phylogeny_mean, scale=state.phylogeny_std)
+        by_variable = fastdist.norm_logpdf(log_vw, state.phylogeny_mean, state.phylogeny_std)
         total_duration = float(self.data.experiment_end - self.data.experiment_start)
         durations = pop._durations_by_window / ((1.0 + self.window_duration_epsilon) * total_duration)
         window_a = state.window_concentration * state.window_typical_fraction
         window_b = state.window_concentration * (1.0 - state.window_typical_fraction)
-        by_window = scipy.stats.beta.logpdf(durations, window_a, window_b)
+        by_window = fastdist.beta_logpdf(durations, window_a, window_b)
         counts = pop.group_counts()
         terms = by_variable[pop._group_variable] + by_window[pop._group_window]
         live = counts > 0
-        normalization = logsumexp(terms[live], b=counts[live]) if live.any() else 0.0
+        normalization = fastdist.logsumexp(terms[live], b=counts[live]) if live.any() else 0.0
         result = (by_variable, by_window, float(normalization))
         cache.append((key, result))
         del cache[:-6]

@@ -70,3 +70,42 @@ def test_primitive_rule_and_rule_list_semantics():
         assert False
     except ValueError:
         pass
+
+
+def test_fastdist_is_bit_identical_to_scipy():
+    """mitre_b200/fastdist.py restates the scipy evaluations of the sampler's prior
+    (logit_rules.py:232-457) without scipy's argument machinery; the chain's accept/reject
+    sequence only stays put if the values are the same to the last bit."""
+    import scipy.special
+    import scipy.stats
+    from mitre_b200 import fastdist as F
+    rng = np.random.RandomState(0)
+    for _ in range(1500):
+        x = rng.normal(size=rng.randint(1, 50)) * 3
+        loc, scale = rng.normal(), abs(rng.normal()) + 1e-3
+        assert np.array_equal(F.norm_logpdf(x, loc, scale), scipy.stats.norm.logpdf(x, loc=loc, scale=scale))
+        xs = float(rng.normal() * 3)
+        assert F.norm_logpdf(xs, loc, scale) == scipy.stats.norm.logpdf(xs, loc=loc, scale=scale)
+        e = abs(rng.normal()) * 5
+        assert F.expon_logpdf(e, scale) == scipy.stats.expon.logpdf(e, scale=scale)
+        a, b = abs(rng.normal()) * 3 + 0.01, abs(rng.normal()) * 3 + 0.01
+        u = rng.rand(rng.randint(1, 30))
+        assert np.array_equal(F.beta_logpdf(u, a, b), scipy.stats.beta.logpdf(u, a, b))
+        us = float(rng.rand())
+        assert F.beta_logpdf(us, a, b) == scipy.stats.beta.logpdf(us, a, b)
+        n, p = abs(rng.normal()) * 3 + 0.1, rng.rand() * 0.98 + 0.01
+        nb, ref = F.NegativeBinomial(n, p), scipy.stats.nbinom(n, p)
+        k = rng.randint(0, 12, size=rng.randint(1, 6))
+        assert np.array_equal(nb.logpmf(k), ref.logpmf(k))
+        assert nb.logpmf(int(k[0])) == ref.logpmf(int(k[0]))
+        assert nb.logcdf(9) == ref.logcdf(9)
+        v = rng.normal(size=rng.randint(1, 200)) * 20
+        w = rng.randint(0, 5, size=v.size).astype(float)
+        assert F.logsumexp(v) == scipy.special.logsumexp(v)
+        if w.sum() > 0:
+            assert F.logsumexp(v, b=w) == scipy.special.logsumexp(v, b=w)
+    # edges scipy defines
+    assert np.isnan(F.norm_logpdf(0.0, 0.0, -1.0)) and np.isnan(scipy.stats.norm.logpdf(0.0, 0.0, -1.0))
+    assert F.expon_logpdf(-1.0, 2.0) == scipy.stats.expon.logpdf(-1.0, scale=2.0) == -np.inf
+    assert F.beta_logpdf(1.5, 2.0, 2.0) == scipy.stats.beta.logpdf(1.5, 2.0, 2.0) == -np.inf
+    assert F.logsumexp(np.array([-np.inf, -np.inf])) == scipy.special.logsumexp(np.array([-np.inf, -np.inf]))
