@@ -168,3 +168,207 @@ class ShardedScorer:
             return int(D.draw_index(local_out, local_prior, u_local, stabilise=True,
                                     buffers=self.draw_buffers, reuse_stats=True).item())
         return two_stage_draw(stats, local_draw, self.start, u, self.group, stabilise)
+
+
+# ---- variable-sharded population build (SURVEY 8e, row "Detector evaluation") ------------------
+#
+# Every (window, variable, type) group depends only on its variable's series (rules.py:585-599),
+# so detector evaluation shards by VARIABLE with no exchange.  What the ranks must agree on is the
+# reference's global candidate order: enumeration is window-major over ALL variables
+# (rules.py:465-511) and the lexsort is stable in that enumeration (rules.py:439-462).  The build
+# below follows the survey's first option: ranks all-gather (packed row, global enumeration
+# index) pairs -- 16 bytes per candidate, once per model build -- lay them out in enumeration
+# order, run the same stable radix sort as the single-GPU path (replicated), and keep their own
+# contiguous slice of the sorted order for scoring.  The host arithmetic (global group ids, global
+# enumeration indices, descriptor lookup) is plain numpy and is tested under gloo on CPU.
+
+def variable_bounds(V, world_size, rank):
+    """Contiguous block [v0, v1) of variables for `rank`."""
+    return shard_bounds(V, world_size, rank)
+
+
+def global_group_ids(ok_slope, V_total, v0, v1):
+    """Global group id of every local group of a rank holding variables [v0, v1).
+
+    Local and global enumeration are both window-major, then variable, then type (slope before
+    average, slope only where `ok_slope[w]`): local group (w, v_local, t) is global group
+    GB[w] + (v0 + v_local) * nt_w + t with GB[w] = V_total * sum_{w' < w} nt_{w'}."""
+    nt = 1 + np.asarray(ok_slope, dtype=np.int64).reshape(-1)
+    GB = np.zeros(nt.shape[0] + 1, dtype=np.int64)
+    np.cumsum(V_total * nt, out=GB[1:])
+    n_local = int(v1 - v0)
+    per_window = n_local * nt
+    w_of = np.repeat(np.arange(nt.shape[0], dtype=np.int64), per_window)
+    lb = np.zeros(nt.shape[0] + 1, dtype=np.int64)
+    np.cumsum(per_window, out=lb[1:])
+    within = np.arange(int(lb[-1]), dtype=np.int64) - lb[w_of]
+    return GB[w_of] + v0 * nt[w_of] + within, GB
+
+
+def describe_group(g_global, GB, ok_slope, V_total):
+    """Inverse of global_group_ids for one group: (window, variable, type) with type 0 = slope,
+    1 = average (the reference's ('slope', 'average') order, rules.py:585-599)."""
+    w = int(np.searchsorted(GB, g_global, side='right') - 1)
+    nt = 2 if ok_slope[w] else 1
+    within = int(g_global - GB[w])
+    return w, within // nt, (within % nt if nt == 2 else 1)
+
+
+def global_enumeration_indices(K_local, g_global_local, row_offsets_global):
+    """Global enumeration index of every local row, local rows in local enumeration order
+    (group-major, then threshold, then direction): row_offsets_global[g] + slot."""
+    counts = 2 * np.asarray(K_local, dtype=np.int64)
+    first = np.repeat(np.asarray(row_offsets_global)[g_global_local], counts)
+    local_off = np.zeros(counts.shape[0] + 1, dtype=np.int64)
+    np.cumsum(counts, out=local_off[1:])
+    slot = np.arange(int(local_off[-1]), dtype=np.int64) - np.repeat(local_off[:-1], counts)
+    return first + slot
+
+
+def _allgather_ragged(t, group=None):
+    """all-gather of 1-D/2-D tensors whose leading sizes differ between ranks -> list per rank."""
+    ws, _ = world(group)
+    if ws == 1:
+        return [t]
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    sizes = torch.empty(ws, dtype=torch.int64, device=t.device)
+    dist.all_gather_into_tensor(sizes, n, group=group)
+    sizes = [int(x) for x in sizes.cpu()]
+    width = max(max(sizes), 1)
+    padded = t.new_zeros((width,) + tuple(t.shape[1:]))
+    padded[:t.shape[0]] = t
+    out = t.new_empty((ws * width,) + tuple(t.shape[1:]))
+    dist.all_gather_into_tensor(out, padded.contiguous(), group=group)
+    return [out[r * width:r * width + sizes[r]] for r in range(ws)]
+
+
+class ShardedPopulation:
+    """The candidate table built by `world` ranks, each evaluating the detectors of its own
+    variables; every rank ends with its contiguous slice of the reference's global sorted order.
+
+    data: the FULL Dataset (same on every rank; only the rank's variables are staged on its GPU).
+    After construction:
+        P, start, stop      global candidate count and this rank's slice of the sorted index
+        local_rows          int64[stop-start, W64] packed truth rows of the slice (CUDA)
+        local_perm          int64[stop-start] global enumeration index of each of them
+        scorer()            ShardedScorer over the slice
+        describe(k)         (variable, window, type, direction, threshold) of global sorted index k
+    """
+
+    def __init__(self, data, tmin, N_intervals, tmax=None, group=None):
+        from . import device as D
+        from . import rules as R
+        self.group = group
+        self.ws, self.rank = world(group)
+        self.N = data.n_subjects
+        self.V = data.n_variables
+        self.v0, self.v1 = variable_bounds(self.V, self.ws, self.rank)
+        X_local = [np.ascontiguousarray(x[self.v0:self.v1]) for x in data.X]
+        names = list(data.variable_names[self.v0:self.v1])
+        weights = np.asarray(data.variable_weights)[self.v0:self.v1]
+        local_data = R.Dataset(X_local, data.T, data.y, names, weights, data.experiment_start,
+                               data.experiment_end)
+        pop = R.DiscreteRulePopulation.__new__(R.DiscreteRulePopulation)
+        pop.model, pop.data, pop.tmin = None, local_data, tmin
+        pop.tmax = np.inf if tmax is None else tmax
+        pop.N_intervals, pop.max_thresholds, pop.applied_filters = N_intervals, np.inf, []
+        pop._enumerate_windows()
+        pop.calculate_values()
+        pop.update_base_rules()
+        self.local_population = pop
+        self.windows = list(pop.windows)
+        self.ok_slope = np.array(pop.windows_ok_for_slope, dtype=bool)
+        dev = D.dev()
+
+        # -- global group ids and global row offsets (needs every rank's K) --
+        g_local, self.GB = global_group_ids(self.ok_slope, self.V, self.v0, self.v1)
+        self.G = int(self.GB[-1])
+        K_local = pop._K if pop._G else torch.empty(0, dtype=torch.int32, device=dev)
+        d_g_local = torch.as_tensor(g_local, device=dev)
+        K_parts = _allgather_ragged(K_local, group)
+        g_parts = _allgather_ragged(d_g_local, group)
+        K_global = torch.zeros(self.G, dtype=torch.int32, device=dev)
+        for Kp, gp in zip(K_parts, g_parts):
+            K_global[gp] = Kp
+        self.row_offsets = D.detector_row_offsets(K_global) if self.G else torch.zeros(1, dtype=torch.int64,
+                                                                                       device=dev)
+        self._row_offsets_host = self.row_offsets.cpu().numpy()
+        self.P = int(self._row_offsets_host[-1])
+        W64 = D.words_for(self.N)
+
+        # -- local rows in local enumeration order + their global enumeration indices --
+        if pop._P:
+            if getattr(pop, '_rows_padded', None) is not None:
+                L = pop._rows_padded.shape[1]
+                live = torch.arange(L, device=dev)[None, :] < (2 * pop._K.to(torch.int64))[:, None]
+                rows_local = pop._rows_padded[live].view(-1, 1)
+            else:
+                rows_local = pop._rows
+            e_local = torch.as_tensor(global_enumeration_indices(pop._K_host, g_local, self._row_offsets_host),
+                                      device=dev)
+        else:
+            rows_local = torch.empty((0, W64), dtype=torch.int64, device=dev)
+            e_local = torch.empty(0, dtype=torch.int64, device=dev)
+
+        # -- the one exchange of the build: 8*W64 + 8 bytes per candidate --
+        rows_enum = torch.empty((self.P, W64), dtype=torch.int64, device=dev)
+        for rp, ep in zip(_allgather_ragged(rows_local.contiguous(), group), _allgather_ragged(e_local, group)):
+            rows_enum[ep] = rp
+        del rows_local, e_local
+        if self.P:
+            perm, sorted_rows = D.lexsort_rows(rows_enum, self.N)
+        else:
+            perm, sorted_rows = torch.empty(0, dtype=torch.int64, device=dev), rows_enum
+        del rows_enum
+        self.start, self.stop = shard_bounds(self.P, self.ws, self.rank)
+        self.local_rows = sorted_rows[self.start:self.stop].clone()
+        self.local_perm = perm[self.start:self.stop].clone()
+        del perm, sorted_rows
+        pop._rows = None
+        pop._rows_padded = None
+
+    def scorer(self):
+        return ShardedScorer(self.local_rows, self.P, self.N, self.group)
+
+    def owner_of_index(self, k):
+        for r in range(self.ws):
+            a, b = shard_bounds(self.P, self.ws, r)
+            if a <= k < b:
+                return r
+        raise IndexError(k)
+
+    def owner_of_variable(self, v):
+        for r in range(self.ws):
+            a, b = variable_bounds(self.V, self.ws, r)
+            if a <= v < b:
+                return r
+        raise IndexError(v)
+
+    def _bcast(self, value, src, dtype):
+        t = torch.zeros(1, dtype=dtype, device=self.local_rows.device)
+        if self.rank == src:
+            t[0] = value
+        if self.ws > 1:
+            dist.broadcast(t, src=dist.get_global_rank(self.group, src) if self.group is not None else src,
+                           group=self.group)
+        return t.item()
+
+    def describe(self, k):
+        """Global sorted index -> the reference's primitive tuple
+        (variable, (t0, t1), type, direction, threshold) (rules.py:23-44), identical on every rank.
+        Two 8-byte broadcasts: the enumeration index from the rank that owns slice position k, the
+        threshold from the rank that owns the variable."""
+        k = int(k)
+        owner = self.owner_of_index(k)
+        e = int(self._bcast(int(self.local_perm[k - self.start]) if self.rank == owner else 0, owner, torch.int64))
+        g = int(np.searchsorted(self._row_offsets_host, e, side='right') - 1)
+        slot = e - int(self._row_offsets_host[g])
+        w, v, t = describe_group(g, self.GB, self.ok_slope, self.V)
+        vowner = self.owner_of_variable(v)
+        thr = 0.0
+        if self.rank == vowner:
+            pop = self.local_population
+            g_loc = int(pop._group_base[w]) + (v - self.v0) * (2 if self.ok_slope[w] else 1) + (t if self.ok_slope[w] else 0)
+            thr = float(pop._thresholds[g_loc, slot >> 1])
+        thr = float(self._bcast(thr, vowner, torch.float64))
+        return (v, tuple(self.windows[w]), ('slope', 'average')[t], ('above', 'below')[slot & 1], thr)

@@ -292,6 +292,13 @@ class DiscreteRulePopulation:
 
     # -- step 1: windows (rules.py:391-421) ---------------------------------------------------------
     def mine_rules(self):
+        self._enumerate_windows()
+        self.calculate_values()
+        self.update_base_rules()
+        self.sort_base_rules()
+
+    def _enumerate_windows(self):
+        """rules.py:391-421: admissible (t0, t1) windows and their slope flags."""
         from . import device as D
         import torch
         data = self.data
@@ -317,9 +324,6 @@ class DiscreteRulePopulation:
                     ok_slope.append(bool(c >= min_observations_slope))
         self.windows = windows
         self.windows_ok_for_slope = ok_slope
-        self.calculate_values()
-        self.update_base_rules()
-        self.sort_base_rules()
 
     # -- step 2 (rules.py:578-600) ----------------------------------------------------------------------
     def calculate_values(self):

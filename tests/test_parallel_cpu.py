@@ -113,3 +113,83 @@ def test_gloo_world2_gather_and_two_stage_draw(P):
     for idx, want, log_total in by_rank[0][1]:
         assert abs(idx - want) <= 1
         assert np.isfinite(log_total)
+
+
+# ---- variable-sharded build: host arithmetic ------------------------------------------------------
+
+def _brute_force_enumeration(ok, V, K_of):
+    """(window, variable, type) groups in the reference's enumeration order (rules.py:585-599:
+    window, then variable, then ('slope', 'average') with slope only where allowed) and the
+    enumeration index of every (group, threshold, direction) row (rules.py:465-511)."""
+    groups, rows = [], []
+    for w, o in enumerate(ok):
+        for v in range(V):
+            for t in ((0, 1) if o else (1,)):
+                groups.append((w, v, t))
+    e = 0
+    first = []
+    for g in groups:
+        first.append(e)
+        e += 2 * K_of[g]
+    return groups, first, e
+
+
+@pytest.mark.parametrize("V,ws", [(7, 2), (10, 4), (5, 8), (3, 1)])
+def test_global_group_ids_and_enumeration_indices(V, ws):
+    rng = np.random.RandomState(V * 10 + ws)
+    ok = rng.rand(6) < 0.6
+    K_of = {(w, v, t): int(rng.randint(0, 5)) for w in range(6) for v in range(V) for t in (0, 1)}
+    groups, first, P = _brute_force_enumeration(ok, V, K_of)
+    index_of_group = {g: i for i, g in enumerate(groups)}
+    row_offsets = np.array(first + [P], dtype=np.int64)
+    seen = np.zeros(P, dtype=bool)
+    covered = 0
+    for rank in range(ws):
+        v0, v1 = PL.variable_bounds(V, ws, rank)
+        g_global, GB = PL.global_group_ids(ok, V, v0, v1)
+        local_groups = [(w, v, t) for w, o in enumerate(ok) for v in range(v0, v1) for t in ((0, 1) if o else (1,))]
+        assert [index_of_group[g] for g in local_groups] == list(g_global)
+        assert GB[-1] == len(groups)
+        for g, gid in zip(local_groups, g_global):
+            assert PL.describe_group(int(gid), GB, ok, V) == g
+        K_local = np.array([K_of[g] for g in local_groups], dtype=np.int32)
+        e = PL.global_enumeration_indices(K_local, g_global, row_offsets)
+        want = np.concatenate([first[index_of_group[g]] + np.arange(2 * K_of[g]) for g in local_groups] +
+                              [np.zeros(0, dtype=np.int64)]).astype(np.int64)
+        assert np.array_equal(e, want)
+        assert np.all(np.diff(e) > 0)            # local enumeration order is global enumeration order
+        assert not seen[e].any()
+        seen[e] = True
+        covered += v1 - v0
+    assert covered == V and seen.all()
+
+
+def _ragged_worker(rank, ws, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    try:
+        t1 = torch.arange(3 + 2 * rank, dtype=torch.int64) + 100 * rank
+        t2 = (torch.arange((rank * 4) * 2, dtype=torch.int64) + 1000 * rank).view(-1, 2)
+        p1 = PL._allgather_ragged(t1)
+        p2 = PL._allgather_ragged(t2)
+        q.put((rank, [x.tolist() for x in p1], [x.tolist() for x in p2]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_ragged_allgather():
+    ws = 2
+    port = free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ragged_worker, args=(r, ws, port, q)) for r in range(ws)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=120) for _ in range(ws)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, p1, p2 in out:
+        assert p1 == [[0, 1, 2], [100, 101, 102, 103, 104]]
+        assert p2 == [[], [[1000, 1001], [1002, 1003], [1004, 1005], [1006, 1007]]]

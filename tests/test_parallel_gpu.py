@@ -1,5 +1,10 @@
 """NCCL parity of candidate sharding (needs >= 2 GPUs; skipped otherwise): sharded scoring +
-all-gather equals the single-GPU sweep bit for bit, and the two-stage draw picks the same index."""
+all-gather equals the single-GPU sweep, and the two-stage draw picks the same index.
+
+The log-likelihoods of a slice agree with the whole-table sweep to ~3e-16 relative, not bit for bit:
+the scoring kernels share table lookups between the four consecutive rows a thread owns, so the
+association of a row's masked sums depends on where its quad starts (and on which kernel variant the
+slice's length selects).  The bound asserted here is 1e-12; the contract is 1e-9 (BASELINE.json)."""
 import os
 import socket
 
@@ -37,7 +42,7 @@ def _worker(rank, ws, port, q):
         local, status = sh.score(c["X"], c["omega"], c["y"] - 0.5, 100.0, mask=mask)
         D.raise_on_status(status)
         gathered = sh.gather(local)
-        same = bool(torch.equal(gathered, full))
+        same = bool(((gathered - full).abs() <= 1e-12 * full.abs()).all())
         idxs = []
         for u in [0.0, 0.31, 0.64, 0.98]:
             want = int(D.draw_index(full, None, u, stabilise=True).item())
@@ -71,3 +76,79 @@ def test_sharded_scoring_matches_single_gpu():
             assert abs(got - want) <= 1
             assert abs(log_total - lse) < 1e-9
     assert [x[0] for x in out[0][2]] == [x[0] for x in out[1][2]]
+
+
+# ---- variable-sharded population build (detector evaluation) ---------------------------
+
+def _population_case():
+    from mitre_b200 import rules as R, synthetic
+    d = synthetic.make_series(N=23, V=11, T=(5, 9), span=(0.0, 40.0), seed=9)
+    data = R.Dataset(d["X"], d["T"], d["y"], ["v%d" % i for i in range(11)], d["variable_weights"],
+                     d["experiment_start"], d["experiment_end"])
+    return data, dict(tmin=1.0, N_intervals=5, tmax=None)
+
+
+def test_sharded_population_world1_equals_plain_population():
+    """Without a process group the sharded build is the whole build: same sorted table, same
+    permutation, same primitive descriptors as DiscreteRulePopulation."""
+    import torch
+    from mitre_b200 import parallel as PL, rules as R
+    data, cfg = _population_case()
+    pop = R.DiscreteRulePopulation(None, cfg["tmin"], cfg["N_intervals"], tmax=cfg["tmax"], data=data)
+    sp = PL.ShardedPopulation(data, cfg["tmin"], cfg["N_intervals"], tmax=cfg["tmax"])
+    assert sp.P == len(pop) and (sp.start, sp.stop) == (0, len(pop))
+    assert torch.equal(sp.local_rows, pop.packed_truth)
+    assert np.array_equal(sp.local_perm.cpu().numpy(), pop._perm_host())
+    for k in [0, 1, len(pop) // 3, len(pop) - 1]:
+        assert sp.describe(k) == pop._tuple_at(k)
+
+
+def _pop_worker(rank, ws, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=ws, device_id=torch.device("cuda", rank))
+    try:
+        from mitre_b200 import device as D, parallel as PL, rules as R
+        data, cfg = _population_case()
+        pop = R.DiscreteRulePopulation(None, cfg["tmin"], cfg["N_intervals"], tmax=cfg["tmax"], data=data)
+        sp = PL.ShardedPopulation(data, cfg["tmin"], cfg["N_intervals"], tmax=cfg["tmax"])
+        full = pop.packed_truth
+        ok_rows = bool(torch.equal(sp.local_rows, full[sp.start:sp.stop]))
+        ok_perm = bool(np.array_equal(sp.local_perm.cpu().numpy(), pop._perm_host()[sp.start:sp.stop]))
+        ks = [0, 5, len(pop) // 2, len(pop) - 1]
+        ok_desc = all(sp.describe(k) == pop._tuple_at(k) for k in ks)
+        # the slice scores like the same slice of the single-GPU table
+        from tests.golden import make_golden as MG
+        c = MG.scoring_inputs(seed=5, N=data.n_subjects, p=3, P=4)
+        whole, status = D.score_all(full, data.n_subjects, c["X"], c["omega"], c["y"] - 0.5, 100.0)
+        whole = whole.clone()
+        local, status = sp.scorer().score(c["X"], c["omega"], c["y"] - 0.5, 100.0)
+        ref = whole[sp.start:sp.stop]
+        ok_score = bool(((local - ref).abs() <= 1e-12 * ref.abs()).all())
+        q.put((rank, sp.P, len(pop), (sp.v0, sp.v1), ok_rows, ok_perm, ok_desc, ok_score))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_population_two_gpus_matches_single_gpu_build():
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ws = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_pop_worker, args=(r, ws, port, q)) for r in range(ws)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=300) for _ in range(ws)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(o[3] for o in out) == [(0, 6), (6, 11)]
+    for rank, P, P_plain, _, ok_rows, ok_perm, ok_desc, ok_score in out:
+        assert P == P_plain and ok_rows and ok_perm and ok_desc and ok_score
