@@ -81,11 +81,14 @@ int mitre_unpack_rows_u8(void *stream, const uint64_t *packed, int64_t P, int N,
  * bytes and stay untouched until the launch has run.  `status` (device int32, caller-zeroed)
  * receives MITRE_STATUS_* flags.
  * Kernel selection (N <= 64): tables of subset sums -- 8-subject tables in shared memory for small
- * candidate sets, 16-subject tables in L2 for P >= 4 Mi rows (mitre_set_large_table_min_rows moves
- * that switch point; a tuning / test hook).
+ * candidate sets; for P >= 4 Mi rows (mitre_set_large_table_min_rows moves that switch point; a
+ * tuning / test hook) 16-subject tables in L2, the leading ones shared by the four consecutive rows
+ * a thread owns.  mitre_set_split_tables(1) selects a variant that keeps the table of the last 10-11
+ * subjects in shared memory instead (same speed on B200, see scoring.cu; off by default).
  */
 size_t mitre_score_workspace_bytes(int N, int p);
 int mitre_set_large_table_min_rows(int64_t rows);
+int mitre_set_split_tables(int enable);
 int mitre_score_all(void *stream, const uint64_t *packed_truth, int64_t P, int W64,
                     const uint64_t *mask, const double *X, const double *omega,
                     const double *kappa, int N, int p, double sigma2, void *workspace,

@@ -511,6 +511,7 @@ score_w1r4_kernel(const uint64_t *__restrict__ rows, int64_t P, const double *__
 // ---------------------------------------------------------------------------------------------
 constexpr int64_t kLargeTableMinRows = 4 << 20;
 static int64_t g_large_table_min_rows = kLargeTableMinRows;
+static int g_split_tables = 0;   // 1: last table in shared memory (score_w1s4_kernel), 0: score_w1g4_kernel (default)
 
 // Table t covers subjects [table16_start, +table16_bits): the split is aligned to the LAST subject
 // (table 0 takes the N mod 16 remainder), because neighbouring rows of a lexsorted table differ in
@@ -951,6 +952,219 @@ score_w1g4_kernel(const uint64_t *__restrict__ rows, int64_t P, const double *__
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Split tables: the LAST `LB` subjects' subset-sum table lives in shared memory, the leading
+// N - LB subjects keep 16-subject tables in global memory.  score_w1g4_kernel fetches one 48-byte
+// entry of a 3 MB table per candidate from L2 (divergent: one L1 tag per lane per 16 bytes and
+// ~48 B of L2 traffic per candidate, the two units ncu shows saturated); here the per-candidate
+// lookup is a shared-memory read and only the leading lookups -- shared by the four consecutive
+// rows of a thread whenever they agree on the leading subjects, which lexsorted neighbours nearly
+// always do -- go to L1/L2.
+// Measured (S5, 2.94e8 candidates, p = 4): 1.94 ms against 1.97 ms for score_w1g4_kernel, and
+// 2.46 ms against 2.33 ms with the fused stats: both variants sit on the same unit, the L1 data
+// pipe's wavefront rate (87 % of peak in ncu) -- a 48-byte entry per lane costs ~25 wavefronts per
+// warp from shared memory (bank conflicts of random 16-byte reads) where the divergent global
+// read cost tags instead.  Kept selectable (mitre_set_split_tables), not the default.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSplitThreads = 384;
+
+__host__ __device__ inline int split_last_bits(int N, int EP)
+{
+    const int lb = (EP <= 6) ? 11 : 10;     // 2^LB * EP * 8 bytes <= ~98 KB: two blocks per SM
+    return N < lb ? N : lb;
+}
+// leading tables: 16 subjects each from subject 0, the remainder (R mod 16) in the LAST leading
+// table, so that rows which agree on everything but their trailing subjects disagree only there
+__host__ __device__ inline int split_n_lead(int R) { return (R + 15) >> 4; }
+__host__ __device__ inline int split_lead_bits(int R, int t) { return (16 * (t + 1) <= R) ? 16 : R - 16 * t; }
+__host__ __device__ inline size_t split_tables_doubles(int N, int EP)
+{
+    const int LB = split_last_bits(N, EP), R = N - LB;
+    size_t n = ((size_t)1 << LB) * EP;
+    for (int t = 0; t < split_n_lead(R); ++t) n += ((size_t)1 << split_lead_bits(R, t)) * EP;
+    return n;
+}
+
+// leading tables over subjects [16 t, 16 t + bits), then the last table over subjects [R, N)
+__global__ void __launch_bounds__(256)
+score_build_tables_split_kernel(const double *__restrict__ ws, int N, int EP, double *__restrict__ tables)
+{
+    const double *q = ws + kHdr;
+    const int LB = split_last_bits(N, EP), R = N - LB;
+    const int nt = split_n_lead(R);
+    size_t base = 0;
+    for (int t = 0; t <= nt; ++t) {
+        const int bits = t < nt ? split_lead_bits(R, t) : LB;
+        const int start = t < nt ? 16 * t : R;
+        const size_t count = ((size_t)1 << bits) * EP;
+        for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < count;
+             idx += (size_t)gridDim.x * blockDim.x) {
+            const int e = (int)(idx % EP);
+            const unsigned pat = (unsigned)(idx / EP);
+            double acc = 0.0;
+            for (int j = 0; j < bits; ++j)
+                if ((pat >> (bits - 1 - j)) & 1) acc += q[(size_t)(start + j) * EP + e];
+            tables[base + idx] = acc;
+        }
+        base += count;
+    }
+}
+
+template <int EP, bool STATS>
+__global__ void __launch_bounds__(kSplitThreads, 2)
+score_w1s4_kernel(const uint64_t *__restrict__ rows, int64_t P, const double *__restrict__ ws, int N,
+                  const double *__restrict__ tables, double *__restrict__ out, int32_t *status,
+                  const double *__restrict__ log_prior, double *__restrict__ stat_partials)
+{
+    extern __shared__ __align__(16) double last_tab[];    // [2^LB][EP]
+    __shared__ double2 logtab[kLogTab];
+    __shared__ double exptab[kExpTab];
+    build_math_tables(logtab, exptab);
+    const int LB = split_last_bits(N, EP), R = N - LB;
+    const int nt = split_n_lead(R);
+    const double inv_s2 = ws[1], C1 = ws[3];
+    const double *tb[4];
+    int shift[4];
+    unsigned msk[4];
+    size_t base = 0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int bits = t < nt ? split_lead_bits(R, t) : 0;
+        tb[t] = tables + base;
+        shift[t] = 64 - 16 * t - bits;
+        msk[t] = (1u << bits) - 1u;
+        base += t < nt ? ((size_t)1 << bits) * EP : 0;
+    }
+    // subjects covered by all leading tables but the last one: the second sharing level
+    const int R1 = nt > 1 ? 16 * (nt - 1) : 0;
+    {
+        const double2 *src = reinterpret_cast<const double2 *>(tables + base);
+        double2 *dst = reinterpret_cast<double2 *>(last_tab);
+        const int n2 = (EP << LB) >> 1;
+        for (int i = threadIdx.x; i < n2; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const int last_shift = 64 - N;
+    const unsigned last_msk = (1u << LB) - 1u;
+    bool bad = false;
+    MaxSum run = {-INFINITY, 0.0};
+    const int64_t quads = P >> 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const ulonglong2 *rows2 = reinterpret_cast<const ulonglong2 *>(rows);
+    double2 *out2 = reinterpret_cast<double2 *>(out);
+    int64_t q4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    ulonglong2 ra = make_ulonglong2(0, 0), rb = ra;
+    if (q4 < quads) { ra = rows2[2 * q4]; rb = rows2[2 * q4 + 1]; }
+    for (; q4 < quads; q4 += stride) {
+        const int64_t nq = q4 + stride;
+        ulonglong2 na = make_ulonglong2(0, 0), nb = na;
+        if (nq < quads) { na = rows2[2 * nq]; nb = rows2[2 * nq + 1]; }
+        const uint64_t r[4] = {ra.x, ra.y, rb.x, rb.y};
+        ra = na; rb = nb;
+        const uint64_t diff = (r[0] ^ r[1]) | (r[0] ^ r[2]) | (r[0] ^ r[3]);
+        // how many leading tables the four rows share: all of them (lexsorted neighbours nearly
+        // always), all but the last (short) one, or none
+        const int n_shared = (R == 0 || (diff >> (64 - R)) == 0) ? nt
+                             : (R1 > 0 && (diff >> (64 - R1)) == 0) ? nt - 1 : 0;
+        double val[4];
+        double prefix[EP];
+#pragma unroll
+        for (int e = 0; e < EP; ++e) prefix[e] = 0.0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            if (t < n_shared) lut_add_g<EP>(prefix, tb[t] + (size_t)((unsigned)(r[0] >> shift[t]) & msk[t]) * EP);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            double acc[EP];
+#pragma unroll
+            for (int e = 0; e < EP; ++e) acc[e] = prefix[e];
+            if (n_shared < nt) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    if (t >= n_shared && t < nt)
+                        lut_add_g<EP>(acc, tb[t] + (size_t)((unsigned)(r[i] >> shift[t]) & msk[t]) * EP);
+            }
+            lut_add<EP>(acc, last_tab + ((unsigned)(r[i] >> last_shift) & last_msk) * EP);
+            val[i] = finish_tab<EP>(acc, inv_s2, C1, logtab, bad);
+        }
+        out2[2 * q4] = make_double2(val[0], val[1]);
+        out2[2 * q4 + 1] = make_double2(val[2], val[3]);
+        if (STATS) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ms_push(run, log_prior ? val[i] + log_prior[4 * q4 + i] : val[i], exptab);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (P & 3)) {      // tail rows
+        const int64_t k = (quads << 2) + threadIdx.x;
+        const uint64_t r = rows[k];
+        double acc[EP];
+#pragma unroll
+        for (int e = 0; e < EP; ++e) acc[e] = 0.0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            if (t < nt) lut_add_g<EP>(acc, tb[t] + (size_t)((unsigned)(r >> shift[t]) & msk[t]) * EP);
+        lut_add<EP>(acc, last_tab + ((unsigned)(r >> last_shift) & last_msk) * EP);
+        const double val = finish_tab<EP>(acc, inv_s2, C1, logtab, bad);
+        out[k] = val;
+        if (STATS) ms_push(run, log_prior ? val + log_prior[k] : val, exptab);
+    }
+    if (bad && status) atomicOr(reinterpret_cast<unsigned int *>(status), MITRE_STATUS_BAD_SCHUR);
+    if (STATS) {
+        __shared__ double sm[kSplitThreads], ss[kSplitThreads];
+        sm[threadIdx.x] = run.m; ss[threadIdx.x] = run.s;
+        __syncthreads();
+        for (int s = 256; s > 0; s >>= 1) {
+            if (threadIdx.x < s && threadIdx.x + s < kSplitThreads) {
+                const MaxSum x = ms_merge(MaxSum{sm[threadIdx.x], ss[threadIdx.x]},
+                                          MaxSum{sm[threadIdx.x + s], ss[threadIdx.x + s]});
+                sm[threadIdx.x] = x.m; ss[threadIdx.x] = x.s;
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) { stat_partials[2 * blockIdx.x] = sm[0]; stat_partials[2 * blockIdx.x + 1] = ss[0]; }
+    }
+}
+
+template <int EP>
+static int launch_w1s4(cudaStream_t st, const uint64_t *rows, int64_t P, double *ws, int N, double *out,
+                       int32_t *status, const double *log_prior, double *stats)
+{
+    double *partials = ws + kHdr + (size_t)N * EP;
+    double *tables = partials + 2 * kMaxStatCtas;
+    const size_t entries = split_tables_doubles(N, EP);
+    int64_t bblocks = ceil_div64((int64_t)entries, 256);
+    if (bblocks > 8 * sm_count()) bblocks = 8 * sm_count();
+    score_build_tables_split_kernel<<<(unsigned)bblocks, 256, 0, st>>>(ws, N, EP, tables);
+    MITRE_LAUNCH_CHECK();
+    const size_t smem = (sizeof(double) * EP) << split_last_bits(N, EP);
+    int per_sm = 1;
+    int64_t blocks = 0;
+#define MITRE_S4_LAUNCH(STATSV)                                                                          \
+    {                                                                                                    \
+        auto kern = score_w1s4_kernel<EP, STATSV>;                                                       \
+        MITRE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        MITRE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSplitThreads, smem)); \
+        if (per_sm < 1) return MITRE_ERR_UNSUPPORTED;                                                    \
+        blocks = (int64_t)sm_count() * per_sm;                                                           \
+        const int64_t need = ceil_div64(P >> 2, kSplitThreads);                                          \
+        if (need < blocks) blocks = need;                                                                \
+        if (blocks < 1) blocks = 1;                                                                      \
+        if (blocks > kMaxStatCtas) blocks = kMaxStatCtas;                                                \
+        kern<<<(unsigned)blocks, kSplitThreads, smem, st>>>(rows, P, ws, N, tables, out, status, log_prior, \
+                                                            partials);                                   \
+        MITRE_LAUNCH_CHECK();                                                                            \
+    }
+    if (stats) {
+        MITRE_S4_LAUNCH(true)
+        score_stats_final_kernel<<<1, 256, 0, st>>>(partials, (int)blocks, stats);
+        MITRE_LAUNCH_CHECK();
+    } else {
+        MITRE_S4_LAUNCH(false)
+    }
+#undef MITRE_S4_LAUNCH
+    return MITRE_OK;
+}
+
 template <int EP>
 static int launch_w1r4(cudaStream_t st, const uint64_t *rows, int64_t P, double *ws, int N, double *out,
                        int32_t *status, const double *log_prior, double *stats)
@@ -1048,7 +1262,12 @@ static int launch_ep(cudaStream_t st, const uint64_t *rows, int64_t P, int W64, 
         *stats_done = true;
         const size_t lut8 = (size_t)((N + 7) / 8) * 256 * EP * sizeof(double);
         // keep >= 2 CTAs per SM where the byte table allows it, else fall to nibble tables
-        if (P >= g_large_table_min_rows) return launch_w1g<EP>(st, rows, P, ws, N, out, status, log_prior, stats);
+        if (P >= g_large_table_min_rows) {
+            const bool aligned = ((reinterpret_cast<uintptr_t>(rows) | reinterpret_cast<uintptr_t>(out)) & 31) == 0;
+            if (g_split_tables && EP <= 8 && aligned)
+                return launch_w1s4<(EP <= 8 ? EP : 8)>(st, rows, P, ws, N, out, status, log_prior, stats);
+            return launch_w1g<EP>(st, rows, P, ws, N, out, status, log_prior, stats);
+        }
         const bool aligned32 = ((reinterpret_cast<uintptr_t>(rows) | reinterpret_cast<uintptr_t>(out)) & 31) == 0;
         if (EP <= 8 && lut8 <= 100 * 1024 && aligned32 && P >= 64)
             return launch_w1r4<EP>(st, rows, P, ws, N, out, status, log_prior, stats);
@@ -1067,7 +1286,10 @@ extern "C" size_t mitre_score_workspace_bytes(int N, int p)
 {
     if (N <= 0 || p <= 0 || p > MITRE_MAX_P) return 0;
     size_t n = (size_t)kHdr + (size_t)N * ep_for(p) + 2 * (size_t)kMaxStatCtas;
-    if (N <= 64) n += tables16_doubles(N, ep_for(p));     // 16-subject tables of the large-table kernel
+    if (N <= 64) {   // tables of the large-table kernels (either layout)
+        const size_t a = tables16_doubles(N, ep_for(p)), b = split_tables_doubles(N, ep_for(p));
+        n += a > b ? a : b;
+    }
     return sizeof(double) * n;
 }
 
@@ -1076,6 +1298,12 @@ extern "C" int mitre_set_large_table_min_rows(int64_t rows)
 {
     if (rows < 0) return MITRE_ERR_INVALID;
     g_large_table_min_rows = rows;
+    return MITRE_OK;
+}
+
+extern "C" int mitre_set_split_tables(int enable)
+{
+    g_split_tables = enable ? 1 : 0;
     return MITRE_OK;
 }
 

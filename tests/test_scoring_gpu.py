@@ -212,13 +212,16 @@ def test_score_all_stats_fused_logsumexp():
         assert abs(st2[0] + np.log(st2[1]) - want2) < 1e-11 * abs(want2)
 
 
-def test_large_table_kernel_parity():
-    """The 16-subject global-table kernel (default for P >= 4 Mi rows) forced onto small cases:
-    reference golden vectors, odd shapes, masks and the fused stats."""
+@pytest.mark.parametrize("split", [0, 1])
+def test_large_table_kernel_parity(split):
+    """The large-table kernels (default for P >= 4 Mi rows) forced onto small cases: reference golden
+    vectors, odd shapes, masks and the fused stats.  split=0: every table in L2
+    (score_w1g4_kernel, the default); split=1: last subjects' table in shared memory (score_w1s4_kernel)."""
     import torch
     from mitre_b200 import device as D
     from mitre_b200._lib import lib
     assert lib().mitre_set_large_table_min_rows(0) == 0
+    assert lib().mitre_set_split_tables(split) == 0
     try:
         for name in sorted(MG.SCORING_CASES):
             c = MG.scoring_inputs(**MG.SCORING_CASES[name])
@@ -239,3 +242,4 @@ def test_large_table_kernel_parity():
         assert abs(st[0] + np.log(st[1]) - want) < 1e-11 * abs(want)
     finally:
         lib().mitre_set_large_table_min_rows(4 << 20)
+        lib().mitre_set_split_tables(0)
