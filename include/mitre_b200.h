@@ -89,6 +89,7 @@ int mitre_unpack_rows_u8(void *stream, const uint64_t *packed, int64_t P, int N,
 size_t mitre_score_workspace_bytes(int N, int p);
 int mitre_set_large_table_min_rows(int64_t rows);
 int mitre_set_split_tables(int enable);
+int mitre_set_wide_tables(int enable);   /* N > 64: 1 (default) byte tables in L2, 0 one fetch per set bit */
 int mitre_score_all(void *stream, const uint64_t *packed_truth, int64_t P, int W64,
                     const uint64_t *mask, const double *X, const double *omega,
                     const double *kappa, int N, int p, double sigma2, void *workspace,

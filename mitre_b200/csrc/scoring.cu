@@ -511,6 +511,7 @@ score_w1r4_kernel(const uint64_t *__restrict__ rows, int64_t P, const double *__
 // ---------------------------------------------------------------------------------------------
 constexpr int64_t kLargeTableMinRows = 4 << 20;
 static int64_t g_large_table_min_rows = kLargeTableMinRows;
+static int g_wide_tables = 1;    // N > 64: 1 byte tables (score_wide8_kernel), 0 per-set-bit sums (score_wide_kernel)
 static int g_split_tables = 0;   // 1: last table in shared memory (score_w1s4_kernel), 0: score_w1g4_kernel (default)
 
 // Table t covers subjects [table16_start, +table16_bits): the split is aligned to the LAST subject
@@ -676,6 +677,68 @@ score_wide_kernel(const uint64_t *__restrict__ rows, int64_t P, int W64, const d
             for (int e = 0; e < EP; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], off);
         }
         if (lane == 0) out[k] = finish_candidate<EP>(acc, C0, inv_s2, s2, bad);
+    }
+    if (bad && status) atomicOr(reinterpret_cast<unsigned int *>(status), MITRE_STATUS_BAD_SCHUR);
+}
+
+// ---------------------------------------------------------------------------------------------
+// N > 64, byte tables: table b holds the 256 subset sums of subjects [8b, 8b + 8) (3 MB at
+// N = 2000, p = 4: L2 resident, rebuilt per sweep).  A candidate is ceil(N/8) lookups instead of
+// one q_i fetch + EP adds per SET BIT (~N/2 of them): ~4x fewer loads and adds.  A group of
+// LPC = 2^k lanes owns one candidate (LPC = 32 from N = 249 up; smaller N put several candidates
+// in a warp), lane j of the group takes bytes j, j + LPC, ...; fixed-order butterfly => deterministic.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t tables8_doubles(int N, int EP) { return (size_t)((N + 7) / 8) * 256 * EP; }
+
+__global__ void __launch_bounds__(256)
+score_build_tables8_kernel(const double *__restrict__ ws, int N, int EP, double *__restrict__ tables)
+{
+    const double *q = ws + kHdr;
+    const size_t count = tables8_doubles(N, EP);
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < count;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int e = (int)(idx % EP);
+        const unsigned pat = (unsigned)((idx / EP) & 255);
+        const int b = (int)(idx / ((size_t)EP * 256));
+        double acc = 0.0;
+        for (int j = 0; j < 8; ++j) {
+            const int subject = 8 * b + j;
+            if (subject < N && ((pat >> (7 - j)) & 1)) acc += q[(size_t)subject * EP + e];
+        }
+        tables[idx] = acc;
+    }
+}
+
+template <int EP>
+__global__ void __launch_bounds__(256)
+score_wide8_kernel(const uint64_t *__restrict__ rows, int64_t P, int W64, const double *__restrict__ ws,
+                   int N, const double *__restrict__ tables, int lpc_log2, double *__restrict__ out,
+                   int32_t *status)
+{
+    const double C0 = ws[0], inv_s2 = ws[1], s2 = ws[2];
+    const int nbytes = (N + 7) >> 3;
+    const int LPC = 1 << lpc_log2, cpw = 32 >> lpc_log2;
+    const int lane = threadIdx.x & 31, sub = lane & (LPC - 1), slot = lane >> lpc_log2;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    bool bad = false;
+    for (int64_t k0 = warp0 * cpw; k0 < P; k0 += nwarps * cpw) {      // warp-uniform trip count
+        const int64_t k = k0 + slot;
+        double acc[EP];
+#pragma unroll
+        for (int e = 0; e < EP; ++e) acc[e] = 0.0;
+        if (k < P) {
+            const uint64_t *row = rows + k * W64;
+            for (int b = sub; b < nbytes; b += LPC) {
+                const unsigned pat = (unsigned)(__ldg(row + (b >> 3)) >> (56 - 8 * (b & 7))) & 255u;
+                if (pat) lut_add_g<EP>(acc, tables + ((size_t)b * 256 + pat) * EP);
+            }
+        }
+        for (int off = LPC >> 1; off > 0; off >>= 1) {
+#pragma unroll
+            for (int e = 0; e < EP; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], off);
+        }
+        if (sub == 0 && k < P) out[k] = finish_candidate<EP>(acc, C0, inv_s2, s2, bad);
     }
     if (bad && status) atomicOr(reinterpret_cast<unsigned int *>(status), MITRE_STATUS_BAD_SCHUR);
 }
@@ -1239,11 +1302,30 @@ static int launch_w1g(cudaStream_t st, const uint64_t *rows, int64_t P, double *
 }
 
 template <int EP>
-static int launch_wide(cudaStream_t st, const uint64_t *rows, int64_t P, int W64, const double *ws,
+static int launch_wide(cudaStream_t st, const uint64_t *rows, int64_t P, int W64, double *ws,
                        int N, double *out, int32_t *status)
 {
-    auto kern = score_wide_kernel<EP>;
     int per_sm = 1;
+    if (g_wide_tables) {
+        double *tables = ws + kHdr + (size_t)N * EP + 2 * kMaxStatCtas;
+        int64_t bblocks = ceil_div64((int64_t)tables8_doubles(N, EP), 256);
+        if (bblocks > 8 * sm_count()) bblocks = 8 * sm_count();
+        score_build_tables8_kernel<<<(unsigned)bblocks, 256, 0, st>>>(ws, N, EP, tables);
+        MITRE_LAUNCH_CHECK();
+        const int nbytes = (N + 7) / 8;
+        int lpc_log2 = 0;
+        while (lpc_log2 < 5 && (1 << lpc_log2) < nbytes) ++lpc_log2;
+        auto kern = score_wide8_kernel<EP>;
+        MITRE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
+        int64_t blocks = (int64_t)sm_count() * (per_sm > 0 ? per_sm : 1);
+        const int64_t need = ceil_div64(P, 8 * (32 >> lpc_log2));
+        if (need < blocks) blocks = need;
+        if (blocks < 1) blocks = 1;
+        kern<<<(unsigned)blocks, 256, 0, st>>>(rows, P, W64, ws, N, tables, lpc_log2, out, status);
+        MITRE_LAUNCH_CHECK();
+        return MITRE_OK;
+    }
+    auto kern = score_wide_kernel<EP>;
     MITRE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
     int64_t blocks = (int64_t)sm_count() * (per_sm > 0 ? per_sm : 1);
     const int64_t need = ceil_div64(P, 8);
@@ -1289,6 +1371,8 @@ extern "C" size_t mitre_score_workspace_bytes(int N, int p)
     if (N <= 64) {   // tables of the large-table kernels (either layout)
         const size_t a = tables16_doubles(N, ep_for(p)), b = split_tables_doubles(N, ep_for(p));
         n += a > b ? a : b;
+    } else {
+        n += tables8_doubles(N, ep_for(p));                // byte tables of score_wide8_kernel
     }
     return sizeof(double) * n;
 }
@@ -1304,6 +1388,12 @@ extern "C" int mitre_set_large_table_min_rows(int64_t rows)
 extern "C" int mitre_set_split_tables(int enable)
 {
     g_split_tables = enable ? 1 : 0;
+    return MITRE_OK;
+}
+
+extern "C" int mitre_set_wide_tables(int enable)
+{
+    g_wide_tables = enable ? 1 : 0;
     return MITRE_OK;
 }
 

@@ -243,3 +243,21 @@ def test_large_table_kernel_parity(split):
     finally:
         lib().mitre_set_large_table_min_rows(4 << 20)
         lib().mitre_set_split_tables(0)
+
+
+@pytest.mark.parametrize("tables", [1, 0])
+def test_wide_path_parity(tables):
+    """N > 64 (several 64-subject words per row): byte-table kernel (default) and the per-set-bit
+    kernel against the C oracle, odd subject counts, masks, several candidates per warp and one."""
+    from mitre_b200._lib import lib
+    assert lib().mitre_set_wide_tables(tables) == 0
+    try:
+        for N, p, P in [(65, 1, 40), (72, 3, 333), (100, 4, 257), (129, 2, 100), (200, 5, 64), (257, 7, 129),
+                        (600, 4, 50), (2000, 4, 12)]:
+            c = MG.scoring_inputs(seed=900 + N + p, N=N, p=p, P=P)
+            opts = (c["truth"] * c["mask"]).astype(np.float64)
+            want = oracle.likelihoods_of_all_options(c["X"], c["omega"], (c["y"] - 0.5) / c["omega"], opts,
+                                                     c["sigma2"])
+            assert rel(gpu_score(c), want) < RTOL, (N, p, P)
+    finally:
+        lib().mitre_set_wide_tables(1)
