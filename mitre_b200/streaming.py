@@ -1,0 +1,169 @@
+"""Candidate sweeps over populations whose packed truth table does not fit in HBM
+(configuration S3: 2 000 subjects x 5 000 variables x 50 timepoints, mean + slope,
+full threshold grid -> 3.1e9 candidates, 0.8 TB packed; the reference would need 6 TB of bool
+and a 50 TB float64 temporary, logit_rules.py:214-217).
+
+The table is never materialised.  Variables are walked in tiles; per tile the detector kernels
+rebuild values, thresholds and truth rows (every group depends only on its own variable's series,
+rules.py:585-599), the scoring kernel evaluates the tile's candidates and reduces
+(max, sum exp) of log-likelihood + log-prior in the same launch, and the rows are dropped.  What
+survives a sweep is one 16-byte pair per tile: enough for the log-sum-exp the add/remove moves
+need (logit_rules.py:959, 1064) and for a two-stage draw -- pick the tile that holds
+u * total, rebuild that one tile, draw inside it -- exactly the exchange `parallel.two_stage_draw`
+makes between ranks, here made between tiles in time.
+
+Candidates are indexed (tile, position in the tile's enumeration order).  That is a different
+ORDER from the reference's global lexsort (which nothing that large can compute), over the same
+candidate SET with the same weights, so the draw has the same distribution; chains are not
+RNG-stream-aligned with a hypothetical resident run.  For populations that do fit,
+tests/test_streaming_gpu.py checks tile by tile that every candidate carries the likelihood the
+resident population gives it.
+"""
+import numpy as np
+
+from .parallel import owner_of_marker
+from .rules import DIRECTIONS, TYPES
+
+
+class StreamingSweep:
+    def __init__(self, data, tmin, N_intervals, tmax=None, tile_variables=64):
+        import torch
+        from . import device as D
+        from . import rules as R
+        self.data = data
+        self.N = data.n_subjects
+        self.V = data.n_variables
+        self.tile_variables = int(tile_variables)
+        pop = R.DiscreteRulePopulation.__new__(R.DiscreteRulePopulation)
+        pop.model, pop.data, pop.tmin = None, data, tmin
+        pop.tmax = np.inf if tmax is None else tmax
+        pop.N_intervals = N_intervals
+        pop._enumerate_windows()
+        self.windows = list(pop.windows)
+        self.ok_slope = np.array(pop.windows_ok_for_slope, dtype=np.uint8)
+        self.durations = np.array([w[1] - w[0] for w in self.windows], dtype=np.float64)
+        self._ds = data.device_series()
+        W = len(self.windows)
+        self._d_windows = torch.as_tensor(np.array(self.windows, dtype=np.float64).reshape(-1, 2), device=D.dev())
+        self._d_ok = torch.as_tensor(self.ok_slope, device=D.dev())
+        if W:
+            self._lo, self._cnt = D.window_ranges(self._ds['times'], self._ds['t_offsets'], self._d_windows)
+        self.tiles = [(v0, min(v0 + self.tile_variables, self.V)) for v0 in range(0, self.V, self.tile_variables)]
+        self._buffers = None
+        self._draw = None
+        self.tile_stats = None
+
+    # -- one tile: detector kernels -> rows in enumeration order (window, variable, type, threshold, direction)
+    def _group_base(self, n_vars):
+        per_window = n_vars * (1 + self.ok_slope.astype(np.int64))
+        gb = np.zeros(len(self.windows) + 1, dtype=np.int64)
+        np.cumsum(per_window, out=gb[1:])
+        return gb
+
+    def build_tile(self, t):
+        """-> dict(rows int64[P_t, W64], K, thresholds, row_offsets (device), group_base (host), v0, v1)."""
+        import torch
+        from . import device as D
+        v0, v1 = self.tiles[t]
+        gb = self._group_base(v1 - v0)
+        G = int(gb[-1])
+        ds = self._ds
+        d_gb = torch.as_tensor(gb[:-1].copy(), device=D.dev())
+        values = D.detector_values(ds['series'][v0:v1], ds['times'], ds['t_offsets'], self._d_windows,
+                                   self._lo, self._cnt, d_gb, self._d_ok, G, ds['max_T'])
+        thresholds, K = D.detector_thresholds(values)
+        row_offsets = D.detector_row_offsets(K)
+        P = int(row_offsets[-1].item())
+        rows = D.detector_rows(values, thresholds, K, row_offsets, P) if P else \
+            torch.empty((0, D.words_for(self.N)), dtype=torch.int64, device=D.dev())
+        return dict(rows=rows, K=K, thresholds=thresholds, row_offsets=row_offsets, group_base=gb, v0=v0, v1=v1,
+                    P=P, G=G)
+
+    def _tile_prior(self, tile, prior_tables):
+        """float64[P_t] log-prior of the tile's rows from the factored tables
+        (by_variable[V], by_window[W], normalisation) of LogisticRuleModel._prior_tables."""
+        import torch
+        from . import device as D
+        if prior_tables is None or tile['P'] == 0:
+            return None
+        bv, bw, norm = prior_tables
+        gb = tile['group_base']
+        nt = 1 + self.ok_slope.astype(np.int64)
+        w_of = np.repeat(np.arange(len(self.windows), dtype=np.int32), np.diff(gb))
+        within = np.arange(tile['G'], dtype=np.int64) - gb[w_of]
+        gvar = (tile['v0'] + within // nt[w_of]).astype(np.int32)
+        ident = torch.arange(tile['P'], dtype=torch.int64, device=D.dev())
+        rg = D.row_groups(ident, tile['row_offsets'])
+        return D.row_prior(rg, torch.as_tensor(gvar, device=D.dev()), torch.as_tensor(w_of, device=D.dev()),
+                           torch.as_tensor(np.asarray(bv, dtype=np.float64), device=D.dev()),
+                           torch.as_tensor(np.asarray(bw, dtype=np.float64), device=D.dev()), float(norm))
+
+    def _score_tile(self, tile, X, omega, kappa, sigma2, mask, prior_tables):
+        import torch
+        from . import device as D
+        P = tile['P']
+        p = int(np.shape(X)[1])
+        if self._buffers is None or self._buffers.out.shape[0] < P or self._buffers.p != p:
+            self._buffers = D.ScoreBuffers(max(P, 1), self.N, p)
+            self._buffers.p = p
+            self._draw = D.DrawBuffers(max(P, 1))
+        prior = self._tile_prior(tile, prior_tables)
+        d_mask = None if mask is None else torch.as_tensor(D.pack_mask(np.asarray(mask, dtype=bool)), device=D.dev())
+        out, status, stats = D.score_all_stats(tile['rows'], self.N, X, omega, kappa, sigma2, mask=d_mask,
+                                               buffers=self._buffers, out=self._buffers.out[:P], log_prior=prior,
+                                               draw_buffers=self._draw)
+        return out, status, stats, prior
+
+    def sweep(self, X, omega, kappa, sigma2, mask=None, prior_tables=None):
+        """Scores every candidate once.  Returns (log_total, n_candidates) and keeps one
+        (max, sum-exp) pair per tile for `draw`."""
+        import torch
+        from . import device as D
+        self._sweep_args = (X, omega, kappa, sigma2, mask, prior_tables)
+        pairs = torch.zeros((len(self.tiles), 2), dtype=torch.float64, device=D.dev())
+        pairs[:, 0] = -np.inf
+        counts = []
+        status_all = None
+        for t in range(len(self.tiles)):
+            tile = self.build_tile(t)
+            counts.append(tile['P'])
+            if tile['P'] == 0:
+                continue
+            out, status, stats, _ = self._score_tile(tile, X, omega, kappa, sigma2, mask, prior_tables)
+            pairs[t] = stats
+            status_all = status
+            del tile, out
+        if status_all is not None:
+            D.raise_on_status(status_all)
+        self.tile_stats = pairs.cpu().numpy()
+        self.tile_counts = np.array(counts, dtype=np.int64)
+        _, _, log_total = owner_of_marker(self.tile_stats, 0.5)
+        return log_total, int(self.tile_counts.sum())
+
+    def draw(self, u):
+        """Two-stage draw from the weights of the last sweep: (tile, index within the tile's
+        enumeration order, primitive tuple)."""
+        from . import device as D
+        if self.tile_stats is None:
+            raise RuntimeError("draw() needs a sweep() first")
+        t, u_local, _ = owner_of_marker(self.tile_stats, u)
+        X, omega, kappa, sigma2, mask, prior_tables = self._sweep_args
+        tile = self.build_tile(t)
+        out, status, stats, prior = self._score_tile(tile, X, omega, kappa, sigma2, mask, prior_tables)
+        k = int(D.draw_index(out, prior, u_local, stabilise=True, buffers=self._draw, reuse_stats=True).item())
+        k = min(k, tile['P'] - 1)
+        return t, k, self.describe(tile, k)
+
+    def describe(self, tile, k):
+        """(variable, window, type, direction, threshold) of row k of a built tile (rules.py:23-44)."""
+        ro = tile['row_offsets'].cpu().numpy()
+        g = int(np.searchsorted(ro, k, side='right') - 1)
+        slot = int(k - ro[g])
+        gb = tile['group_base']
+        w = int(np.searchsorted(gb, g, side='right') - 1)
+        nt = 2 if self.ok_slope[w] else 1
+        within = g - int(gb[w])
+        v = tile['v0'] + within // nt
+        ty = within % nt if nt == 2 else 1
+        thr = float(tile['thresholds'][g, slot >> 1].item())
+        return (int(v), self.windows[w], TYPES[ty], DIRECTIONS[slot & 1], thr)

@@ -1,0 +1,89 @@
+"""Streaming sweep (mitre_b200/streaming.py; SURVEY 8d, S3 'full grid streamed in tiles') against the
+resident population on problems that fit: every candidate of every tile carries the likelihood the
+resident, lexsorted table gives the same primitive; the per-tile (max, sum-exp) pairs add up to the
+resident log-sum-exp; the two-stage draw lands where a flat cumulative sum over the tiles'
+enumeration order lands."""
+import numpy as np
+import pytest
+
+from mitre_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(N, V, seed):
+    from mitre_b200 import rules as R
+    d = synthetic.make_series(N=N, V=V, T=(5, 9), span=(0.0, 40.0), seed=seed)
+    data = R.Dataset(d["X"], d["T"], d["y"], ["v%d" % i for i in range(V)], d["variable_weights"],
+                     d["experiment_start"], d["experiment_end"])
+    return d, data
+
+
+def _index_of(pop, tup):
+    """pop._index_of, except that slope thresholds are matched to 1e-9 relative: the streaming tiles
+    evaluate slopes with the phase-by-phase kernel, the resident N <= 63 population with the fused one
+    (same closed form, different summation order; DESIGN.md 'slope parity')."""
+    i = pop._index_of(tup)
+    if i is not None or tup[2] != 'slope':
+        return i
+    variable, window, type_, direction, threshold = tup
+    w = pop._window_lookup[(float(window[0]), float(window[1]))]
+    g = int(pop._group_base[w] + variable * 2)
+    K = int(pop._K_host[g])
+    thr = pop._thresholds_host()[g, :K]
+    k = int(np.argmin(np.abs(thr - threshold)))
+    assert abs(thr[k] - threshold) <= 1e-9 * max(abs(threshold), np.abs(thr).max())
+    r = int(pop._row_offsets_host[g]) + 2 * k + ('above', 'below').index(direction)
+    return int(pop._inv_perm_host()[r])
+
+
+@pytest.mark.parametrize("N,V,tile", [(70, 12, 5), (20, 9, 4), (130, 6, 6)])
+def test_streaming_sweep_matches_resident_population(N, V, tile):
+    import torch
+    from mitre_b200 import device as D, rules as R, streaming
+    d, data = _case(N, V, seed=N + V)
+    pop = R.DiscreteRulePopulation(None, 1.0, 4, tmax=None, data=data)
+    sw = streaming.StreamingSweep(data, 1.0, 4, tmax=None, tile_variables=tile)
+    assert sw.windows == pop.windows and len(sw.tiles) == -(-V // tile)
+    rng = np.random.RandomState(N)
+    P = len(pop)
+    state = synthetic.make_sweep_state(N, 2, np.stack([pop._truth_row(int(rng.randint(P))) for _ in range(8)]),
+                                       seed=1)
+    X, omega, kappa, mask = state["X"], state["omega"], state["y"] - 0.5, state["mask"]
+    bv = rng.normal(size=V)
+    bw = rng.normal(size=len(pop.windows))
+    prior_tables = (bv, bw, 0.7)
+    log_total, n = sw.sweep(X, omega, kappa, 100.0, mask=mask, prior_tables=prior_tables)
+    assert n == P
+    # resident reference: likelihoods in sorted order + the same factored prior per row
+    d_mask = torch.as_tensor(D.pack_mask(mask), device=D.dev())
+    res, status = D.score_all(pop.packed_truth, N, X, omega, kappa, 100.0, mask=d_mask)
+    D.raise_on_status(status)
+    res = res.cpu().numpy()
+    prior_res = np.array([bv[pop._tuple_at(i)[0]] + bw[pop._window_lookup[tuple(map(float, pop._tuple_at(i)[1]))]]
+                          - 0.7 for i in range(P)])
+    want_total = float(torch.logsumexp(torch.as_tensor(res + prior_res), 0))
+    assert abs(log_total - want_total) <= 1e-11 * abs(want_total)
+    # tile by tile: same primitive -> same likelihood and prior
+    flat_w = []
+    for t in range(len(sw.tiles)):
+        tile_d = sw.build_tile(t)
+        out, status, stats, prior = sw._score_tile(tile_d, X, omega, kappa, 100.0, mask, prior_tables)
+        out = out.cpu().numpy().copy()
+        prior = prior.cpu().numpy()
+        flat_w.append(out + prior)
+        for k in list(rng.randint(0, tile_d['P'], size=25)) + [0, tile_d['P'] - 1]:
+            tup = sw.describe(tile_d, int(k))
+            i = _index_of(pop, tup)
+            assert i is not None, tup
+            assert abs(out[k] - res[i]) <= 1e-12 * abs(res[i])
+            assert abs(prior[k] - prior_res[i]) <= 1e-12
+    flat_w = np.concatenate(flat_w)
+    # two-stage draw == flat draw over (tile-major, enumeration) order
+    offs = np.concatenate([[0], np.cumsum(sw.tile_counts)])
+    c = np.cumsum(np.exp(flat_w - flat_w.max()))
+    for u in [0.0, 0.2, 0.55, 0.93]:
+        t, k, tup = sw.draw(u)
+        want = int(np.sum(c < u * c[-1]))
+        assert abs(int(offs[t]) + k - want) <= 1
+        assert _index_of(pop, tup) is not None

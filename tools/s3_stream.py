@@ -1,0 +1,62 @@
+"""S3 (BASELINE configs[2] shape: N = 2000 subjects, T = 50, 12 intervals, mean + slope, full threshold
+grid) streamed in variable tiles (mitre_b200/streaming.py): per-tile detector evaluation + scoring +
+fused (max, sum-exp), then a two-stage draw.  usage: python tools/s3_stream.py [V] [tile_variables]
+Times V variables and extrapolates linearly to the configuration's 5000 (tiles are independent)."""
+import json
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, '.')
+from mitre_b200 import rules as R, streaming, synthetic  # noqa: E402
+import oracle  # noqa: E402
+from oracle import detectors_oracle as DO  # noqa: E402
+
+V = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+TILE = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+d = synthetic.make_shape("S3", seed=0, V=V)
+N = len(d["X"])
+data = R.Dataset(d["X"], d["T"], d["y"], ["v%d" % i for i in range(V)], d["variable_weights"],
+                 d["experiment_start"], d["experiment_end"])
+sw = streaming.StreamingSweep(data, d["tmin"], d["N_intervals"], tmax=d["tmax"], tile_variables=TILE)
+rng = np.random.RandomState(1)
+omega = rng.gamma(2.0, 0.125, size=N) + 0.05
+y = np.arange(N) % 2 == 0
+X = np.stack([(rng.rand(N) > 0.5).astype(float) for _ in range(3)] + [np.ones(N)], axis=1)
+mask = rng.rand(N) > 0.3
+bv, bw = rng.normal(size=V), rng.normal(size=len(sw.windows))
+sw.sweep(X, omega, y - 0.5, 100.0, mask=mask, prior_tables=(bv, bw, 0.0))      # warm-up (allocations)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+log_total, n = sw.sweep(X, omega, y - 0.5, 100.0, mask=mask, prior_tables=(bv, bw, 0.0))
+torch.cuda.synchronize()
+sweep_s = time.perf_counter() - t0
+# phase split on one tile
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+ev[0].record()
+tile = sw.build_tile(0)
+ev[1].record()
+out, status, stats, prior = sw._score_tile(tile, X, omega, y - 0.5, 100.0, mask, (bv, bw, 0.0))
+ev[2].record()
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+t, k, tup = sw.draw(0.4321)
+torch.cuda.synchronize()
+draw_s = time.perf_counter() - t0
+# parity spot check of one tile against the oracle
+idx = np.sort(rng.choice(tile['P'], size=24, replace=False))
+from mitre_b200 import device as D  # noqa: E402
+rows = D.unpack_rows(tile['rows'][torch.as_tensor(idx, device=D.dev())], N).cpu().numpy().astype(bool)
+want = oracle.likelihoods_of_all_options(X, omega, (y - 0.5) / omega, (rows * mask).astype(float), 100.0)
+got = out.cpu().numpy()[idx]
+print(json.dumps(dict(
+    N=N, V=V, tile_variables=TILE, tiles=len(sw.tiles), windows=len(sw.windows), candidates=n,
+    packed_bytes_never_materialised=int(n) * 8 * ((N + 63) // 64),
+    sweep_wall_s=sweep_s, evals_per_s=n / sweep_s,
+    tile0=dict(candidates=tile['P'], detectors_ms=ev[0].elapsed_time(ev[1]), score_ms=ev[1].elapsed_time(ev[2])),
+    draw_wall_s=draw_s, drawn=[int(t), int(k), str(tup)],
+    log_total=log_total, max_rel_diff_vs_oracle=float(np.max(np.abs(got - want) / np.abs(want))),
+    extrapolated_full_S3=dict(variables=5000, candidates=int(n * 5000 / V), sweep_s_1gpu=sweep_s * 5000 / V,
+                              sweep_s_8gpu=sweep_s * 5000 / V / 8))))
