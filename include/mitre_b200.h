@@ -109,6 +109,20 @@ int mitre_score_all_stats(void *stream, const uint64_t *packed_truth, int64_t P,
                           const double *log_prior, double *stats, void *stats_workspace,
                           size_t stats_workspace_bytes);
 
+/* Group scoring: the same log-likelihoods for ALL candidates of G (window, variable, type) groups,
+ * in the reference's ENUMERATION order (rules.py:465-511: group, threshold ascending, above then
+ * below), computed from the detector values without truth rows.  Within a group the candidates are
+ * nested sets along the sorted order of its N values, so their masked sums are suffix sums: O(N p)
+ * per group instead of per candidate (the equivalent algebra noted next to
+ * efficient_likelihoods.pyx:66-167's shared-prefix reuse).  values float64[G, N], thresholds
+ * float64[G, N-1], K int32[G], row_offsets int64[G+1] as produced by mitre_detector_values /
+ * _thresholds / _row_offsets (or mitre_detectors_fused); out float64[row_offsets[G]].
+ * mask / X / omega / kappa / workspace / status as for mitre_score_all.  N <= 65535. */
+int mitre_score_groups(void *stream, const double *values, const double *thresholds, const int32_t *K,
+                       const int64_t *row_offsets, int64_t G, const uint64_t *mask, const double *X,
+                       const double *omega, const double *kappa, int N, int p, double sigma2,
+                       void *workspace, size_t workspace_bytes, double *out, int32_t *status);
+
 /*
  * Drop-in compatibility form with the reference's exact arguments, all HOST pointers
  * (efficient_likelihoods.pyx:15-21): X[N,p], omega[N], response[N] (= kappa/omega),

@@ -356,30 +356,64 @@ rows_warp_kernel(const double *__restrict__ values, const double *__restrict__ t
     }
 }
 
-// rows, any N: one CTA per group; thread = (threshold k, word).
+// rows, any N: one CTA per group.
+//   1. rank_i = #{k : theta_k < v_i} by binary search (v_i > theta_k  <=>  k < rank_i; the
+//      thresholds are ascending and unique), one subject per thread;
+//   2. the ranks are bit-sliced with warp ballots: plane b, word w holds bit b of the ranks of
+//      subjects 64w .. 64w+63 in the packed-row bit order;
+//   3. thread = (threshold k, word w): `rank > k` for the word's 64 subjects at once, as a
+//      bit-serial comparison over the B = ceil(log2(K+1)) planes (~6 logic ops per plane instead
+//      of 64 fp64 compares per word), then one coalesced store of the (above, below) words.
 __global__ void __launch_bounds__(256)
 rows_block_kernel(const double *__restrict__ values, const double *__restrict__ thresholds,
                   const int32_t *__restrict__ K, const int64_t *__restrict__ row_offsets, int64_t G, int N,
                   int W64, uint64_t *__restrict__ packed)
 {
-    extern __shared__ __align__(16) double sval[];   // [N]
+    extern __shared__ __align__(16) uint64_t planes[];   // [B <= 32][W64]
+    uint32_t *planes32 = reinterpret_cast<uint32_t *>(planes);
+    const int lane = threadIdx.x & 31;
+    const int n_chunks = (N + 31) >> 5;
     for (int64_t g = blockIdx.x; g < G; g += gridDim.x) {
-        for (int i = threadIdx.x; i < N; i += blockDim.x) sval[i] = values[g * N + i];
-        __syncthreads();
         const int k_g = K[g];
         const double *tg = thresholds + g * (N - 1);
+        int B = 0;
+        while ((1 << B) <= k_g) ++B;                     // ranks are in [0, k_g]
+        // -- 1 + 2: ranks and their bit planes; a warp takes 32 consecutive subjects at a time --
+        for (int c = threadIdx.x >> 5; c < n_chunks; c += blockDim.x >> 5) {
+            const int i = c * 32 + lane;
+            int rank = 0;
+            if (i < N) {
+                const double v = values[g * N + i];
+                int lo = 0, hi = k_g;                    // first index with theta >= v (NaN: 0)
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (tg[mid] < v) lo = mid + 1; else hi = mid;
+                }
+                rank = lo;
+            }
+            for (int b = 0; b < B; ++b) {
+                const uint32_t bal = __ballot_sync(0xffffffffu, (rank >> b) & 1);
+                // subject 64w + j sits at bit 63 - j: the first 32 subjects of a word are its high half
+                if (lane == 0) planes32[(size_t)b * 2 * W64 + (c ^ 1)] = __brev(bal);
+            }
+        }
+        if ((n_chunks & 1) && threadIdx.x < B) planes32[(size_t)threadIdx.x * 2 * W64 + (n_chunks ^ 1)] = 0;
+        __syncthreads();
+        // -- 3: emit --
         uint64_t *dst = packed + row_offsets[g] * W64;
+        const int last_bits = N - 64 * (W64 - 1);
         for (int item = threadIdx.x; item < k_g * W64; item += blockDim.x) {
-            const int k = item / W64, w = item % W64;
-            const double th = tg[k];
-            uint64_t m = 0;
-            const int i0 = w * 64, i1 = min(N, i0 + 64);
-            for (int i = i0; i < i1; ++i)
-                if (sval[i] > th) m |= subject_bit(i);
-            const int nbits = i1 - i0;
-            const uint64_t valid = (nbits == 64) ? ~0ull : (~0ull << (64 - nbits));
-            dst[(size_t)(2 * k) * W64 + w] = m;
-            dst[(size_t)(2 * k + 1) * W64 + w] = ~m & valid;
+            const int k = item / W64, w = item - k * W64;
+            uint64_t gt = 0, eq = ~0ull;
+            for (int b = B - 1; b >= 0; --b) {
+                const uint64_t p = planes[(size_t)b * W64 + w];
+                const uint64_t kb = ((k >> b) & 1) ? ~0ull : 0ull;
+                gt |= eq & p & ~kb;
+                eq &= ~(p ^ kb);
+            }
+            const uint64_t valid = (w == W64 - 1 && last_bits < 64) ? (~0ull << (64 - last_bits)) : ~0ull;
+            dst[(size_t)(2 * k) * W64 + w] = gt;
+            dst[(size_t)(2 * k + 1) * W64 + w] = ~gt & valid;
         }
         __syncthreads();
     }
@@ -485,7 +519,7 @@ extern "C" int mitre_detector_rows(void *stream, const double *values, const dou
         rows_warp_kernel<<<capped_grid(ceil_div64(G, 8), 8), 256, 0, st>>>(values, thresholds, K, row_offsets,
                                                                           G, N, packed_truth);
     } else {
-        const size_t smem = (size_t)N * sizeof(double);
+        const size_t smem = (size_t)32 * words_for(N) * sizeof(uint64_t);   // up to 32 rank bit planes
         if (smem > smem_optin()) return MITRE_ERR_UNSUPPORTED;
         auto kern = rows_block_kernel;
         MITRE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

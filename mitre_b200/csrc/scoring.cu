@@ -744,6 +744,139 @@ score_wide8_kernel(const uint64_t *__restrict__ rows, int64_t P, int W64, const 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Group scoring: candidates in ENUMERATION order, straight from the detector values -- no truth
+// rows at all.  Within one (window, variable, type) group the 2K candidates are nested sets along
+// the sorted order of the group's N values ('above theta_k' = subjects whose rank exceeds k,
+// 'below' = the rest; rules.py:465-511), so every masked sum is a suffix sum of the per-subject
+// vectors q_i in rank order: O(N p) per GROUP instead of O(N p) (or N/8 table lookups) per
+// candidate.  One CTA per group:
+//   rank_i = #{k : theta_k < v_i} (binary search)  ->  bitonic sort of (rank, subject) keys in
+//   shared memory  ->  chunked suffix scan of q over the sorted order  ->  at every rank boundary
+//   finish the candidates above(k) = suffix, below(k) = total - suffix.
+// Used by the streaming sweep (streaming.py), where tables exist only tile by tile.
+// Deterministic: fixed sort, fixed scan order.
+// ---------------------------------------------------------------------------------------------
+template <int EP>
+__global__ void __launch_bounds__(256)
+score_groups_kernel(const double *__restrict__ values, const double *__restrict__ thresholds,
+                    const int32_t *__restrict__ K, const int64_t *__restrict__ row_offsets, int64_t G, int N,
+                    int NP2, const double *__restrict__ ws, double *__restrict__ out, int32_t *status)
+{
+    extern __shared__ __align__(16) uint32_t gkeys[];          // [NP2] (rank << 16 | subject), sorted in place
+    double *warp_tot = reinterpret_cast<double *>(gkeys + NP2);  // [8][EP]
+    double *total = warp_tot + 8 * EP;                           // [EP]
+    const double *q = ws + kHdr;
+    const double C0 = ws[0], inv_s2 = ws[1], s2 = ws[2];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int chunk = (N + 255) >> 8;
+    bool bad = false;
+    for (int64_t g = blockIdx.x; g < G; g += gridDim.x) {
+        const int k_g = K[g];
+        const double *tg = thresholds + g * (N - 1);
+        const double *vg = values + g * N;
+        for (int i = tid; i < NP2; i += 256) {
+            uint32_t key = 0xffffffffu;
+            if (i < N) {
+                const double v = vg[i];
+                int lo = 0, hi = k_g;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (tg[mid] < v) lo = mid + 1; else hi = mid;
+                }
+                key = ((uint32_t)lo << 16) | (uint32_t)i;
+            }
+            gkeys[i] = key;
+        }
+        __syncthreads();
+        for (int size = 2; size <= NP2; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int t = tid; t < (NP2 >> 1); t += 256) {
+                    const int lo_i = 2 * t - (t & (stride - 1));
+                    const int hi_i = lo_i + stride;
+                    const bool up = (lo_i & size) == 0;
+                    const uint32_t a = gkeys[lo_i], b = gkeys[hi_i];
+                    if ((a > b) == up) { gkeys[lo_i] = b; gkeys[hi_i] = a; }
+                }
+                __syncthreads();
+            }
+        }
+        // chunked suffix scan over sorted positions [0, N): thread t owns [t * chunk, (t + 1) * chunk)
+        const int j0 = tid * chunk, j1 = min(N, j0 + chunk);
+        double loc[EP];
+#pragma unroll
+        for (int e = 0; e < EP; ++e) loc[e] = 0.0;
+        for (int j = j1 - 1; j >= j0; --j) {
+            const double *qi = q + (size_t)(gkeys[j] & 0xffffu) * EP;
+#pragma unroll
+            for (int e = 0; e < EP; ++e) loc[e] += qi[e];
+        }
+        // exclusive suffix over threads: sum of the chunks of all higher threads
+        double suf[EP];
+#pragma unroll
+        for (int e = 0; e < EP; ++e) {
+            double x = loc[e];
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const double y = __shfl_down_sync(0xffffffffu, x, off);
+                if (lane + off < 32) x += y;
+            }
+            suf[e] = x - loc[e];                       // higher lanes of this warp
+            if (lane == 0) warp_tot[wid * EP + e] = x;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < EP; ++e) {
+            double hi_sum = 0.0;
+            for (int w = 7; w > wid; --w) hi_sum += warp_tot[w * EP + e];
+            suf[e] += hi_sum;
+            if (tid == 0) total[e] = suf[e] + loc[e];
+        }
+        __syncthreads();
+        double tot[EP];
+#pragma unroll
+        for (int e = 0; e < EP; ++e) tot[e] = total[e];
+        double *og = out + row_offsets[g];
+        for (int j = j1 - 1; j >= j0; --j) {
+            const uint32_t key = gkeys[j];
+            const double *qi = q + (size_t)(key & 0xffffu) * EP;
+#pragma unroll
+            for (int e = 0; e < EP; ++e) suf[e] += qi[e];          // suffix including position j
+            if (j == 0) break;
+            const int r = (int)(key >> 16), r_prev = (int)(gkeys[j - 1] >> 16);
+            for (int k = r_prev; k < r; ++k) {                     // thresholds between the two ranks
+                double below[EP];
+#pragma unroll
+                for (int e = 0; e < EP; ++e) below[e] = tot[e] - suf[e];
+                og[2 * k] = finish_candidate<EP>(suf, C0, inv_s2, s2, bad);
+                og[2 * k + 1] = finish_candidate<EP>(below, C0, inv_s2, s2, bad);
+            }
+        }
+        __syncthreads();
+    }
+    if (bad && status) atomicOr(reinterpret_cast<unsigned int *>(status), MITRE_STATUS_BAD_SCHUR);
+}
+
+template <int EP>
+static int launch_groups(cudaStream_t st, const double *values, const double *thresholds, const int32_t *K,
+                         const int64_t *row_offsets, int64_t G, int N, const double *ws, double *out,
+                         int32_t *status)
+{
+    int NP2 = 2;
+    while (NP2 < N) NP2 <<= 1;
+    const size_t smem = sizeof(uint32_t) * (size_t)NP2 + sizeof(double) * 9 * EP;
+    if (smem > smem_optin()) return MITRE_ERR_UNSUPPORTED;
+    auto kern = score_groups_kernel<EP>;
+    MITRE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    MITRE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+    int64_t blocks = (int64_t)sm_count() * (per_sm > 0 ? per_sm : 1);
+    if (G < blocks) blocks = G;
+    kern<<<(unsigned)blocks, 256, smem, st>>>(values, thresholds, K, row_offsets, G, N, NP2, ws, out, status);
+    MITRE_LAUNCH_CHECK();
+    return MITRE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Batched dense likelihood: one CTA per design matrix.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
@@ -1448,6 +1581,42 @@ extern "C" int mitre_score_all_stats(void *stream, const uint64_t *packed_truth,
         return mitre_weight_stats(stream, out, log_prior, P, stats, stats_workspace, stats_workspace_bytes);
     }
     return MITRE_OK;
+}
+
+extern "C" int mitre_score_groups(void *stream, const double *values, const double *thresholds,
+                                  const int32_t *K, const int64_t *row_offsets, int64_t G, const uint64_t *mask,
+                                  const double *X, const double *omega, const double *kappa, int N, int p,
+                                  double sigma2, void *workspace, size_t workspace_bytes, double *out,
+                                  int32_t *status)
+{
+    if (G < 0 || N <= 1 || p <= 0 || !X || !omega || !kappa || !workspace) return MITRE_ERR_INVALID;
+    if (G > 0 && (!values || !thresholds || !K || !row_offsets || !out)) return MITRE_ERR_INVALID;
+    if (p > MITRE_MAX_P || N > 65535) return MITRE_ERR_UNSUPPORTED;
+    if (!(sigma2 > 0.0)) return MITRE_ERR_INVALID;
+    if (workspace_bytes < mitre_score_workspace_bytes(N, p)) return MITRE_ERR_WORKSPACE;
+    cudaStream_t st = as_stream(stream);
+    double *ws = static_cast<double *>(workspace);
+    score_setup_kernel<<<1, 256, 0, st>>>(X, omega, kappa, mask, N, p, sigma2, ws, status);
+    MITRE_LAUNCH_CHECK();
+    if (G == 0) return MITRE_OK;
+    switch (ep_for(p)) {
+#define MITRE_EP_CASE(E) \
+    case E: return launch_groups<E>(st, values, thresholds, K, row_offsets, G, N, ws, out, status);
+        MITRE_EP_CASE(4)
+        MITRE_EP_CASE(6)
+        MITRE_EP_CASE(8)
+        MITRE_EP_CASE(10)
+        MITRE_EP_CASE(12)
+        MITRE_EP_CASE(14)
+        MITRE_EP_CASE(16)
+        MITRE_EP_CASE(18)
+        MITRE_EP_CASE(20)
+        MITRE_EP_CASE(22)
+        MITRE_EP_CASE(24)
+        MITRE_EP_CASE(26)
+#undef MITRE_EP_CASE
+    }
+    return MITRE_ERR_UNSUPPORTED;
 }
 
 extern "C" int mitre_score_all(void *stream, const uint64_t *packed_truth, int64_t P, int W64,

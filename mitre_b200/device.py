@@ -176,6 +176,27 @@ def score_all_stats(packed, N, X, omega, kappa, sigma2, mask=None, buffers=None,
     return out, buffers.status, draw_buffers.stats
 
 
+def score_groups(values, thresholds, K, row_offsets, P, X, omega, kappa, sigma2, mask=None, buffers=None,
+                 out=None):
+    """Log-likelihood of every candidate of G groups in ENUMERATION order, from the detector values
+    (mitre_score_groups: suffix sums along each group's sorted order; no truth rows).
+    Returns (out float64[P], status)."""
+    G, N = values.shape
+    X = _dev_f64(X)
+    omega = _dev_f64(omega)
+    kappa = _dev_f64(kappa)
+    p = X.shape[1]
+    if buffers is None:
+        buffers = ScoreBuffers(max(P, 1), N, p)
+    if out is None:
+        out = buffers.out[:P] if buffers.out.shape[0] >= P else torch.empty(P, dtype=F64, device=dev())
+    ws = buffers.workspace
+    check(lib().mitre_score_groups(_stream(), _p(values), _p(thresholds), _p(K), _p(row_offsets), G, _p(mask),
+                                   _p(X), _p(omega), _p(kappa), int(N), int(p), float(sigma2), _p(ws), ws.numel(),
+                                   _p(out), _p(buffers.status)), "mitre_score_groups")
+    return out, buffers.status
+
+
 def raise_on_status(status):
     """Synchronises; maps device status flags to numpy's LinAlgError like the reference
     (efficient_likelihoods.pyx:42 -> np.linalg.cholesky)."""

@@ -4,10 +4,12 @@ full threshold grid -> 3.1e9 candidates, 0.8 TB packed; the reference would need
 and a 50 TB float64 temporary, logit_rules.py:214-217).
 
 The table is never materialised.  Variables are walked in tiles; per tile the detector kernels
-rebuild values, thresholds and truth rows (every group depends only on its own variable's series,
-rules.py:585-599), the scoring kernel evaluates the tile's candidates and reduces
-(max, sum exp) of log-likelihood + log-prior in the same launch, and the rows are dropped.  What
-survives a sweep is one 16-byte pair per tile: enough for the log-sum-exp the add/remove moves
+rebuild values and thresholds (every group depends only on its own variable's series,
+rules.py:585-599) and the tile's candidates are scored straight from them: within a group the 2K
+candidates are nested sets along the sorted order of its values, so mitre_score_groups gets every
+masked sum as a suffix sum -- O(N p) per group, no truth rows at all (group_scoring=False builds
+the rows and uses the row kernels instead; the tests compare the two).  (max, sum exp) of
+log-likelihood + log-prior is reduced per tile.  What survives a sweep is one 16-byte pair per tile: enough for the log-sum-exp the add/remove moves
 need (logit_rules.py:959, 1064) and for a two-stage draw -- pick the tile that holds
 u * total, rebuild that one tile, draw inside it -- exactly the exchange `parallel.two_stage_draw`
 makes between ranks, here made between tiles in time.
@@ -26,7 +28,7 @@ from .rules import DIRECTIONS, TYPES
 
 
 class StreamingSweep:
-    def __init__(self, data, tmin, N_intervals, tmax=None, tile_variables=64):
+    def __init__(self, data, tmin, N_intervals, tmax=None, tile_variables=64, group_scoring=True):
         import torch
         from . import device as D
         from . import rules as R
@@ -34,6 +36,7 @@ class StreamingSweep:
         self.N = data.n_subjects
         self.V = data.n_variables
         self.tile_variables = int(tile_variables)
+        self.group_scoring = bool(group_scoring)
         pop = R.DiscreteRulePopulation.__new__(R.DiscreteRulePopulation)
         pop.model, pop.data, pop.tmin = None, data, tmin
         pop.tmax = np.inf if tmax is None else tmax
@@ -60,8 +63,9 @@ class StreamingSweep:
         np.cumsum(per_window, out=gb[1:])
         return gb
 
-    def build_tile(self, t):
-        """-> dict(rows int64[P_t, W64], K, thresholds, row_offsets (device), group_base (host), v0, v1)."""
+    def build_tile(self, t, rows=False):
+        """-> dict(values, K, thresholds, row_offsets (device), group_base (host), v0, v1, P, G) and, on
+        request, rows int64[P_t, W64] in enumeration order (scoring does not need them)."""
         import torch
         from . import device as D
         v0, v1 = self.tiles[t]
@@ -74,10 +78,21 @@ class StreamingSweep:
         thresholds, K = D.detector_thresholds(values)
         row_offsets = D.detector_row_offsets(K)
         P = int(row_offsets[-1].item())
-        rows = D.detector_rows(values, thresholds, K, row_offsets, P) if P else \
-            torch.empty((0, D.words_for(self.N)), dtype=torch.int64, device=D.dev())
-        return dict(rows=rows, K=K, thresholds=thresholds, row_offsets=row_offsets, group_base=gb, v0=v0, v1=v1,
-                    P=P, G=G)
+        tile = dict(values=values, K=K, thresholds=thresholds, row_offsets=row_offsets, group_base=gb, v0=v0,
+                    v1=v1, P=P, G=G)
+        if rows:
+            tile['rows'] = D.detector_rows(values, thresholds, K, row_offsets, P) if P else \
+                torch.empty((0, D.words_for(self.N)), dtype=torch.int64, device=D.dev())
+        return tile
+
+    def truth_row(self, tile, k):
+        """bool[N] truth vector of candidate k of a built tile (what the sampler appends to X)."""
+        ro = tile['row_offsets'].cpu().numpy()
+        g = int(np.searchsorted(ro, k, side='right') - 1)
+        slot = int(k - ro[g])
+        v = tile['values'][g].cpu().numpy()
+        thr = float(tile['thresholds'][g, slot >> 1].item())
+        return (v > thr) if (slot & 1) == 0 else (v <= thr)          # rules.py:494-497
 
     def _tile_prior(self, tile, prior_tables):
         """float64[P_t] log-prior of the tile's rows from the factored tables
@@ -109,9 +124,18 @@ class StreamingSweep:
             self._draw = D.DrawBuffers(max(P, 1))
         prior = self._tile_prior(tile, prior_tables)
         d_mask = None if mask is None else torch.as_tensor(D.pack_mask(np.asarray(mask, dtype=bool)), device=D.dev())
-        out, status, stats = D.score_all_stats(tile['rows'], self.N, X, omega, kappa, sigma2, mask=d_mask,
-                                               buffers=self._buffers, out=self._buffers.out[:P], log_prior=prior,
-                                               draw_buffers=self._draw)
+        if self.group_scoring:
+            # suffix sums along each group's sorted order: no truth rows (mitre_score_groups)
+            out, status = D.score_groups(tile['values'], tile['thresholds'], tile['K'], tile['row_offsets'], P,
+                                         X, omega, kappa, sigma2, mask=d_mask, buffers=self._buffers,
+                                         out=self._buffers.out[:P])
+            stats = D.weight_stats(out, prior, buffers=self._draw)
+        else:
+            if 'rows' not in tile:
+                tile['rows'] = D.detector_rows(tile['values'], tile['thresholds'], tile['K'], tile['row_offsets'], P)
+            out, status, stats = D.score_all_stats(tile['rows'], self.N, X, omega, kappa, sigma2, mask=d_mask,
+                                                   buffers=self._buffers, out=self._buffers.out[:P],
+                                                   log_prior=prior, draw_buffers=self._draw)
         return out, status, stats, prior
 
     def sweep(self, X, omega, kappa, sigma2, mask=None, prior_tables=None):

@@ -37,13 +37,14 @@ def _index_of(pop, tup):
     return int(pop._inv_perm_host()[r])
 
 
+@pytest.mark.parametrize("group_scoring", [True, False])
 @pytest.mark.parametrize("N,V,tile", [(70, 12, 5), (20, 9, 4), (130, 6, 6)])
-def test_streaming_sweep_matches_resident_population(N, V, tile):
+def test_streaming_sweep_matches_resident_population(N, V, tile, group_scoring):
     import torch
     from mitre_b200 import device as D, rules as R, streaming
     d, data = _case(N, V, seed=N + V)
     pop = R.DiscreteRulePopulation(None, 1.0, 4, tmax=None, data=data)
-    sw = streaming.StreamingSweep(data, 1.0, 4, tmax=None, tile_variables=tile)
+    sw = streaming.StreamingSweep(data, 1.0, 4, tmax=None, tile_variables=tile, group_scoring=group_scoring)
     assert sw.windows == pop.windows and len(sw.tiles) == -(-V // tile)
     rng = np.random.RandomState(N)
     P = len(pop)
@@ -78,6 +79,7 @@ def test_streaming_sweep_matches_resident_population(N, V, tile):
             assert i is not None, tup
             assert abs(out[k] - res[i]) <= 1e-12 * abs(res[i])
             assert abs(prior[k] - prior_res[i]) <= 1e-12
+            assert np.array_equal(sw.truth_row(tile_d, int(k)), pop._truth_row(i))
     flat_w = np.concatenate(flat_w)
     # two-stage draw == flat draw over (tile-major, enumeration) order
     offs = np.concatenate([[0], np.cumsum(sw.tile_counts)])
@@ -87,3 +89,39 @@ def test_streaming_sweep_matches_resident_population(N, V, tile):
         want = int(np.sum(c < u * c[-1]))
         assert abs(int(offs[t]) + k - want) <= 1
         assert _index_of(pop, tup) is not None
+
+
+@pytest.mark.parametrize("N,p", [(2, 1), (3, 2), (17, 1), (35, 4), (64, 3), (65, 2), (200, 5), (700, 4), (2000, 4)])
+def test_score_groups_equals_row_scoring_and_oracle(N, p):
+    """mitre_score_groups (suffix sums along each group's sorted order) against the row kernels on the
+    same tile, and against the C oracle on sampled candidates; ties and zero-inflated series included."""
+    import torch
+    import oracle
+    from mitre_b200 import device as D, streaming
+    from oracle import detectors_oracle as DO
+    V = 3 if N > 300 else 7
+    d, data = _case(N, V, seed=3 * N + p)
+    sw = streaming.StreamingSweep(data, 1.0, 3, tmax=None, tile_variables=V)
+    tile = sw.build_tile(0, rows=True)
+    P = tile['P']
+    if N == 2:
+        assert P > 0
+    rng = np.random.RandomState(N + p)
+    X = np.concatenate([(rng.rand(N, p - 1) > 0.5).astype(float), np.ones((N, 1))], axis=1)
+    omega = rng.gamma(2.0, 0.125, size=N) + 0.05
+    y = rng.rand(N) > 0.5
+    mask = rng.rand(N) > 0.25
+    d_mask = torch.as_tensor(D.pack_mask(mask), device=D.dev())
+    a, status = D.score_groups(tile['values'], tile['thresholds'], tile['K'], tile['row_offsets'], P, X, omega,
+                               y - 0.5, 100.0, mask=d_mask)
+    D.raise_on_status(status)
+    a = a.cpu().numpy().copy()
+    b, status = D.score_all(tile['rows'], N, X, omega, y - 0.5, 100.0, mask=d_mask)
+    D.raise_on_status(status)
+    b = b.cpu().numpy()
+    assert np.isfinite(a).all()
+    assert np.max(np.abs(a - b) / np.abs(b)) <= 1e-11
+    idx = np.unique(np.concatenate([[0, 1, P - 2, P - 1], rng.randint(0, P, size=20)]))
+    rows = D.unpack_rows(tile['rows'][torch.as_tensor(idx, device=D.dev())], N).cpu().numpy().astype(bool)
+    want = oracle.likelihoods_of_all_options(X, omega, (y - 0.5) / omega, (rows & mask).astype(float), 100.0)
+    assert np.max(np.abs(a[idx] - want) / np.abs(want)) <= 1e-9

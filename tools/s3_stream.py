@@ -40,15 +40,17 @@ tile = sw.build_tile(0)
 ev[1].record()
 out, status, stats, prior = sw._score_tile(tile, X, omega, y - 0.5, 100.0, mask, (bv, bw, 0.0))
 ev[2].record()
+out = out.clone()          # the sweep's output buffer is reused by draw()
 torch.cuda.synchronize()
 t0 = time.perf_counter()
 t, k, tup = sw.draw(0.4321)
 torch.cuda.synchronize()
 draw_s = time.perf_counter() - t0
 # parity spot check of one tile against the oracle
+check = sw.build_tile(0, rows=True)
 idx = np.sort(rng.choice(tile['P'], size=24, replace=False))
 from mitre_b200 import device as D  # noqa: E402
-rows = D.unpack_rows(tile['rows'][torch.as_tensor(idx, device=D.dev())], N).cpu().numpy().astype(bool)
+rows = D.unpack_rows(check['rows'][torch.as_tensor(idx, device=D.dev())], N).cpu().numpy().astype(bool)
 want = oracle.likelihoods_of_all_options(X, omega, (y - 0.5) / omega, (rows * mask).astype(float), 100.0)
 got = out.cpu().numpy()[idx]
 print(json.dumps(dict(
