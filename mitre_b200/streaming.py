@@ -12,7 +12,9 @@ the rows and uses the row kernels instead; the tests compare the two).  (max, su
 log-likelihood + log-prior is reduced per tile.  What survives a sweep is one 16-byte pair per tile: enough for the log-sum-exp the add/remove moves
 need (logit_rules.py:959, 1064) and for a two-stage draw -- pick the tile that holds
 u * total, rebuild that one tile, draw inside it -- exactly the exchange `parallel.two_stage_draw`
-makes between ranks, here made between tiles in time.
+makes between ranks, here made between tiles in time.  With a process group the tiles are dealt
+round-robin to the ranks (each GPU stages the series and walks its own tiles), the pairs are
+all-gathered (16 bytes per tile) and the tile's owner makes the inner draw.
 
 Candidates are indexed (tile, position in the tile's enumeration order).  That is a different
 ORDER from the reference's global lexsort (which nothing that large can compute), over the same
@@ -23,12 +25,12 @@ resident population gives it.
 """
 import numpy as np
 
-from .parallel import owner_of_marker
+from .parallel import owner_of_marker, world
 from .rules import DIRECTIONS, TYPES
 
 
 class StreamingSweep:
-    def __init__(self, data, tmin, N_intervals, tmax=None, tile_variables=64, group_scoring=True):
+    def __init__(self, data, tmin, N_intervals, tmax=None, tile_variables=64, group_scoring=True, group=None):
         import torch
         from . import device as D
         from . import rules as R
@@ -37,6 +39,8 @@ class StreamingSweep:
         self.V = data.n_variables
         self.tile_variables = int(tile_variables)
         self.group_scoring = bool(group_scoring)
+        self.group = group
+        self.ws, self.rank = world(group)
         pop = R.DiscreteRulePopulation.__new__(R.DiscreteRulePopulation)
         pop.model, pop.data, pop.tmin = None, data, tmin
         pop.tmax = np.inf if tmax is None else tmax
@@ -144,13 +148,15 @@ class StreamingSweep:
         import torch
         from . import device as D
         self._sweep_args = (X, omega, kappa, sigma2, mask, prior_tables)
-        pairs = torch.zeros((len(self.tiles), 2), dtype=torch.float64, device=D.dev())
+        import torch.distributed as dist
+        n_tiles = len(self.tiles)
+        pairs = torch.zeros((n_tiles, 2), dtype=torch.float64, device=D.dev())
         pairs[:, 0] = -np.inf
-        counts = []
+        counts = torch.zeros(n_tiles, dtype=torch.int64, device=D.dev())
         status_all = None
-        for t in range(len(self.tiles)):
+        for t in range(self.rank, n_tiles, self.ws):          # tiles are dealt round-robin to the ranks
             tile = self.build_tile(t)
-            counts.append(tile['P'])
+            counts[t] = tile['P']
             if tile['P'] == 0:
                 continue
             out, status, stats, _ = self._score_tile(tile, X, omega, kappa, sigma2, mask, prior_tables)
@@ -159,8 +165,15 @@ class StreamingSweep:
             del tile, out
         if status_all is not None:
             D.raise_on_status(status_all)
+        if self.ws > 1:
+            # the sweep's only exchange: 16 bytes per tile (every rank ends up with every tile's pair)
+            gathered = torch.empty((self.ws, n_tiles, 2), dtype=torch.float64, device=D.dev())
+            dist.all_gather_into_tensor(gathered, pairs, group=self.group)
+            owner = torch.arange(n_tiles, device=D.dev()) % self.ws
+            pairs = gathered[owner, torch.arange(n_tiles, device=D.dev())]
+            dist.all_reduce(counts, group=self.group)
         self.tile_stats = pairs.cpu().numpy()
-        self.tile_counts = np.array(counts, dtype=np.int64)
+        self.tile_counts = counts.cpu().numpy()
         _, _, log_total = owner_of_marker(self.tile_stats, 0.5)
         return log_total, int(self.tile_counts.sum())
 
@@ -172,11 +185,19 @@ class StreamingSweep:
             raise RuntimeError("draw() needs a sweep() first")
         t, u_local, _ = owner_of_marker(self.tile_stats, u)
         X, omega, kappa, sigma2, mask, prior_tables = self._sweep_args
-        tile = self.build_tile(t)
-        out, status, stats, prior = self._score_tile(tile, X, omega, kappa, sigma2, mask, prior_tables)
-        k = int(D.draw_index(out, prior, u_local, stabilise=True, buffers=self._draw, reuse_stats=True).item())
-        k = min(k, tile['P'] - 1)
-        return t, k, self.describe(tile, k)
+        result = [None]
+        if t % self.ws == self.rank:                           # the tile's owner redraws inside it
+            tile = self.build_tile(t)
+            out, status, stats, prior = self._score_tile(tile, X, omega, kappa, sigma2, mask, prior_tables)
+            k = int(D.draw_index(out, prior, u_local, stabilise=True, buffers=self._draw, reuse_stats=True).item())
+            k = min(k, tile['P'] - 1)
+            result = [(t, k, self.describe(tile, k))]
+        if self.ws > 1:
+            import torch.distributed as dist
+            src = t % self.ws
+            dist.broadcast_object_list(result, src=dist.get_global_rank(self.group, src) if self.group is not None
+                                       else src, group=self.group)
+        return result[0]
 
     def describe(self, tile, k):
         """(variable, window, type, direction, threshold) of row k of a built tile (rules.py:23-44)."""

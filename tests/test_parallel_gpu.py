@@ -152,3 +152,61 @@ def test_sharded_population_two_gpus_matches_single_gpu_build():
     assert sorted(o[3] for o in out) == [(0, 6), (6, 11)]
     for rank, P, P_plain, _, ok_rows, ok_perm, ok_desc, ok_score in out:
         assert P == P_plain and ok_rows and ok_perm and ok_desc and ok_score
+
+
+# ---- streaming sweep with its tiles dealt to the ranks ---------------------------------------------
+
+def _stream_worker(rank, ws, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=ws, device_id=torch.device("cuda", rank))
+    try:
+        from mitre_b200 import rules as R, streaming, synthetic
+        solo = [dist.new_group([r]) for r in range(ws)][rank]        # every rank must create every group
+        d = synthetic.make_series(N=90, V=10, T=(5, 9), span=(0.0, 40.0), seed=21)
+        data = R.Dataset(d["X"], d["T"], d["y"], ["v%d" % i for i in range(10)], d["variable_weights"],
+                         d["experiment_start"], d["experiment_end"])
+        rng = np.random.RandomState(4)
+        N = 90
+        X = np.concatenate([(rng.rand(N, 2) > 0.5).astype(float), np.ones((N, 1))], axis=1)
+        omega = rng.gamma(2.0, 0.125, size=N) + 0.05
+        y = rng.rand(N) > 0.5
+        mask = rng.rand(N) > 0.2
+        tables = (rng.normal(size=10), rng.normal(size=64), 0.3)
+        res = {}
+        for name, group in (("solo", solo), ("all", None)):
+            sw = streaming.StreamingSweep(data, 1.0, 4, tmax=None, tile_variables=3, group=group)
+            tabs = (tables[0], tables[1][:len(sw.windows)], tables[2])
+            log_total, n = sw.sweep(X, omega, y - 0.5, 100.0, mask=mask, prior_tables=tabs)
+            draws = [sw.draw(u) for u in (0.05, 0.5, 0.95)]
+            res[name] = (log_total, n, [(t, k, repr(tup)) for t, k, tup in draws], sw.ws)
+        q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_streaming_sweep_two_gpus_matches_one():
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ws = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_stream_worker, args=(r, ws, port, q)) for r in range(ws)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=300) for _ in range(ws)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, res in out:
+        assert res["solo"][3] == 1 and res["all"][3] == 2
+        assert res["all"][1] == res["solo"][1]
+        assert abs(res["all"][0] - res["solo"][0]) <= 1e-12 * abs(res["solo"][0])
+        assert res["all"][2] == res["solo"][2]
+    assert out[0][1]["all"] == out[1][1]["all"]

@@ -14,6 +14,13 @@ from mitre_b200 import rules as R, streaming, synthetic  # noqa: E402
 import oracle  # noqa: E402
 from oracle import detectors_oracle as DO  # noqa: E402
 
+import os  # noqa: E402
+WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+RANK = int(os.environ.get("RANK", "0"))
+if WORLD > 1:      # torchrun: the tiles are dealt to the ranks
+    import torch.distributed as dist
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
 V = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 TILE = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 d = synthetic.make_shape("S3", seed=0, V=V)
@@ -29,14 +36,20 @@ mask = rng.rand(N) > 0.3
 bv, bw = rng.normal(size=V), rng.normal(size=len(sw.windows))
 sw.sweep(X, omega, y - 0.5, 100.0, mask=mask, prior_tables=(bv, bw, 0.0))      # warm-up (allocations)
 torch.cuda.synchronize()
+if WORLD > 1:
+    dist.barrier()
 t0 = time.perf_counter()
-log_total, n = sw.sweep(X, omega, y - 0.5, 100.0, mask=mask, prior_tables=(bv, bw, 0.0))
+REPS = 3
+for _ in range(REPS):
+    log_total, n = sw.sweep(X, omega, y - 0.5, 100.0, mask=mask, prior_tables=(bv, bw, 0.0))
 torch.cuda.synchronize()
-sweep_s = time.perf_counter() - t0
+if WORLD > 1:
+    dist.barrier()
+sweep_s = (time.perf_counter() - t0) / REPS
 # phase split on one tile
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
 ev[0].record()
-tile = sw.build_tile(0)
+tile = sw.build_tile(RANK % len(sw.tiles))
 ev[1].record()
 out, status, stats, prior = sw._score_tile(tile, X, omega, y - 0.5, 100.0, mask, (bv, bw, 0.0))
 ev[2].record()
@@ -47,18 +60,21 @@ t, k, tup = sw.draw(0.4321)
 torch.cuda.synchronize()
 draw_s = time.perf_counter() - t0
 # parity spot check of one tile against the oracle
-check = sw.build_tile(0, rows=True)
+check = sw.build_tile(RANK % len(sw.tiles), rows=True)
 idx = np.sort(rng.choice(tile['P'], size=24, replace=False))
 from mitre_b200 import device as D  # noqa: E402
 rows = D.unpack_rows(check['rows'][torch.as_tensor(idx, device=D.dev())], N).cpu().numpy().astype(bool)
 want = oracle.likelihoods_of_all_options(X, omega, (y - 0.5) / omega, (rows * mask).astype(float), 100.0)
 got = out.cpu().numpy()[idx]
-print(json.dumps(dict(
-    N=N, V=V, tile_variables=TILE, tiles=len(sw.tiles), windows=len(sw.windows), candidates=n,
+if RANK == 0:
+  print(json.dumps(dict(
+    n_gpus=WORLD, N=N, V=V, tile_variables=TILE, tiles=len(sw.tiles), windows=len(sw.windows), candidates=n,
     packed_bytes_never_materialised=int(n) * 8 * ((N + 63) // 64),
     sweep_wall_s=sweep_s, evals_per_s=n / sweep_s,
     tile0=dict(candidates=tile['P'], detectors_ms=ev[0].elapsed_time(ev[1]), score_ms=ev[1].elapsed_time(ev[2])),
     draw_wall_s=draw_s, drawn=[int(t), int(k), str(tup)],
     log_total=log_total, max_rel_diff_vs_oracle=float(np.max(np.abs(got - want) / np.abs(want))),
-    extrapolated_full_S3=dict(variables=5000, candidates=int(n * 5000 / V), sweep_s_1gpu=sweep_s * 5000 / V,
-                              sweep_s_8gpu=sweep_s * 5000 / V / 8))))
+    extrapolated_full_S3=dict(variables=5000, candidates=int(n * 5000 / V), n_gpus=WORLD,
+                              sweep_s=sweep_s * 5000 / V))))
+if WORLD > 1:
+    dist.destroy_process_group()
