@@ -59,12 +59,18 @@ sort_scatter_kernel(const uint64_t *__restrict__ rows, const uint64_t *__restric
 {
     __shared__ int cnt[8][256];            // per-warp digit counts, then running bases
     __shared__ long long gbase[256];       // global offset of (digit, this tile)
+    __shared__ int dbase[256];             // offset of the digit's run inside the tile
+    __shared__ int wsum[8];
+    __shared__ uint64_t skey[KV ? kSortTile : 1];
+    __shared__ int64_t sidx[kSortTile];
+    __shared__ uint8_t sdig[kSortTile];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < 8 * 256; i += 256) (&cnt[0][0])[i] = 0;
     gbase[threadIdx.x] = offsets[(int64_t)threadIdx.x * ntiles + blockIdx.x];
     __syncthreads();
 
-    const int64_t wbase = (int64_t)blockIdx.x * kSortTile + (int64_t)wid * (kRounds * 32);
+    const int64_t tile_base = (int64_t)blockIdx.x * kSortTile;
+    const int64_t wbase = tile_base + (int64_t)wid * (kRounds * 32);
     int dig[kRounds];
     uint64_t key[kRounds];
     int64_t idx[kRounds];
@@ -89,7 +95,7 @@ sort_scatter_kernel(const uint64_t *__restrict__ rows, const uint64_t *__restric
         __syncwarp();
     }
     __syncthreads();
-    // exclusive prefix over warps for digit = threadIdx.x
+    // digit = threadIdx.x: exclusive prefix over warps, then exclusive prefix over digits of the totals
     {
         int run = 0;
         for (int w = 0; w < 8; ++w) {
@@ -97,8 +103,22 @@ sort_scatter_kernel(const uint64_t *__restrict__ rows, const uint64_t *__restric
             cnt[w][threadIdx.x] = run;
             run += c;
         }
+        int inc = run;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, inc, off);
+            if (lane >= off) inc += y;
+        }
+        if (lane == 31) wsum[wid] = inc;
+        __syncthreads();
+        int before = 0;
+        for (int w = 0; w < wid; ++w) before += wsum[w];
+        dbase[threadIdx.x] = before + inc - run;
     }
     __syncthreads();
+    // stable position inside the tile, ordered by digit: stage there, then write digit runs out
+    // with consecutive threads on consecutive addresses (a direct scatter writes 8-byte pieces of
+    // 256 different runs from every warp)
 #pragma unroll
     for (int r = 0; r < kRounds; ++r) {
         const unsigned peers = __match_any_sync(0xffffffffu, dig[r]);
@@ -106,13 +126,21 @@ sort_scatter_kernel(const uint64_t *__restrict__ rows, const uint64_t *__restric
         if (dig[r] >= 0) base = cnt[wid][dig[r]];
         __syncwarp();
         if (dig[r] >= 0) {
-            const int rank = base + __popc(peers & lt);
-            const int64_t dst = gbase[dig[r]] + rank;
-            perm_out[dst] = idx[r];
-            if (KV) keys_out[dst] = key[r];
+            const int local = dbase[dig[r]] + base + __popc(peers & lt);
+            sidx[local] = idx[r];
+            sdig[local] = (uint8_t)dig[r];
+            if (KV) skey[local] = key[r];
             if ((peers & lt) == 0) cnt[wid][dig[r]] = base + __popc(peers);
         }
         __syncwarp();
+    }
+    __syncthreads();
+    const int n_valid = (int)((P - tile_base < kSortTile) ? (P - tile_base) : kSortTile);
+    for (int i = threadIdx.x; i < n_valid; i += 256) {
+        const int dg = sdig[i];
+        const int64_t dst = gbase[dg] + (i - dbase[dg]);
+        perm_out[dst] = sidx[i];
+        if (KV) keys_out[dst] = skey[i];
     }
 }
 

@@ -36,6 +36,11 @@ def main():
         same = all(torch.equal(a, b) for a, b in zip(ref, out))
         print("%-36s %.3f ms  identical=%s" % (name, ms, same))
     lib().mitre_set_detector_split(1)
+    N = fa[1]
+    padded = ref[3]
+    D.lexsort_rows(padded.view(-1, 1), N + 1)
+    ms = min(bench.cuda_time_ms(torch, lambda: D.lexsort_rows(padded.view(-1, 1), N + 1), 3) for _ in range(2))
+    print("lexsort of the padded table (%d slots): %.2f ms" % (padded.numel(), ms))
 
 
 if __name__ == "__main__":
