@@ -98,13 +98,55 @@ class StreamingSweep:
         thr = float(tile['thresholds'][g, slot >> 1].item())
         return (v > thr) if (slot & 1) == 0 else (v <= thr)          # rules.py:494-497
 
-    def _tile_prior(self, tile, prior_tables):
+    def locate(self, primitive, tile=None):
+        """(tile index, position in the tile's enumeration order) of a primitive tuple
+        (variable, (t0, t1), type, direction, threshold), or None if it is not a candidate.  Builds the
+        tile unless the caller passes the built one."""
+        try:
+            variable, window, type_, direction, threshold = primitive
+            w = self.windows.index((window[0], window[1]))
+        except (TypeError, ValueError, IndexError):
+            return None
+        if not (0 <= variable < self.V) or type_ not in TYPES or direction not in DIRECTIONS:
+            return None
+        ok = bool(self.ok_slope[w])
+        if type_ == 'slope' and not ok:
+            return None
+        t = variable // self.tile_variables
+        if tile is None:
+            tile = self.build_tile(t)
+        g = int(tile['group_base'][w]) + (variable - tile['v0']) * (2 if ok else 1) + (TYPES.index(type_) if ok else 0)
+        K = int(tile['K'][g].item())
+        thr = tile['thresholds'][g, :K].cpu().numpy()
+        k = int(np.searchsorted(thr, threshold))
+        if k >= K or thr[k] != threshold:
+            return None
+        return t, int(tile['row_offsets'][g].item()) + 2 * k + DIRECTIONS.index(direction)
+
+    def _tile_prior(self, tile, prior_tables, deltas=None):
         """float64[P_t] log-prior of the tile's rows from the factored tables
-        (by_variable[V], by_window[W], normalisation) of LogisticRuleModel._prior_tables."""
+        (by_variable[V], by_window[W], normalisation) of LogisticRuleModel._prior_tables, plus the
+        sparse corrections `deltas` {(tile, position): additive term} the sampler applies to the
+        primitives already in the rule list (logit_rules.py:861-862, 1058-1066)."""
         import torch
         from . import device as D
-        if prior_tables is None or tile['P'] == 0:
+        if tile['P'] == 0:
             return None
+        mine = [(k, dv) for (t, k), dv in (deltas or {}).items() if self.tiles[t][0] == tile['v0']]
+        if prior_tables is None:
+            if not mine:
+                return None
+            prior = torch.zeros(tile['P'], dtype=torch.float64, device=D.dev())
+        else:
+            prior = self._tile_prior_tables(tile, prior_tables)
+        if mine:
+            idx = torch.as_tensor([k for k, _ in mine], dtype=torch.int64, device=D.dev())
+            prior[idx] += torch.as_tensor([dv for _, dv in mine], dtype=torch.float64, device=D.dev())
+        return prior
+
+    def _tile_prior_tables(self, tile, prior_tables):
+        import torch
+        from . import device as D
         bv, bw, norm = prior_tables
         gb = tile['group_base']
         nt = 1 + self.ok_slope.astype(np.int64)
@@ -117,7 +159,7 @@ class StreamingSweep:
                            torch.as_tensor(np.asarray(bv, dtype=np.float64), device=D.dev()),
                            torch.as_tensor(np.asarray(bw, dtype=np.float64), device=D.dev()), float(norm))
 
-    def _score_tile(self, tile, X, omega, kappa, sigma2, mask, prior_tables):
+    def _score_tile(self, tile, X, omega, kappa, sigma2, mask, prior_tables, deltas=None):
         import torch
         from . import device as D
         P = tile['P']
@@ -126,7 +168,7 @@ class StreamingSweep:
             self._buffers = D.ScoreBuffers(max(P, 1), self.N, p)
             self._buffers.p = p
             self._draw = D.DrawBuffers(max(P, 1))
-        prior = self._tile_prior(tile, prior_tables)
+        prior = self._tile_prior(tile, prior_tables, deltas)
         d_mask = None if mask is None else torch.as_tensor(D.pack_mask(np.asarray(mask, dtype=bool)), device=D.dev())
         if self.group_scoring:
             # suffix sums along each group's sorted order: no truth rows (mitre_score_groups)
@@ -142,12 +184,13 @@ class StreamingSweep:
                                                    log_prior=prior, draw_buffers=self._draw)
         return out, status, stats, prior
 
-    def sweep(self, X, omega, kappa, sigma2, mask=None, prior_tables=None):
+    def sweep(self, X, omega, kappa, sigma2, mask=None, prior_tables=None, deltas=None):
         """Scores every candidate once.  Returns (log_total, n_candidates) and keeps one
-        (max, sum-exp) pair per tile for `draw`."""
+        (max, sum-exp) pair per tile for `draw`.  deltas: {(tile, position): term added to that
+        candidate's log-weight} (see `locate`)."""
         import torch
         from . import device as D
-        self._sweep_args = (X, omega, kappa, sigma2, mask, prior_tables)
+        self._sweep_args = (X, omega, kappa, sigma2, mask, prior_tables, deltas)
         import torch.distributed as dist
         n_tiles = len(self.tiles)
         pairs = torch.zeros((n_tiles, 2), dtype=torch.float64, device=D.dev())
@@ -159,7 +202,7 @@ class StreamingSweep:
             counts[t] = tile['P']
             if tile['P'] == 0:
                 continue
-            out, status, stats, _ = self._score_tile(tile, X, omega, kappa, sigma2, mask, prior_tables)
+            out, status, stats, _ = self._score_tile(tile, X, omega, kappa, sigma2, mask, prior_tables, deltas)
             pairs[t] = stats
             status_all = status
             del tile, out
@@ -184,11 +227,11 @@ class StreamingSweep:
         if self.tile_stats is None:
             raise RuntimeError("draw() needs a sweep() first")
         t, u_local, _ = owner_of_marker(self.tile_stats, u)
-        X, omega, kappa, sigma2, mask, prior_tables = self._sweep_args
+        X, omega, kappa, sigma2, mask, prior_tables, deltas = self._sweep_args
         result = [None]
         if t % self.ws == self.rank:                           # the tile's owner redraws inside it
             tile = self.build_tile(t)
-            out, status, stats, prior = self._score_tile(tile, X, omega, kappa, sigma2, mask, prior_tables)
+            out, status, stats, prior = self._score_tile(tile, X, omega, kappa, sigma2, mask, prior_tables, deltas)
             k = int(D.draw_index(out, prior, u_local, stabilise=True, buffers=self._draw, reuse_stats=True).item())
             k = min(k, tile['P'] - 1)
             result = [(t, k, self.describe(tile, k))]
@@ -198,6 +241,17 @@ class StreamingSweep:
             dist.broadcast_object_list(result, src=dist.get_global_rank(self.group, src) if self.group is not None
                                        else src, group=self.group)
         return result[0]
+
+    def log_weight(self, t, k):
+        """log-weight (likelihood + prior + correction) the last sweep gave candidate (t, k), and
+        log-weight minus the sweep's log-total = the log-probability `draw` picks it (what the
+        reverse-move probabilities of add/remove need, logit_rules.py:1168-1170)."""
+        X, omega, kappa, sigma2, mask, prior_tables, deltas = self._sweep_args
+        tile = self.build_tile(t)
+        out, status, stats, prior = self._score_tile(tile, X, omega, kappa, sigma2, mask, prior_tables, deltas)
+        w = float(out[k].item()) + (float(prior[k].item()) if prior is not None else 0.0)
+        _, _, log_total = owner_of_marker(self.tile_stats, 0.5)
+        return w, w - log_total
 
     def describe(self, tile, k):
         """(variable, window, type, direction, threshold) of row k of a built tile (rules.py:23-44)."""

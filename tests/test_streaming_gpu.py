@@ -125,3 +125,48 @@ def test_score_groups_equals_row_scoring_and_oracle(N, p):
     rows = D.unpack_rows(tile['rows'][torch.as_tensor(idx, device=D.dev())], N).cpu().numpy().astype(bool)
     want = oracle.likelihoods_of_all_options(X, omega, (y - 0.5) / omega, (rows & mask).astype(float), 100.0)
     assert np.max(np.abs(a[idx] - want) / np.abs(want)) <= 1e-9
+
+
+def test_streaming_locate_deltas_and_log_weight():
+    """The pieces a sampler needs around the sweep: primitive tuple -> (tile, position), sparse additive
+    corrections on named candidates (logit_rules.py:861-862), and one candidate's log-weight /
+    log-probability under the last sweep."""
+    import torch
+    from mitre_b200 import streaming
+    N, V = 40, 7
+    d, data = _case(N, V, seed=77)
+    sw = streaming.StreamingSweep(data, 1.0, 4, tmax=None, tile_variables=3)
+    rng = np.random.RandomState(5)
+    X = np.concatenate([(rng.rand(N, 1) > 0.5).astype(float), np.ones((N, 1))], axis=1)
+    omega = rng.gamma(2.0, 0.125, size=N) + 0.05
+    y = rng.rand(N) > 0.5
+    tables = (rng.normal(size=V), rng.normal(size=len(sw.windows)), -0.2)
+    picks, flat = [], []
+    for t in range(len(sw.tiles)):
+        tile = sw.build_tile(t)
+        for k in rng.randint(0, tile['P'], size=2):
+            tup = sw.describe(tile, int(k))
+            assert sw.locate(tup) == (t, int(k)) and sw.locate(tup, tile=tile) == (t, int(k))
+            picks.append(((t, int(k)), tup))
+    assert sw.locate((0, sw.windows[0], 'average', 'above', 1e99)) is None
+    assert sw.locate((V + 3, sw.windows[0], 'average', 'above', 0.0)) is None
+    deltas = {loc: float(dv) for (loc, _), dv in zip(picks, rng.normal(size=len(picks)) * 3)}
+    log_total, n = sw.sweep(X, omega, y - 0.5, 100.0, prior_tables=tables, deltas=deltas)
+    offs = np.concatenate([[0], np.cumsum(sw.tile_counts)])
+    for t in range(len(sw.tiles)):
+        tile = sw.build_tile(t)
+        out, status, stats, prior = sw._score_tile(tile, X, omega, y - 0.5, 100.0, None, tables, None)
+        flat.append(out.cpu().numpy() + prior.cpu().numpy())
+    flat = np.concatenate(flat)
+    for (t, k), dv in deltas.items():
+        flat[offs[t] + k] += dv
+    want = float(torch.logsumexp(torch.as_tensor(flat), 0))
+    assert abs(log_total - want) <= 1e-11 * abs(want)
+    for (t, k), _ in picks[:3]:
+        w, logp = sw.log_weight(t, k)
+        assert abs(w - flat[offs[t] + k]) <= 1e-11 * abs(w)
+        assert abs(logp - (flat[offs[t] + k] - want)) <= 1e-9
+    c = np.cumsum(np.exp(flat - flat.max()))
+    for u in [0.1, 0.6, 0.99]:
+        t, k, tup = sw.draw(u)
+        assert abs(int(offs[t]) + k - int(np.sum(c < u * c[-1]))) <= 1
