@@ -108,6 +108,7 @@ class LogisticRuleModel(object):
         state.pop('_prior_table_cache', None)
         state.pop('_structure_terms', None)
         state.pop('_prior_device_cache', None)
+        state.pop('_prior_count_cache', None)
         return state
 
     def _dev(self):
@@ -294,9 +295,10 @@ class LogisticRuleModel(object):
 
     def _prior_tables(self, state):
         """flat_prior in factored form: (by_variable[V], by_window[W], normalisation).  A primitive's
-        log-prior depends only on its (variable, window); the normalisation is the log-sum-exp over
-        the G groups weighted by their primitive counts instead of over the P primitives
-        (identical up to summation order)."""
+        log-prior depends only on its (variable, window); the normalisation is
+        log sum_w e^{bw[w]} sum_v C[w, v] e^{bv[v]} with C[w, v] the number of active primitives of
+        (window, variable) -- a W x V matrix-vector product instead of a log-sum-exp over the P
+        primitives (identical up to summation order)."""
         pop = self.rule_population
         key = (state.phylogeny_mean, state.phylogeny_std, state.window_concentration,
                state.window_typical_fraction, id(pop._filter_map), pop.n_primitives)
@@ -311,14 +313,33 @@ class LogisticRuleModel(object):
         window_a = state.window_concentration * state.window_typical_fraction
         window_b = state.window_concentration * (1.0 - state.window_typical_fraction)
         by_window = fastdist.beta_logpdf(durations, window_a, window_b)
-        counts = pop.group_counts()
-        terms = by_variable[pop._group_variable] + by_window[pop._group_window]
-        live = counts > 0
-        normalization = fastdist.logsumexp(terms[live], b=counts[live]) if live.any() else 0.0
+        C = self._prior_count_matrix()
+        m_v = float(np.max(by_variable)) if by_variable.size else np.nan
+        m_w = float(np.max(by_window)) if by_window.size else np.nan
+        if np.isfinite(m_v) and np.isfinite(m_w) and not (np.isnan(by_variable).any() or np.isnan(by_window).any()):
+            total = float(np.dot(np.exp(by_window - m_w), C.dot(np.exp(by_variable - m_v))))
+            normalization = m_v + m_w + np.log(total) if total > 0 else 0.0
+        else:     # degenerate hyperparameters (e.g. a non-positive scale proposed by the MH update)
+            counts = pop.group_counts()
+            terms = by_variable[pop._group_variable] + by_window[pop._group_window]
+            live = counts > 0
+            normalization = fastdist.logsumexp(terms[live], b=counts[live]) if live.any() else 0.0
         result = (by_variable, by_window, float(normalization))
         cache.append((key, result))
         del cache[:-6]
         return result
+
+    def _prior_count_matrix(self):
+        """float64[W, V]: active primitives per (window, variable), both detector types together."""
+        pop = self.rule_population
+        key = (id(pop._filter_map), pop.n_primitives, id(pop._K_host))
+        cached = self.__dict__.get('_prior_count_cache')
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        C = np.zeros((len(pop.windows), self.data.n_variables), dtype=np.float64)
+        np.add.at(C, (pop._group_window, pop._group_variable), pop.group_counts().astype(np.float64))
+        self._prior_count_cache = (key, C)
+        return C
 
     def flat_prior_device(self, state):
         """flat_prior as a float64[P] CUDA tensor (mitre_row_prior), cached per hyperparameter state."""
