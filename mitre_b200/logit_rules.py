@@ -263,11 +263,13 @@ class LogisticRuleModel(object):
             sublength_distribution = fastdist.NegativeBinomial(
                 self.hyperparameter_alpha_primitives,
                 self.hyperparameter_beta_primitives / (1.0 + self.hyperparameter_beta_primitives))
-            frozen = (length_distribution, length_distribution.logcdf(self.max_rules - 1),
-                      sublength_distribution, sublength_distribution.logcdf(self.max_primitives - 1))
+            # log-pmf tables over the admissible lengths: the same values logpmf returns, looked up
+            frozen = (length_distribution.logpmf(np.arange(self.max_rules + 1)),
+                      length_distribution.logcdf(self.max_rules - 1),
+                      sublength_distribution.logpmf(np.arange(self.max_primitives + 1)),
+                      sublength_distribution.logcdf(self.max_primitives - 1))
             self._structure_terms = frozen
-        length_distribution, log_rule_normalization, sublength_distribution, \
-            log_primitive_normalization = frozen
+        length_logpmf, log_rule_normalization, sublength_logpmf, log_primitive_normalization = frozen
         rules = rule_list.rules
         if len(rules) == 0:
             return np.log(empty_probability)
@@ -276,9 +278,11 @@ class LogisticRuleModel(object):
         sublengths = np.array([len(rule) for rule in rules])
         if np.max(sublengths) > self.max_primitives:
             return -np.inf
+        if np.min(sublengths) < 1:      # logpmf(-1) = -inf (never produced by the sampler's moves)
+            return -np.inf
         l0 = np.log(1 - empty_probability)
-        l1 = (length_distribution.logpmf(len(rules) - 1) - log_rule_normalization)
-        l2 = (np.sum(sublength_distribution.logpmf(sublengths - 1)) -
+        l1 = (length_logpmf[len(rules) - 1] - log_rule_normalization)
+        l2 = (np.sum(sublength_logpmf[sublengths - 1]) -
               len(rules) * log_primitive_normalization)
         return l0 + l1 + l2
 
