@@ -340,13 +340,22 @@ class DiscreteRulePopulation:
         self._G = int(group_base[-1])
         self._window_lookup = {(float(a), float(b)): i for i, (a, b) in enumerate(self.windows)}
         self._durations_by_window = np.array([w[1] - w[0] for w in self.windows], dtype=np.float64)
-        # group -> (window, variable, type)
-        gw = np.repeat(np.arange(W, dtype=np.int32), per_window)
-        within = np.arange(self._G, dtype=np.int64) - group_base[gw]
-        nt = (1 + ok.astype(np.int64))[gw]
-        self._group_window = gw
-        self._group_variable = (within // nt).astype(np.int32)
-        self._group_type = np.where(nt == 2, within % 2, 1).astype(np.int8)
+        # group -> (window, variable, type): per window either (v, slope), (v, average) pairs or
+        # (v, average) alone -- two patterns, concatenated (no G-long integer divisions on the host)
+        key = (W, V, ok.tobytes())
+        cached = self.__dict__.get('_group_tables_cache')
+        if cached is None or cached[0] != key:
+            var2 = np.repeat(np.arange(V, dtype=np.int32), 2)
+            var1 = np.arange(V, dtype=np.int32)
+            typ2 = np.tile(np.array([0, 1], dtype=np.int8), V)
+            typ1 = np.ones(V, dtype=np.int8)
+            empty_i, empty_b = np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int8)
+            cached = (key,
+                      np.repeat(np.arange(W, dtype=np.int32), per_window),
+                      np.concatenate([var2 if o else var1 for o in ok] + [empty_i]),
+                      np.concatenate([typ2 if o else typ1 for o in ok] + [empty_b]))
+            self._group_tables_cache = cached
+        _, self._group_window, self._group_variable, self._group_type = cached
         self._host_cache = {}
         if W == 0:
             self._values = torch.empty((0, self.data.n_subjects), dtype=torch.float64, device=D.dev())
