@@ -266,3 +266,95 @@ class StreamingSweep:
         ty = within % nt if nt == 2 else 1
         thr = float(tile['thresholds'][g, slot >> 1].item())
         return (int(v), self.windows[w], TYPES[ty], DIRECTIONS[slot & 1], thr)
+
+
+class StreamingDetectorGibbs:
+    """The sampler's detector update (LogisticRuleSampler.update_primitives, logit_rules.py:794-881)
+    and its omega / beta Gibbs sweeps (logit_rules.py:567-573) over a StreamingSweep: the part of a
+    chain that touches all P candidates, for tables that do not fit in HBM.  The rule list's
+    STRUCTURE (number of rules, detectors per rule) is held fixed: the add / remove / move moves
+    and the hyperparameter updates of the full sampler are not restated here.
+
+    For detector j of rule i the conditional draws a replacement with log-weight
+        log-likelihood([X_without_i | rule i with the candidate in place of j])
+      + log-prior(candidate)                          (factored tables, LogisticRuleModel._prior_tables)
+      + sum over candidates already in rule i:  -gammaln(n + 2) + log(1 + n)      (logit_rules.py:856-862)
+    exactly the weights of the resident sampler (`_device_gibbs_draw`); only the ORDER in which the
+    candidates are laid out differs (tile, enumeration) -- the same distribution over the same set.
+
+    rule_list: list of rules, each a list of primitive tuples (variable, window, type, direction, threshold).
+    """
+
+    def __init__(self, sweep, y, rule_list, prior_coefficient_variance=100.0, prior_tables=None, seed=0):
+        self.sweep = sweep
+        self.y = np.asarray(y, dtype=bool)
+        self.kappa = self.y.astype(np.float64) - 0.5
+        self.sigma2 = float(prior_coefficient_variance)
+        self.prior_tables = prior_tables
+        self.rng = np.random.RandomState(seed)
+        self.rules = [list(rule) for rule in rule_list]
+        self.truth = [[self._truth_of(p) for p in rule] for rule in self.rules]
+        N = sweep.N
+        self.omega = np.full(N, 0.25)
+        self.beta = np.zeros(len(self.rules) + 1)
+        self.log = []
+
+    def _truth_of(self, primitive):
+        loc = self.sweep.locate(primitive)
+        if loc is None:
+            raise ValueError("not a candidate of this population: %r" % (primitive,))
+        tile = self.sweep.build_tile(loc[0])
+        return self.sweep.truth_row(tile, loc[1])
+
+    def design_matrix(self, skip_rule=None):
+        """[rule columns | 1] (rules.py:1173-1175); a rule's column is the AND of its detectors."""
+        cols = [np.logical_and.reduce(t).astype(np.float64) for i, t in enumerate(self.truth) if i != skip_rule]
+        return np.stack(cols + [np.ones(self.sweep.N)], axis=1)
+
+    def update_omega_beta(self, n_iters=10):
+        from . import device as D
+        X = self.design_matrix()
+        beta0 = self.beta if len(self.beta) == X.shape[1] else np.zeros(X.shape[1])
+        omega, beta, betas, status = D.gibbs_omega_beta(X, self.kappa, self.sigma2, beta0, n_iters,
+                                                        int(self.rng.randint(0, 2 ** 62)))
+        D.raise_on_status(status)
+        self.omega = omega.cpu().numpy()
+        self.beta = beta.cpu().numpy()
+
+    def conditional(self, i, j):
+        """Runs the sweep for position (i, j); returns (log_total, n_candidates)."""
+        from scipy.special import gammaln
+        others = [t for jj, t in enumerate(self.truth[i]) if jj != j]
+        mask = np.logical_and.reduce(others) if others else np.ones(self.sweep.N, dtype=bool)
+        X = self.design_matrix(skip_rule=i)
+        counts = {}
+        for jj, p in enumerate(self.rules[i]):
+            if jj != j:
+                counts[p] = counts.get(p, 0) + 1
+        deltas = {}
+        for p, n in counts.items():
+            loc = self.sweep.locate(p)
+            if loc is not None:
+                deltas[loc] = -1.0 * gammaln(n + 1 + 1) + np.log(1.0 + n)
+        return self.sweep.sweep(X, self.omega, self.kappa, self.sigma2, mask=mask, prior_tables=self.prior_tables,
+                                deltas=deltas)
+
+    def update_detector(self, i=None, j=None):
+        """One Gibbs update of a detector (uniformly chosen unless given)."""
+        positions = [(a, b) for a, rule in enumerate(self.rules) for b in range(len(rule))]
+        if i is None:
+            i, j = positions[self.rng.randint(len(positions))]
+        log_total, n = self.conditional(i, j)
+        t, k, primitive = self.sweep.draw(self.rng.rand())
+        tile = self.sweep.build_tile(t)
+        old = self.rules[i][j]
+        self.rules[i][j] = primitive
+        self.truth[i][j] = self.sweep.truth_row(tile, k)
+        self.log.append((i, j, old, primitive, log_total))
+        return primitive
+
+    def step(self, n_gibbs=10):
+        """update_detector + the omega / beta sweeps: the P-dependent part of
+        LogisticRuleSampler.step (logit_rules.py:469-504) at fixed structure."""
+        self.update_detector()
+        self.update_omega_beta(n_gibbs)

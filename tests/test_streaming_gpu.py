@@ -170,3 +170,63 @@ def test_streaming_locate_deltas_and_log_weight():
     for u in [0.1, 0.6, 0.99]:
         t, k, tup = sw.draw(u)
         assert abs(int(offs[t]) + k - int(np.sum(c < u * c[-1]))) <= 1
+
+
+def test_streaming_detector_gibbs_samples_the_resident_conditional():
+    """StreamingDetectorGibbs.conditional(i, j) must weigh every candidate exactly as the resident
+    sampler's detector update does (logit_rules.py:794-881: likelihood under the rule's other
+    detectors as mask + flat_prior + the multinomial / relative-rate terms of the detectors already
+    in the rule), and its update must return a candidate with a valid truth row."""
+    import torch
+    from scipy.special import gammaln
+    from mitre_b200 import chains, device as D, rules as R, streaming, synthetic
+    data, model = chains.build_model("S2", seed=6, variables=7)
+    pop = model.rule_population
+    sampler = chains.run_chain(model, 2, 2, chains.initial_rule_list(model))
+    state = sampler.current_state
+    cfg = synthetic.SHAPES["S2"]
+    sw = streaming.StreamingSweep(data, cfg["tmin"], cfg["N_intervals"], tmax=cfg["tmax"], tile_variables=3)
+    assert sw.windows == pop.windows
+    rng = np.random.RandomState(11)
+    P = len(pop)
+    # detectors named by the streaming side; the resident population knows the same ones (its slope
+    # thresholds may differ in the last bits: different kernels, see _index_of above)
+    picks, picks_res = [], []
+    for t in (0, 1, 2):
+        tile = sw.build_tile(t)
+        picks.append(sw.describe(tile, int(rng.randint(0, tile['P']))))
+        picks_res.append(pop._tuple_at(_index_of(pop, picks[-1])))
+    rule_list = [[picks[0], picks[1], picks[0]], [picks[2]]]          # a repeated detector in rule 0
+    rule_list_res = [[picks_res[0], picks_res[1], picks_res[0]], [picks_res[2]]]
+    tables = model._prior_tables(state)
+    g = streaming.StreamingDetectorGibbs(sw, data.y, rule_list, model.prior_coefficient_variance, tables, seed=3)
+    g.omega = np.asarray(state.omega, dtype=np.float64).copy()
+    i, j = 0, 1
+    log_total, n = g.conditional(i, j)
+    assert n == P
+    # resident weights for the same position
+    rl = R.RuleList([[R.PrimitiveRule(*p) for p in rule] for rule in rule_list_res])
+    lik, status = model.likelihoods_of_all_options_device(rl, g.omega, i, j)
+    D.raise_on_status(status)
+    w_res = lik.cpu().numpy() + model.flat_prior_device(state).cpu().numpy()
+    k0 = pop._index_of(picks_res[0])
+    w_res[k0] += -1.0 * gammaln(2 + 1 + 1) + np.log(1.0 + 2)           # picks[0] occurs twice besides position j
+    want_total = float(torch.logsumexp(torch.as_tensor(w_res), 0))
+    assert abs(log_total - want_total) <= 1e-10 * abs(want_total)
+    for t in range(len(sw.tiles)):
+        tile = sw.build_tile(t)
+        for k in list(rng.randint(0, tile['P'], size=15)):
+            tup = sw.describe(tile, int(k))
+            w, logp = sw.log_weight(t, int(k))
+            assert abs(w - w_res[_index_of(pop, tup)]) <= 1e-10 * abs(w)
+    w0, _ = sw.log_weight(*sw.locate(picks[0]))
+    assert abs(w0 - w_res[k0]) <= 1e-10 * abs(w0)
+    # an update replaces the detector by a candidate and keeps the bookkeeping consistent
+    new = g.update_detector(i, j)
+    assert g.rules[i][j] == new and _index_of(pop, new) is not None
+    assert np.array_equal(g.truth[i][j], pop._truth_row(_index_of(pop, new)))
+    g.update_omega_beta(5)
+    assert g.omega.shape == (data.n_subjects,) and np.all(g.omega > 0) and g.beta.shape == (3,)
+    for _ in range(3):
+        g.step(n_gibbs=3)
+    assert len(g.log) == 4

@@ -66,8 +66,27 @@ from mitre_b200 import device as D  # noqa: E402
 rows = D.unpack_rows(check['rows'][torch.as_tensor(idx, device=D.dev())], N).cpu().numpy().astype(bool)
 want = oracle.likelihoods_of_all_options(X, omega, (y - 0.5) / omega, (rows * mask).astype(float), 100.0)
 got = out.cpu().numpy()[idx]
+# detector Gibbs at fixed structure: 2 rules x 2 detectors, full-table conditional per update
+picks = []
+for tt in range(min(4, len(sw.tiles))):
+    tl = sw.build_tile(tt)
+    picks.append(sw.describe(tl, int(np.random.RandomState(tt).randint(0, tl['P']))))
+while len(picks) < 4:
+    picks.append(picks[0])
+gibbs = streaming.StreamingDetectorGibbs(sw, y, [[picks[0], picks[1]], [picks[2], picks[3]]], 100.0, (bv, bw, 0.0), seed=5)
+gibbs.step()
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+GSTEPS = 5
+for _ in range(GSTEPS):
+    gibbs.step()
+torch.cuda.synchronize()
+gibbs_s = (time.perf_counter() - t0) / GSTEPS
 if RANK == 0:
   print(json.dumps(dict(
+    detector_gibbs=dict(what="update one detector from its full conditional over all candidates + 10 omega/beta sweeps, "
+                             "2 rules x 2 detectors", s_per_step=gibbs_s, steps_per_s=1.0 / gibbs_s,
+                        extrapolated_full_S3_s_per_step=gibbs_s * 5000 / V),
     n_gpus=WORLD, N=N, V=V, tile_variables=TILE, tiles=len(sw.tiles), windows=len(sw.windows), candidates=n,
     packed_bytes_never_materialised=int(n) * 8 * ((N + 63) // 64),
     sweep_wall_s=sweep_s, evals_per_s=n / sweep_s,
