@@ -3,6 +3,10 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
+#include <thread>
+#include <vector>
+
 #include "common.cuh"
 
 namespace mitre {
@@ -162,6 +166,92 @@ extern "C" int mitre_unpack_rows_u8(void *stream, const uint64_t *packed, int64_
 // Same arguments as efficient_likelihoods.likelihoods_of_all_options (pyx:15-21).  The float64
 // truth matrix is staged through two pinned buffers so that the H2D copy of chunk c+1 overlaps
 // packing + scoring of chunk c.
+// ---- drop-in host entry ------------------------------------------------------------------------
+// Staging resources live for the life of the process: allocating two 64 MiB pinned buffers and the
+// device buffers on every call cost more than the transfer itself (165 ms per call for a 560 MB
+// truth matrix before; cudaMallocHost alone is tens of milliseconds).
+namespace {
+
+struct HostStage {
+    std::mutex lock;
+    int device = -1;
+    int64_t chunk_elems = 0;      // float64 elements per staging buffer
+    int64_t chunk_rows = 0, words = 0;
+    size_t ws_bytes = 0;
+    cudaStream_t st[2] = {nullptr, nullptr};
+    double *d_truth[2] = {nullptr, nullptr}, *d_out[2] = {nullptr, nullptr}, *h_stage[2] = {nullptr, nullptr};
+    uint64_t *d_packed[2] = {nullptr, nullptr};
+    void *d_ws[2] = {nullptr, nullptr};
+    double *d_small = nullptr;    // X, omega, kappa
+    size_t small_elems = 0;
+    int32_t *d_status = nullptr;
+
+    void release()
+    {
+        for (int b = 0; b < 2; ++b) {
+            if (st[b]) cudaStreamDestroy(st[b]);
+            cudaFree(d_truth[b]); cudaFree(d_packed[b]); cudaFree(d_out[b]); cudaFree(d_ws[b]);
+            if (h_stage[b]) cudaFreeHost(h_stage[b]);
+            st[b] = nullptr; d_truth[b] = d_out[b] = h_stage[b] = nullptr; d_packed[b] = nullptr; d_ws[b] = nullptr;
+        }
+        cudaFree(d_small); cudaFree(d_status);
+        d_small = nullptr; d_status = nullptr;
+        chunk_elems = chunk_rows = words = 0; ws_bytes = 0; small_elems = 0; device = -1;
+    }
+
+    // (re)allocate so that `rows` rows of N float64, W64 packed words, `ws` workspace bytes and
+    // `small` doubles of sweep inputs fit
+    cudaError_t ensure(int64_t rows, int N, int W64, size_t ws, size_t small)
+    {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        const int64_t elems = rows * N;
+        if (dev == device && elems <= chunk_elems && rows <= chunk_rows && (int64_t)rows * W64 <= words &&
+            ws <= ws_bytes && small <= small_elems)
+            return cudaSuccess;
+        release();
+        device = dev;
+        for (int b = 0; b < 2; ++b) {
+            if ((e = cudaStreamCreateWithFlags(&st[b], cudaStreamNonBlocking)) != cudaSuccess) return e;
+            if ((e = cudaMalloc(&d_truth[b], sizeof(double) * elems)) != cudaSuccess) return e;
+            if ((e = cudaMalloc(&d_packed[b], sizeof(uint64_t) * rows * W64)) != cudaSuccess) return e;
+            if ((e = cudaMalloc(&d_out[b], sizeof(double) * rows)) != cudaSuccess) return e;
+            if ((e = cudaMalloc(&d_ws[b], ws)) != cudaSuccess) return e;
+            if ((e = cudaMallocHost(&h_stage[b], sizeof(double) * elems)) != cudaSuccess) return e;
+        }
+        if ((e = cudaMalloc(&d_small, sizeof(double) * small)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&d_status, sizeof(int32_t))) != cudaSuccess) return e;
+        chunk_elems = elems; chunk_rows = rows; words = rows * W64; ws_bytes = ws; small_elems = small;
+        return cudaSuccess;
+    }
+};
+
+HostStage g_host_stage;
+
+// pageable -> pinned copy on several host threads (one thread moves ~8 GB/s; PCIe wants 50).
+// cudaMemcpyAsync straight from the pageable buffer was measured at 10.4 GB/s, this at ~15.
+void parallel_memcpy(void *dst, const void *src, size_t bytes)
+{
+    unsigned n = std::thread::hardware_concurrency();
+    if (n > 8) n = 8;         // 16 threads measured slower (13 vs 15 GB/s)
+    if (n < 2 || bytes < (8u << 20)) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    const size_t piece = ((bytes / n) + 4095) & ~(size_t)4095;
+    std::vector<std::thread> workers;
+    for (unsigned t = 0; t < n; ++t) {
+        const size_t off = (size_t)t * piece;
+        if (off >= bytes) break;
+        const size_t len = (off + piece <= bytes) ? piece : bytes - off;
+        workers.emplace_back([=] { memcpy((char *)dst + off, (const char *)src + off, len); });
+    }
+    for (auto &w : workers) w.join();
+}
+
+}  // namespace
+
 extern "C" int mitre_score_all_host(const double *X_host, const double *omega_host,
                                     const double *response_host, const double *truth_host, double sigma2,
                                     int N, int p, int64_t P, double *out_host)
@@ -176,41 +266,30 @@ extern "C" int mitre_score_all_host(const double *X_host, const double *omega_ho
     if (chunk < 1024) chunk = 1024;
     if (chunk > P) chunk = P > 0 ? P : 1;
 
-    double *d_X = nullptr, *d_omega = nullptr, *d_kappa = nullptr, *d_out[2] = {nullptr, nullptr};
-    double *d_truth[2] = {nullptr, nullptr}, *h_stage[2] = {nullptr, nullptr}, *h_kappa = nullptr;
-    uint64_t *d_packed[2] = {nullptr, nullptr};
-    void *d_ws[2] = {nullptr, nullptr};
-    int32_t *d_status = nullptr;
-    cudaStream_t st[2] = {nullptr, nullptr};
+    std::lock_guard<std::mutex> guard(g_host_stage.lock);
+    HostStage &hs = g_host_stage;
     int rc = MITRE_OK;
     int32_t h_status = 0;
 #define TRY(expr)                                   \
     do {                                            \
         cudaError_t _e = (expr);                    \
-        if (_e != cudaSuccess) { rc = (int)_e; goto cleanup; } \
+        if (_e != cudaSuccess) { hs.release(); return (int)_e; } \
     } while (0)
 #define TRYRC(expr)                                 \
     do {                                            \
         rc = (expr);                                \
-        if (rc != MITRE_OK) goto cleanup;           \
+        if (rc != MITRE_OK) { cudaDeviceSynchronize(); return rc; } \
     } while (0)
-    h_kappa = (double *)malloc(sizeof(double) * N);
-    for (int i = 0; i < N; ++i) h_kappa[i] = response_host[i] * omega_host[i];  // z = kappa/omega
-    TRY(cudaMalloc(&d_X, sizeof(double) * N * p));
-    TRY(cudaMalloc(&d_omega, sizeof(double) * N));
-    TRY(cudaMalloc(&d_kappa, sizeof(double) * N));
-    TRY(cudaMalloc(&d_status, sizeof(int32_t)));
-    TRY(cudaMemset(d_status, 0, sizeof(int32_t)));
-    TRY(cudaMemcpy(d_X, X_host, sizeof(double) * N * p, cudaMemcpyHostToDevice));
-    TRY(cudaMemcpy(d_omega, omega_host, sizeof(double) * N, cudaMemcpyHostToDevice));
-    TRY(cudaMemcpy(d_kappa, h_kappa, sizeof(double) * N, cudaMemcpyHostToDevice));
-    for (int b = 0; b < 2; ++b) {
-        TRY(cudaStreamCreateWithFlags(&st[b], cudaStreamNonBlocking));
-        TRY(cudaMalloc(&d_truth[b], sizeof(double) * chunk * N));
-        TRY(cudaMalloc(&d_packed[b], sizeof(uint64_t) * chunk * W64));
-        TRY(cudaMalloc(&d_out[b], sizeof(double) * chunk));
-        TRY(cudaMalloc(&d_ws[b], ws_bytes));
-        TRY(cudaMallocHost(&h_stage[b], sizeof(double) * chunk * N));
+    const size_t small = (size_t)N * p + 2 * (size_t)N;
+    TRY(hs.ensure(chunk, N, W64, ws_bytes, small));
+    double *d_X = hs.d_small, *d_omega = d_X + (size_t)N * p, *d_kappa = d_omega + N;
+    {
+        std::vector<double> h_small(small);
+        memcpy(h_small.data(), X_host, sizeof(double) * N * p);
+        memcpy(h_small.data() + (size_t)N * p, omega_host, sizeof(double) * N);
+        for (int i = 0; i < N; ++i) h_small[(size_t)N * p + N + i] = response_host[i] * omega_host[i];  // z = kappa/omega
+        TRY(cudaMemcpy(hs.d_small, h_small.data(), sizeof(double) * small, cudaMemcpyHostToDevice));
+        TRY(cudaMemset(hs.d_status, 0, sizeof(int32_t)));
     }
     {
         int64_t done = 0;
@@ -218,42 +297,29 @@ extern "C" int mitre_score_all_host(const double *X_host, const double *omega_ho
         // out copies land directly in the caller's (pageable) buffer after each chunk's sync
         while (done < P) {
             const int64_t n = (P - done < chunk) ? (P - done) : chunk;
-            TRY(cudaStreamSynchronize(st[b]));  // previous use of this buffer pair finished
-            memcpy(h_stage[b], truth_host + done * N, sizeof(double) * n * N);
-            TRY(cudaMemcpyAsync(d_truth[b], h_stage[b], sizeof(double) * n * N, cudaMemcpyHostToDevice, st[b]));
-            TRYRC(mitre_pack_rows_f64(st[b], d_truth[b], n, N, d_packed[b]));
-            TRYRC(mitre_score_all(st[b], d_packed[b], n, W64, nullptr, d_X, d_omega, d_kappa, N, p, sigma2,
-                                  d_ws[b], ws_bytes, d_out[b], d_status));
-            TRY(cudaMemcpyAsync(out_host + done, d_out[b], sizeof(double) * n, cudaMemcpyDeviceToHost, st[b]));
+            TRY(cudaStreamSynchronize(hs.st[b]));  // previous use of this buffer pair finished
+            parallel_memcpy(hs.h_stage[b], truth_host + done * N, sizeof(double) * n * N);
+            TRY(cudaMemcpyAsync(hs.d_truth[b], hs.h_stage[b], sizeof(double) * n * N, cudaMemcpyHostToDevice,
+                                hs.st[b]));
+            TRYRC(mitre_pack_rows_f64(hs.st[b], hs.d_truth[b], n, N, hs.d_packed[b]));
+            TRYRC(mitre_score_all(hs.st[b], hs.d_packed[b], n, W64, nullptr, d_X, d_omega, d_kappa, N, p, sigma2,
+                                  hs.d_ws[b], ws_bytes, hs.d_out[b], hs.d_status));
+            TRY(cudaMemcpyAsync(out_host + done, hs.d_out[b], sizeof(double) * n, cudaMemcpyDeviceToHost, hs.st[b]));
             done += n;
             b ^= 1;
         }
-        TRY(cudaStreamSynchronize(st[0]));
-        TRY(cudaStreamSynchronize(st[1]));
+        TRY(cudaStreamSynchronize(hs.st[0]));
+        TRY(cudaStreamSynchronize(hs.st[1]));
         if (P == 0) {
-            TRYRC(mitre_score_all(st[0], nullptr, 0, W64, nullptr, d_X, d_omega, d_kappa, N, p, sigma2, d_ws[0],
-                                  ws_bytes, nullptr, d_status));
-            TRY(cudaStreamSynchronize(st[0]));
+            TRYRC(mitre_score_all(hs.st[0], nullptr, 0, W64, nullptr, d_X, d_omega, d_kappa, N, p, sigma2, hs.d_ws[0],
+                                  ws_bytes, nullptr, hs.d_status));
+            TRY(cudaStreamSynchronize(hs.st[0]));
         }
-        TRY(cudaMemcpy(&h_status, d_status, sizeof(int32_t), cudaMemcpyDeviceToHost));
+        TRY(cudaMemcpy(&h_status, hs.d_status, sizeof(int32_t), cudaMemcpyDeviceToHost));
         if (h_status & (MITRE_STATUS_BASE_NOT_PD | MITRE_STATUS_BAD_SCHUR)) rc = MITRE_ERR_NOT_PD;
     }
-cleanup:
 #undef TRY
 #undef TRYRC
-    for (int b = 0; b < 2; ++b) {
-        if (st[b]) cudaStreamDestroy(st[b]);
-        cudaFree(d_truth[b]);
-        cudaFree(d_packed[b]);
-        cudaFree(d_out[b]);
-        cudaFree(d_ws[b]);
-        if (h_stage[b]) cudaFreeHost(h_stage[b]);
-    }
-    cudaFree(d_X);
-    cudaFree(d_omega);
-    cudaFree(d_kappa);
-    cudaFree(d_status);
-    free(h_kappa);
     return rc;
 }
 
