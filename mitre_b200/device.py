@@ -206,6 +206,18 @@ def raise_on_status(status):
         raise np.linalg.LinAlgError("Matrix is not positive definite (status flags %d)" % s)
 
 
+def read_with_status(values, status):
+    """values (any small device tensor) as a float64 numpy array, fetched together with the status
+    word in ONE device->host copy; non-zero status raises LinAlgError like raise_on_status.  Every
+    separate .cpu() / .item() is a stream synchronisation (~50 us): at S2 sizes they were a fifth of a
+    sampler step."""
+    packed = torch.cat([values.reshape(-1).to(F64), status.to(F64)]).cpu().numpy()
+    if packed[-1] != 0:
+        status.zero_()
+        raise np.linalg.LinAlgError("Matrix is not positive definite (status flags %d)" % int(packed[-1]))
+    return packed[:-1]
+
+
 def likelihood_z_given_X_batch(Xs, omega, kappa, sigma2, p_b=None):
     """Xs [B, N, pmax] -> float64[B] dense log-likelihoods (logit_rules.py:171-177)."""
     Xs = _dev_f64(Xs)
@@ -412,19 +424,36 @@ def row_prior(row_group, group_variable, group_window, by_variable, by_window, n
 def gibbs_omega_beta(X, kappa, prior_variance, beta, n_iters, seed, omega=None):
     """n_iters x (omega ~ PG(1, X beta), beta | omega) in one launch (omega=None), or n_iters beta
     draws for a given omega.  Returns (omega float64[N], beta float64[p], betas float64[n_iters, p],
-    status) as CUDA tensors."""
+    status) as CUDA tensors (gibbs_read_back brings all of them to the host with one copy)."""
     X = _dev_f64(X)
     kappa = _dev_f64(kappa)
     N, p = X.shape
-    beta_io = _dev_f64(beta).clone()
+    buf = torch.empty(n_iters * p + N + p, dtype=F64, device=dev())
+    betas = buf[:n_iters * p].view(n_iters, p)
+    om = buf[n_iters * p:n_iters * p + N]
+    beta_io = buf[n_iters * p + N:]
+    beta_io.copy_(_dev_f64(beta))
     mode = 0 if omega is None else 1
-    om = torch.empty(N, dtype=F64, device=dev()) if omega is None else _dev_f64(omega).clone()
-    betas = torch.empty((n_iters, p), dtype=F64, device=dev())
+    if omega is not None:
+        om.copy_(_dev_f64(omega))
     status = torch.zeros(1, dtype=I32, device=dev())
     check(lib().mitre_gibbs_omega_beta(_stream(), _p(X), _p(kappa), N, p, float(prior_variance), int(n_iters),
                                        mode, int(seed) & 0xFFFFFFFFFFFFFFFF, _p(beta_io), _p(om), _p(betas),
                                        _p(status)), "mitre_gibbs_omega_beta")
     return om, beta_io, betas, status
+
+
+def gibbs_read_back(om, beta_io, betas, status):
+    """(omega, beta, betas) of gibbs_omega_beta as numpy arrays with ONE device->host copy (plus the
+    status word, raised as LinAlgError like raise_on_status)."""
+    n_iters, p = betas.shape
+    N = om.shape[0]
+    packed = torch.cat([betas.reshape(-1), om, beta_io, status.to(F64)]).cpu().numpy()
+    if packed[-1] != 0:
+        status.zero_()
+        raise np.linalg.LinAlgError("Matrix is not positive definite (status flags %d)" % int(packed[-1]))
+    return (packed[n_iters * p:n_iters * p + N].copy(), packed[n_iters * p + N:n_iters * p + N + p].copy(),
+            packed[:n_iters * p].reshape(n_iters, p).copy())
 
 
 def pg_draw(z, seed):

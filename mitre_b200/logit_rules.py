@@ -170,9 +170,7 @@ class LogisticRuleModel(object):
         out, status = D.likelihood_z_given_X_batch(batch, omega, self.data.y - 0.5,
                                                    self.prior_coefficient_variance,
                                                    p_b=[x.shape[1] for x in Xs])
-        res = out.cpu().numpy()
-        D.raise_on_status(status)
-        return res
+        return D.read_with_status(out, status)
 
     def likelihood_y_given_X_beta(self, X, beta):
         psi = np.dot(X, beta)
@@ -590,10 +588,7 @@ class LogisticRuleSampler(RuleListSampler):
         seed = int(np.random.randint(0, 2 ** 62))
         omega, beta, betas, status = D.gibbs_omega_beta(
             self.current_X, self.model.data.y - 0.5, self.model.prior_coefficient_variance, beta0, n, seed)
-        betas_h = betas.cpu().numpy()
-        D.raise_on_status(status)
-        state.omega = omega.cpu().numpy()
-        state.beta = betas_h[-1].copy()
+        state.omega, state.beta, betas_h = D.gibbs_read_back(omega, beta, betas, status)   # one D2H, one sync
         return [betas_h[i].copy() for i in range(n)]
 
     def update_omega(self):
@@ -694,7 +689,7 @@ class LogisticRuleSampler(RuleListSampler):
         if token is not None:
             d_vec[token[0]] = token[1]
 
-    def _device_draw(self, d_a, d_b, deltas=None):
+    def _device_draw(self, d_a, d_b, deltas=None, status=None):
         """index = #{cumsum(exp(a + b + sparse)) < u * total} with u = np.random.rand()
         (choose_from_relative_probabilities, rules.py:1261-1264) on the device."""
         from . import device as D
@@ -703,7 +698,8 @@ class LogisticRuleSampler(RuleListSampler):
             st['draw'] = D.DrawBuffers(max(len(self.model.rule_population), 1))
         token = self._with_sparse(d_b, deltas) if deltas else None
         u = np.random.rand()
-        k = int(D.draw_index(d_a, d_b, u, stabilise=False, buffers=st['draw']).item())
+        idx = D.draw_index(d_a, d_b, u, stabilise=False, buffers=st['draw'])
+        k = int(D.read_with_status(idx, status)[0]) if status is not None else int(idx.item())
         self._restore(d_b, token)
         return min(k, d_a.shape[0] - 1)
 
@@ -715,9 +711,7 @@ class LogisticRuleSampler(RuleListSampler):
         out, status = self.model.likelihoods_of_all_options_device(rule_list, self.current_state.omega, i, j)
         deltas = {k: -1.0 * gammaln(n + 1 + 1) + np.log(1.0 + n) for k, n in base_counts.items()
                   if k is not None and k >= 0}
-        k = self._device_draw(out, d_prior, deltas)
-        D.raise_on_status(status)
-        return k
+        return self._device_draw(out, d_prior, deltas, status=status)     # index and status in one read
 
     def add_remove(self):
         if np.random.rand() < 0.5:
@@ -745,8 +739,7 @@ class LogisticRuleSampler(RuleListSampler):
             d_prior = self.model.flat_prior_device(self.current_state)
             out, status, stats = self.model.likelihoods_with_stats_device(
                 new_rl, self.current_state.omega, position_to_add_at, 0, d_prior)
-            st = stats.cpu().numpy()
-            D.raise_on_status(status)
+            st = D.read_with_status(stats, status)
             log_marginalized_likelihood = st[0] + np.log(st[1])
             primitive_distribution = ('device', out, d_prior, None)
         else:
@@ -827,12 +820,14 @@ class LogisticRuleSampler(RuleListSampler):
         # C = logsumexp(prior + lik) with the unmodified prior, in the scoring launch
         out, status, stats = self.model.likelihoods_with_stats_device(
             new_rl, self.current_state.omega, position_to_add_to, base_n_istar, d_prior)
-        sC = stats.cpu().numpy().copy()
-        D.raise_on_status(status)
+        import torch
+        sC_d = stats.clone()
         token = self._with_sparse(d_prior, deltas)
-        sA = D.weight_stats(d_prior, None, buffers=st['draw']).cpu().numpy().copy()     # prior + deltas
-        sB = D.weight_stats(out, d_prior, buffers=st['draw']).cpu().numpy().copy()      # + lik
+        sA_d = D.weight_stats(d_prior, None, buffers=st['draw']).clone()     # prior + deltas
+        sB_d = D.weight_stats(out, d_prior, buffers=st['draw']).clone()      # + lik
         self._restore(d_prior, token)
+        three = D.read_with_status(torch.cat([sC_d, sA_d, sB_d]), status)     # one read for all three pairs
+        sC, sA, sB = three[0:2], three[2:4], three[4:6]
         lse = lambda s: s[0] + np.log(s[1])
         log_relative_prior_primitive_piece = c0 + lse(sA)
         log_relative_prior = (log_relative_prior_primitive_piece + log_relative_structure_prior)
