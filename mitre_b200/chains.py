@@ -6,6 +6,7 @@ lexsort on the device), runs its share of the chains one after another with seed
 at the end.  One process per GPU:
 
     python -m torch.distributed.run --nproc-per-node 8 -m mitre_b200.chains --chains 64 --steps 300
+    python -m torch.distributed.run --nproc-per-node 32 -m mitre_b200.chains --chains 64 --steps 300   # 4 processes per GPU
     python -m mitre_b200.chains --chains 2 --steps 50          # single GPU
 """
 import argparse
@@ -70,9 +71,16 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
+    n_dev = torch.cuda.device_count()
+    torch.cuda.set_device(local_rank % n_dev)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # chains are replicas: the only exchange is the final gather of summaries.  With more processes
+        # than GPUs (a step is host-bound at S2 sizes, so several processes per GPU raise the aggregate
+        # rate) NCCL refuses two ranks on one device: use gloo for that gather.
+        if world > n_dev:
+            dist.init_process_group("gloo")
+        else:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     data, model = build_model(args.shape, seed=args.base_seed, variables=args.variables)
     r0 = initial_rule_list(model)
     mine = PL.chains_for_rank(args.chains, world, rank, args.base_seed)
@@ -91,7 +99,7 @@ def main():
     if rank == 0:
         wall = max(g[0] for g in gathered)
         chains = sorted(sum([g[1] for g in gathered], []), key=lambda r: r["chain"])
-        print(json.dumps(dict(n_gpus=world, chains=args.chains, steps=args.steps,
+        print(json.dumps(dict(n_gpus=min(world, n_dev), processes=world, chains=args.chains, steps=args.steps,
                               candidates=len(model.rule_population),
                               samples_per_sec=args.chains * args.steps / wall, wall_s=wall,
                               points=[c["point"] for c in chains])))
