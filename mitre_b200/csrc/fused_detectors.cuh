@@ -863,8 +863,10 @@ __device__ __forceinline__ void resident_prefetch(char *dst, int w, int N, int S
     }
     const double *src = wdt + (int64_t)w * ld;
     if (dt16) {
+#pragma unroll 1
         for (int i = tid; 2 * i < S; i += nthr) cp_async16(dt + 2 * i, src + 2 * i);
     } else {
+#pragma unroll 1
         for (int i = tid; i < S; i += nthr) cp_async8(dt + i, src + i);
     }
 }
@@ -938,8 +940,10 @@ values_resident_kernel(const double *__restrict__ series_t, int64_t vstride, int
         if (((reinterpret_cast<uintptr_t>(out) | (uintptr_t)(n_out & 1) * 8) & 15) == 0) {
             double2 *out2 = reinterpret_cast<double2 *>(out);
             const double2 *st2 = reinterpret_cast<const double2 *>(st);
+#pragma unroll 1
             for (int i = tid; 2 * i < n_out; i += blockDim.x) out2[i] = st2[i];
         } else {
+#pragma unroll 1
             for (int i = tid; i < n_out; i += blockDim.x) out[i] = st[i];
         }
     }
