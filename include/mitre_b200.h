@@ -267,7 +267,6 @@ int mitre_detectors_fused(void *stream, const double *series_t, int64_t vstride,
 int mitre_densify_perm(void *stream, const int64_t *perm_padded, int64_t P, int N,
                        const int64_t *row_offsets, int64_t *perm);
 int mitre_set_detector_split(int enable); /* tuning/test hook, see above */
-int mitre_set_fused_packed(int enable);   /* tuning/test hook: packed-key (1) or value+id (0, default) sort */
 int mitre_selftest_divide(void *stream, const double *a, const int32_t *n, int64_t count,
                           double *fast, double *exact);
 

@@ -70,7 +70,6 @@ SIGNATURES = {
     "mitre_detectors_fused": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int] + [c_void_p] * 7 +
                               [c_i64] + [c_void_p] * 4 + [c_int, c_int, c_i64] + [c_void_p] * 4),
     "mitre_set_detector_split": (c_int, [c_int]),
-    "mitre_set_fused_packed": (c_int, [c_int]),
     "mitre_selftest_divide": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p]),
     "mitre_densify_perm": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p]),
     "mitre_row_groups": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_void_p]),

@@ -5,7 +5,6 @@
 
 namespace mitre {
 int g_detector_split = 1;
-int g_fused_packed = 0;   // measured: the value + id network at 8 warps/SM beats the packed-key one at 11
 int launch_fused_nb4(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
                      const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
                      const double *winv_n, const double *winv_sxx, const int32_t *widx,
@@ -236,12 +235,6 @@ extern "C" int mitre_set_detector_split(int enable)
     return MITRE_OK;
 }
 
-// Test / tuning hook: 1 = packed-key sorting network, 0 = value + id network (default).
-extern "C" int mitre_set_fused_packed(int enable)
-{
-    g_fused_packed = enable ? 1 : 0;
-    return MITRE_OK;
-}
 
 // Test hook: the exact small-integer division used for window means vs the IEEE divide.
 extern "C" int mitre_selftest_divide(void *stream, const double *a, const int32_t *n, int64_t count,

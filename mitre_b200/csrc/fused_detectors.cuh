@@ -32,7 +32,6 @@
 
 namespace mitre {
 
-extern int g_fused_packed;   // 1: packed-key sorting network where it is instantiated (NB <= 40)
 extern int g_detector_split;  // see mitre_set_detector_split
 
 // ---- compile-time Batcher merge-exchange network for n inputs ------------------------------------
@@ -82,24 +81,6 @@ __device__ __forceinline__ void run_network(double (&v)[N], int (&id)[N], std::i
     (cmp_exchange(v[NetHolder<N>::net.a[I]], v[NetHolder<N>::net.b[I]], id[NetHolder<N>::net.a[I]],
                   id[NetHolder<N>::net.b[I]]),
      ...);
-}
-
-// ---- packed-key variant: sort 64-bit keys = order-preserving value bits with the subject id in
-// the low 6 bits (half the registers of the value + id network => twice the resident warps).
-// The truncated key orders every pair of values that differ above their 6 lowest mantissa bits;
-// the exact values are re-read from shared memory by id, adjacent pairs are checked, and the rare
-// group with a mis-ordered near-tie goes through the generic path below.
-__device__ __forceinline__ void cmp_exchange_u64(uint64_t &x, uint64_t &y)
-{
-    const bool sw = x > y;
-    const uint64_t lo = sw ? y : x, hi = sw ? x : y;
-    x = lo; y = hi;
-}
-
-template <int N, size_t... I>
-__device__ __forceinline__ void run_network_u64(uint64_t (&k)[N], std::index_sequence<I...>)
-{
-    (cmp_exchange_u64(k[NetHolder<N>::net.a[I]], k[NetHolder<N>::net.b[I]]), ...);
 }
 
 // ---- 32-bit key variant: sort keys = order-preserving bits of the value rounded toward zero to
@@ -155,128 +136,6 @@ __device__ __forceinline__ void sort_group_key32(const double *vin, int N, doubl
             }
         }
     }
-}
-
-// Generic (any N <= 64) thresholds + rows for one group from its values column in shared memory
-// and a scratch column of subject ids, presorted or not: insertion sort by exact value, then the
-// same two passes as the register path.  Rare path; correctness over speed.
-static __device__ __noinline__ void emit_group_generic(const double *vcol, int *ids, int ids_stride, int N,
-                                                        bool live, uint64_t valid, double *tg, int32_t *Kg,
-                                                        uint64_t *rows_g)
-{
-    for (int i = 1; i < N; ++i) {
-        const int x = ids[i * ids_stride];
-        const double vx = vcol[x];
-        int j = i - 1;
-        while (j >= 0 && vcol[ids[j * ids_stride]] > vx) {
-            ids[(j + 1) * ids_stride] = ids[j * ids_stride];
-            --j;
-        }
-        ids[(j + 1) * ids_stride] = x;
-    }
-    int kcount = 0;
-    double prev = 0.0;
-    for (int k = 0; k < N - 1; ++k) {
-        const double m = __dmul_rn(0.5, __dadd_rn(vcol[ids[k * ids_stride]], vcol[ids[(k + 1) * ids_stride]]));
-        const bool u = (k == 0) || (m != prev);
-        if (u && live) tg[kcount] = m;
-        kcount += u;
-        prev = m;
-    }
-    if (live) {
-        for (int k2 = kcount; k2 < N - 1; ++k2) tg[k2] = 0.0;
-        *Kg = kcount;
-    }
-    ulonglong2 *rg = reinterpret_cast<ulonglong2 *>(rows_g);
-    uint64_t acc = 1ull << (63 - ids[(N - 1) * ids_stride]), Tn = 0;
-    int pos = kcount - 1;
-    for (int k = N - 2; k >= 0; --k) {
-        const double vk = vcol[ids[k * ids_stride]], vk1 = vcol[ids[(k + 1) * ids_stride]];
-        const double m = __dmul_rn(0.5, __dadd_rn(vk, vk1));
-        bool uniq = true;
-        if (k > 0) uniq = m != __dmul_rn(0.5, __dadd_rn(vcol[ids[(k - 1) * ids_stride]], vk));
-        const uint64_t above = (m == vk1) ? Tn : acc;
-        if (uniq && live) rg[pos] = make_ulonglong2(above, ~above & valid);
-        pos -= uniq;
-        Tn = (vk == vk1) ? Tn : acc;
-        acc |= 1ull << (63 - ids[k * ids_stride]);
-    }
-    if (live)
-        for (int k2 = kcount; k2 < N - 1; ++k2) rg[k2] = make_ulonglong2(~0ull, ~0ull);
-}
-
-template <int NB>
-__device__ __forceinline__ void emit_group_packed(const double *vcol, int *ids, int N, bool live,
-                                                  uint64_t valid, double *vg, double *tg, int32_t *Kg,
-                                                  uint64_t *rows_g)
-{
-    uint64_t key[NB];
-#pragma unroll
-    for (int s = 0; s < NB; ++s) {
-        key[s] = ~0ull;
-        if (s < N) {
-            const double v = vcol[s];
-            if (live) vg[s] = v;
-            key[s] = (f64_key(v) & ~63ull) | (uint64_t)s;
-        }
-    }
-    run_network_u64<NB>(key, std::make_index_sequence<NetHolder<NB>::net.count>{});
-    // forward: thresholds (rules.py:539, 576) + exact-order check of neighbours
-    int kcount = 0;
-    bool misordered = false;
-    {
-        double vk = vcol[key[0] & 63], prev = 0.0;
-#pragma unroll
-        for (int k = 0; k < NB - 1; ++k) {
-            if (k < N - 1) {
-                const double vn = vcol[key[k + 1] & 63];
-                misordered = misordered || (vk > vn);
-                const double m = __dmul_rn(0.5, __dadd_rn(vk, vn));
-                const bool u = (k == 0) || (m != prev);
-                if (u && live) tg[kcount] = m;
-                kcount += u;
-                prev = m;
-                vk = vn;
-            }
-        }
-    }
-    if (misordered) {       // near-tie whose truncated keys compare the wrong way: generic path
-#pragma unroll
-        for (int k = 0; k < NB; ++k)
-            if (k < N) ids[k * 64] = (int)(key[k] & 63);
-        emit_group_generic(vcol, ids, 64, N, live, valid, tg, Kg, rows_g);
-        return;
-    }
-    if (live) {
-        for (int k2 = kcount; k2 < N - 1; ++k2) tg[k2] = 0.0;
-        *Kg = kcount;
-    }
-    // backward: rows (rules.py:490-497); see emit_group
-    ulonglong2 *rg = reinterpret_cast<ulonglong2 *>(rows_g);
-    uint64_t acc = 0, Tn = 0;
-    int pos = kcount - 1;
-    double vk1 = 0.0, vk = 0.0;      // val[k+1], val[k]
-#pragma unroll
-    for (int k = NB - 1; k >= 0; --k) {
-        if (k == N - 1) {
-            acc = 1ull << (63 - (int)(key[k] & 63));
-            Tn = 0;
-            vk = vcol[key[k] & 63];
-        } else if (k < N - 1) {
-            vk1 = vk;
-            vk = vcol[key[k] & 63];
-            const double m = __dmul_rn(0.5, __dadd_rn(vk, vk1));
-            bool uniq = true;
-            if (k > 0) uniq = m != __dmul_rn(0.5, __dadd_rn(vcol[key[k - 1] & 63], vk));
-            const uint64_t above = (m == vk1) ? Tn : acc;
-            if (uniq && live) rg[pos] = make_ulonglong2(above, ~above & valid);
-            pos -= uniq;
-            Tn = (vk == vk1) ? Tn : acc;
-            acc |= 1ull << (63 - (int)(key[k] & 63));
-        }
-    }
-    if (live)
-        for (int k2 = kcount; k2 < N - 1; ++k2) rg[k2] = make_ulonglong2(~0ull, ~0ull);
 }
 
 // ---- numpy pairwise sum over a strided column --------------------------------------------------
@@ -454,7 +313,7 @@ __device__ __forceinline__ double pw_sum_staged(const double *x, int n)
 
 // launch bound 256 threads => up to 255 registers/thread: the NB values + ids stay in registers
 // (a 128-register bound spills the network and measured slower)
-template <int NB, bool PACKED> constexpr int fused_threads() { return PACKED ? 512 : 256; }
+constexpr int kFusedThreads = 256;
 constexpr int kFusedCap = 40;   // samples per staging chunk ([cap][32 lanes] doubles = 10 KB per warp)
 
 // Oversized subject (more in-window samples than a staging chunk): straight from global memory.
@@ -472,8 +331,8 @@ static __device__ __noinline__ double subject_value_global(const double *series_
     return sxy * inv_sxx;
 }
 
-template <int NB, bool PACKED>
-__global__ void __launch_bounds__(fused_threads<NB, PACKED>(), 1)
+template <int NB>
+__global__ void __launch_bounds__(kFusedThreads, 1)
 fused_detectors_kernel(const double *__restrict__ series_t, int64_t vstride, int N, int V,
                        const int32_t *__restrict__ wlo, const int32_t *__restrict__ wcnt,
                        const int32_t *__restrict__ wstart, const double *__restrict__ winv_n,
@@ -569,13 +428,6 @@ fused_detectors_kernel(const double *__restrict__ series_t, int64_t vstride, int
             }
             __syncwarp();
             s = e;
-        }
-        if (PACKED) {
-            // ids scratch: this lane's column of the (now idle) sample staging buffer, 2 ints per slot
-            int *ids = reinterpret_cast<int *>(samples) + 2 * lane;
-            emit_group_packed<NB>(vals + lane * vs_stride, ids, N, live, valid, values + g * N,
-                                  thresholds + g * (N - 1), K + g, rows + g * L);
-            continue;
         }
         double val[NB];
         int id[NB];
@@ -1190,7 +1042,7 @@ static int launch_split_impl(cudaStream_t st, const double *series_t, int64_t vs
     return launch_sort_emit_staged<NB>(st, values, G, N, thresholds, K, rows);
 }
 
-template <int NB, bool PACKED>
+template <int NB>
 static int launch_fused_impl(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
                              const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
                              const double *winv_n, const double *winv_sxx, const int32_t *widx,
@@ -1201,10 +1053,10 @@ static int launch_fused_impl(cudaStream_t st, const double *series_t, int64_t vs
     const int vs_stride = N | 1;
     const size_t per_warp = ((size_t)kFusedCap * 32 + (size_t)32 * vs_stride + 3 * NB) * sizeof(double);
     int warps = (int)((smem_optin() - 1024) / per_warp);
-    if (warps > fused_threads<NB, PACKED>() / 32) warps = fused_threads<NB, PACKED>() / 32;
+    if (warps > kFusedThreads / 32) warps = kFusedThreads / 32;
     if (warps < 1) return MITRE_ERR_UNSUPPORTED;
     const size_t smem = per_warp * warps;
-    auto kern = fused_detectors_kernel<NB, PACKED>;
+    auto kern = fused_detectors_kernel<NB>;
     MITRE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     MITRE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));

@@ -18,10 +18,6 @@ int MITRE_CAT(launch_fused_nb, MITRE_FUSED_NB)(cudaStream_t st, const double *se
                      int n_wt, int64_t G, double *values, double *thresholds, int32_t *K, uint64_t *rows)
 {
     if (g_detector_split) return launch_split_impl<MITRE_FUSED_NB>(st, series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_wt, G, values, thresholds, K, rows);
-#if MITRE_FUSED_NB <= 40
-    // packed-key network: half the registers => up to 16 resident warps per SM
-    if (g_fused_packed) return launch_fused_impl<MITRE_FUSED_NB, true>(st, series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_wt, values, thresholds, K, rows);
-#endif
-    return launch_fused_impl<MITRE_FUSED_NB, false>(st, series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_wt, values, thresholds, K, rows);
+    return launch_fused_impl<MITRE_FUSED_NB>(st, series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_wt, values, thresholds, K, rows);
 }
 }  // namespace mitre

@@ -17,12 +17,10 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 def build_gpu_population(d, pop_cfg, fused=True):
     """fused=True: the default device path (N <= 63): values kernel + staged sort/emit kernel;
     "tile" / "flat": other values kernels; "direct": sort/emit without shared-memory staging;
-    "single": the one-kernel variant; "packed": that kernel with the packed-key network (N <= 40);
-    False: phase-by-phase kernels (any N)."""
+    "single": the one-kernel variant; False: phase-by-phase kernels (any N)."""
     from mitre_b200 import rules as R
     from mitre_b200._lib import lib
-    lib().mitre_set_fused_packed(1 if fused == "packed" else 0)
-    lib().mitre_set_detector_split({"single": 0, "packed": 0, "flat": 2, "tile": 3, "direct": 4}.get(fused, 1))
+    lib().mitre_set_detector_split({"single": 0, "flat": 2, "tile": 3, "direct": 4}.get(fused, 1))
     fused = bool(fused)
     V = d["X"][0].shape[0]
     data = R.Dataset(d["X"], d["T"], d["y"], ["v%d" % i for i in range(V)], d["variable_weights"],
@@ -70,7 +68,7 @@ def check_population(pop, gold_windows, gold_ok, gold_groups, gold_values, gold_
         assert np.array_equal(pop.truth_table[t], DO.unpack_rows(gold_packed[i:i + 1], N)[0])
 
 
-@pytest.mark.parametrize("fused", [True, "tile", "flat", "direct", "single", "packed", False])
+@pytest.mark.parametrize("fused", [True, "tile", "flat", "direct", "single", False])
 @pytest.mark.parametrize("name", sorted(MG.DETECTOR_CASES))
 def test_population_vs_reference_golden(name, fused):
     cfg = MG.DETECTOR_CASES[name]
@@ -87,7 +85,7 @@ def test_population_vs_reference_golden(name, fused):
     assert np.array_equal(pop.flat_truth, DO.unpack_rows(gold["sorted_truth_packed"], N))
 
 
-@pytest.mark.parametrize("fused", [True, "tile", "flat", "direct", "single", "packed", False])
+@pytest.mark.parametrize("fused", [True, "tile", "flat", "direct", "single", False])
 @pytest.mark.parametrize("N,V,T,nint", [(2, 3, (2, 3), 1), (3, 2, (2, 4), 2), (8, 40, (3, 6), 3), (9, 33, (3, 6), 3),
                                         (16, 3, (2, 5), 2), (24, 2, (3, 5), 2), (33, 5, (3, 20), 6),
                                         (40, 70, (3, 7), 2), (41, 2, (3, 7), 2), (48, 3, (3, 7), 2),
@@ -238,11 +236,11 @@ def test_exact_division_selftest():
     assert np.array_equal(exact, a / n)
 
 
-@pytest.mark.parametrize("fused", [True, "tile", "flat", "direct", "single", "packed", False])
+@pytest.mark.parametrize("fused", [True, "tile", "flat", "direct", "single", False])
 def test_near_ties_below_key_resolution_take_the_exact_path(fused):
-    """Values that differ only in their lowest mantissa bits collide in the packed sort key (value
-    bits with the subject id in the low 6 bits); the kernel must detect the mis-ordered neighbours
-    and fall back to the exact comparison path.  Constant series with 4 samples have exact means."""
+    """Values that differ only in their lowest mantissa bits collide in the 32-bit sort key (float32
+    image of the value with the subject id in the low 6 bits); the kernel must detect the mis-ordered
+    neighbours and repair them on the exact values.  Two-sample series have exact means."""
     from mitre_b200 import rules as R
     rng = np.random.RandomState(5)
     N, V = 20, 34
