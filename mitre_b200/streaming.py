@@ -29,6 +29,15 @@ from .parallel import owner_of_marker, world
 from .rules import DIRECTIONS, TYPES
 
 
+def combine_tile_pairs(gathered):
+    """gathered [world, n_tiles, 2]: every rank's (max, sum-exp) table in which only its own tiles
+    (t = rank mod world) are filled -> [n_tiles, 2] with every tile's pair taken from its owner."""
+    import torch
+    ws, n_tiles = gathered.shape[0], gathered.shape[1]
+    t = torch.arange(n_tiles, device=gathered.device)
+    return gathered[t % ws, t]
+
+
 class StreamingSweep:
     def __init__(self, data, tmin, N_intervals, tmax=None, tile_variables=64, group_scoring=True, group=None):
         import torch
@@ -212,8 +221,7 @@ class StreamingSweep:
             # the sweep's only exchange: 16 bytes per tile (every rank ends up with every tile's pair)
             gathered = torch.empty((self.ws, n_tiles, 2), dtype=torch.float64, device=D.dev())
             dist.all_gather_into_tensor(gathered, pairs, group=self.group)
-            owner = torch.arange(n_tiles, device=D.dev()) % self.ws
-            pairs = gathered[owner, torch.arange(n_tiles, device=D.dev())]
+            pairs = combine_tile_pairs(gathered)
             dist.all_reduce(counts, group=self.group)
         self.tile_stats = pairs.cpu().numpy()
         self.tile_counts = counts.cpu().numpy()

@@ -193,3 +193,15 @@ def test_gloo_world2_ragged_allgather():
     for rank, p1, p2 in out:
         assert p1 == [[0, 1, 2], [100, 101, 102, 103, 104]]
         assert p2 == [[], [[1000, 1001], [1002, 1003], [1004, 1005], [1006, 1007]]]
+
+
+def test_streaming_tile_pairs_are_taken_from_their_owner():
+    from mitre_b200 import streaming
+    ws, n_tiles = 3, 8
+    truth = torch.arange(n_tiles * 2, dtype=torch.float64).reshape(n_tiles, 2) + 1.0
+    gathered = torch.zeros((ws, n_tiles, 2), dtype=torch.float64)
+    gathered[:, :, 0] = -np.inf
+    for t in range(n_tiles):
+        gathered[t % ws, t] = truth[t]
+    assert torch.equal(streaming.combine_tile_pairs(gathered), truth)
+    assert torch.equal(streaming.combine_tile_pairs(truth[None]), truth)          # world of one
