@@ -318,7 +318,8 @@ def window_lists(times, t_offsets, windows, vstride):
 
 
 def detectors_fused(series_t, N, V, lists, group_base, slope_ok, task_window, task_type, G):
-    """One launch: values f64[G, N], thresholds f64[G, N-1], K i32[G], rows_padded i64[G, 2(N-1)]."""
+    """mitre_detectors_fused (values kernel + sort/emit kernel, no host round trip): values f64[G, N],
+    thresholds f64[G, N-1], K i32[G], rows_padded i64[G, 2(N-1)]."""
     L = 2 * (N - 1)
     values = torch.empty((G, N), dtype=F64, device=dev())
     thresholds = torch.empty((G, N - 1), dtype=F64, device=dev())

@@ -253,7 +253,7 @@ class _PrimitiveValues:
 class DiscreteRulePopulation:
     """rules.py:245-810, mined on the GPU."""
 
-    use_fused = True    # N <= 63: single-launch detector evaluation; False forces the phase-by-phase path
+    use_fused = True    # N <= 63: mitre_detectors_fused (values + sort/emit kernels); False forces the phase-by-phase path
 
     def __init__(self, model, tmin, N_intervals, tmax=None, data=None, max_thresholds=None):
         self.model = model
@@ -370,7 +370,7 @@ class DiscreteRulePopulation:
         self._fused_args = None
         if (self.use_fused and 2 <= N <= 63 and
                 ds['series_t'].shape[0] * ds['series_t'].shape[1] < 2 ** 31 - 1):
-            # one launch: values + thresholds + K + padded truth rows (fused_detectors.cuh)
+            # values + thresholds + K + padded truth rows without a host round trip (fused_detectors.cuh)
             lists = D.window_lists(ds['times'], ds['t_offsets'], self._d_windows,
                                    ds['series_t'].shape[1])
             tw, tt = [], []
