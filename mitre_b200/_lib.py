@@ -34,6 +34,7 @@ SIGNATURES = {
     "mitre_score_workspace_bytes": (c_size_t, [c_int, c_int]),
     "mitre_set_large_table_min_rows": (c_int, [c_i64]),
     "mitre_set_split_tables": (c_int, [c_int]),
+    "mitre_set_groups_warp": (c_int, [c_int]),
     "mitre_set_wide_tables": (c_int, [c_int]),
     "mitre_score_all": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_int, c_int, c_double, c_void_p, c_size_t, c_void_p,

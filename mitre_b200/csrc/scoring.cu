@@ -511,6 +511,7 @@ score_w1r4_kernel(const uint64_t *__restrict__ rows, int64_t P, const double *__
 // ---------------------------------------------------------------------------------------------
 constexpr int64_t kLargeTableMinRows = 4 << 20;
 static int64_t g_large_table_min_rows = kLargeTableMinRows;
+static int g_groups_warp = 1;    // mitre_score_groups, N <= 64: 1 warp per group (default), 0 CTA per group
 static int g_wide_tables = 1;    // N > 64: 1 byte tables (score_wide8_kernel), 0 per-set-bit sums (score_wide_kernel)
 static int g_split_tables = 0;   // 1: last table in shared memory (score_w1s4_kernel), 0: score_w1g4_kernel (default)
 
@@ -856,11 +857,131 @@ score_groups_kernel(const double *__restrict__ values, const double *__restrict_
     if (bad && status) atomicOr(reinterpret_cast<unsigned int *>(status), MITRE_STATUS_BAD_SCHUR);
 }
 
+// Warp-per-group variant for N <= 64 (two subjects per lane): the same ranks -> sort -> suffix
+// sums -> finish, with the sort a 64-key bitonic network over warp shuffles, the suffix sums two
+// shuffle scans per component, q in shared memory and the table-driven log / reciprocal of the
+// row kernels.  Sorted position j lives in lane j % 32, slot j / 32.
+template <int EP>
+__global__ void __launch_bounds__(256)
+score_groups_warp_kernel(const double *__restrict__ values, const double *__restrict__ thresholds,
+                         const int32_t *__restrict__ K, const int64_t *__restrict__ row_offsets, int64_t G, int N,
+                         const double *__restrict__ ws, double *__restrict__ out, int32_t *status)
+{
+    extern __shared__ __align__(16) double sq[];       // [N][EP]
+    __shared__ double2 logtab[kLogTab];
+    __shared__ double exptab[kExpTab];
+    build_math_tables(logtab, exptab);
+    for (int i = threadIdx.x; i < N * EP; i += blockDim.x) sq[i] = ws[kHdr + i];
+    __syncthreads();
+    const double inv_s2 = ws[1], C1 = ws[3];
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    bool bad = false;
+    for (int64_t g = warp0; g < G; g += nwarps) {
+        const int k_g = K[g];
+        const double *tg = thresholds + g * (N - 1);
+        const double *vg = values + g * N;
+        // keys (rank << 6 | subject); padding sorts last
+        uint32_t key[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int i = lane + 32 * h;
+            key[h] = 0xffffffffu;
+            if (i < N) {
+                const double v = vg[i];
+                int lo = 0, hi = k_g;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (__ldg(tg + mid) < v) lo = mid + 1; else hi = mid;
+                }
+                key[h] = ((uint32_t)lo << 6) | (uint32_t)i;
+            }
+        }
+        // bitonic sort of 64 keys, element index j = lane + 32 * slot
+#pragma unroll
+        for (int size = 2; size <= 64; size <<= 1) {
+#pragma unroll
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                if (stride == 32) {
+                    // partner is the other slot of the same lane; size == 64 here: ascending everywhere
+                    const uint32_t a = min(key[0], key[1]), b = max(key[0], key[1]);
+                    key[0] = a; key[1] = b;
+                } else {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int j = lane + 32 * h;
+                        const uint32_t other = __shfl_xor_sync(0xffffffffu, key[h], stride);
+                        const bool up = (j & size) == 0;          // ascending block?
+                        const bool lower = (lane & stride) == 0;   // this element is the lower index of the pair
+                        const uint32_t mn = min(key[h], other), mx = max(key[h], other);
+                        key[h] = (lower == up) ? mn : mx;
+                    }
+                }
+            }
+        }
+        // suffix sums of q over sorted positions: slot 1 (positions 32..63) first, then slot 0
+        double suf[2][EP], tot[EP];
+#pragma unroll
+        for (int h = 1; h >= 0; --h) {
+            const uint32_t k32 = key[h];
+            const bool live = k32 != 0xffffffffu;
+            const double *qi = sq + (live ? (k32 & 63u) : 0u) * EP;
+#pragma unroll
+            for (int e = 0; e < EP; ++e) {
+                double x = live ? qi[e] : 0.0;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const double y = __shfl_down_sync(0xffffffffu, x, off);
+                    if (lane + off < 32) x += y;
+                }
+                if (h == 0) x += tot[e];                     // everything in slot 1 comes after slot 0
+                suf[h][e] = x;
+                tot[e] = __shfl_sync(0xffffffffu, x, 0);     // after h == 0: the group total
+            }
+        }
+        // candidates at rank boundaries
+        double *og = out + row_offsets[g];
+        const int r0 = (int)(key[0] >> 6), r1 = (int)(key[1] >> 6);
+        const int prev0 = __shfl_up_sync(0xffffffffu, r0, 1);            // rank at position lane - 1
+        const int last0 = __shfl_sync(0xffffffffu, r0, 31);              // rank at position 31
+        const int prev1s = __shfl_up_sync(0xffffffffu, r1, 1);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const bool live = key[h] != 0xffffffffu;
+            const int j = lane + 32 * h;
+            if (!live || j == 0) continue;
+            const int r = h == 0 ? r0 : r1;
+            const int rp = h == 0 ? prev0 : (lane == 0 ? last0 : prev1s);
+            for (int k = rp; k < r; ++k) {
+                double below[EP];
+#pragma unroll
+                for (int e = 0; e < EP; ++e) below[e] = tot[e] - suf[h][e];
+                og[2 * k] = finish_tab<EP>(suf[h], inv_s2, C1, logtab, bad);
+                og[2 * k + 1] = finish_tab<EP>(below, inv_s2, C1, logtab, bad);
+            }
+        }
+    }
+    if (bad && status) atomicOr(reinterpret_cast<unsigned int *>(status), MITRE_STATUS_BAD_SCHUR);
+}
+
 template <int EP>
 static int launch_groups(cudaStream_t st, const double *values, const double *thresholds, const int32_t *K,
                          const int64_t *row_offsets, int64_t G, int N, const double *ws, double *out,
                          int32_t *status)
 {
+    if (N <= 64 && g_groups_warp) {
+        auto wkern = score_groups_warp_kernel<EP>;
+        const size_t wsmem = sizeof(double) * (size_t)N * EP;
+        int per_sm = 1;
+        MITRE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wkern, 256, wsmem));
+        int64_t blocks = (int64_t)sm_count() * (per_sm > 0 ? per_sm : 1);
+        const int64_t need = ceil_div64(G, 8);
+        if (need < blocks) blocks = need;
+        wkern<<<(unsigned)blocks, 256, wsmem, st>>>(values, thresholds, K, row_offsets, G, N, ws, out, status);
+        MITRE_LAUNCH_CHECK();
+        return MITRE_OK;
+    }
     int NP2 = 2;
     while (NP2 < N) NP2 <<= 1;
     const size_t smem = sizeof(uint32_t) * (size_t)NP2 + sizeof(double) * 9 * EP;
@@ -1521,6 +1642,12 @@ extern "C" int mitre_set_large_table_min_rows(int64_t rows)
 extern "C" int mitre_set_split_tables(int enable)
 {
     g_split_tables = enable ? 1 : 0;
+    return MITRE_OK;
+}
+
+extern "C" int mitre_set_groups_warp(int enable)
+{
+    g_groups_warp = enable ? 1 : 0;
     return MITRE_OK;
 }
 

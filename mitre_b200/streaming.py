@@ -67,6 +67,7 @@ class StreamingSweep:
         self.tiles = [(v0, min(v0 + self.tile_variables, self.V)) for v0 in range(0, self.V, self.tile_variables)]
         self._buffers = None
         self._draw = None
+        self._tile_static = {}
         self.tile_stats = None
 
     # -- one tile: detector kernels -> rows in enumeration order (window, variable, type, threshold, direction)
@@ -157,14 +158,18 @@ class StreamingSweep:
         import torch
         from . import device as D
         bv, bw, norm = prior_tables
-        gb = tile['group_base']
-        nt = 1 + self.ok_slope.astype(np.int64)
-        w_of = np.repeat(np.arange(len(self.windows), dtype=np.int32), np.diff(gb))
-        within = np.arange(tile['G'], dtype=np.int64) - gb[w_of]
-        gvar = (tile['v0'] + within // nt[w_of]).astype(np.int32)
+        static = self._tile_static.get(tile['v0'])
+        if static is None:      # group -> (variable, window) of this tile: geometry only, kept across sweeps
+            gb = tile['group_base']
+            nt = 1 + self.ok_slope.astype(np.int64)
+            w_of = np.repeat(np.arange(len(self.windows), dtype=np.int32), np.diff(gb))
+            within = np.arange(tile['G'], dtype=np.int64) - gb[w_of]
+            gvar = (tile['v0'] + within // nt[w_of]).astype(np.int32)
+            static = (torch.as_tensor(gvar, device=D.dev()), torch.as_tensor(w_of, device=D.dev()))
+            self._tile_static[tile['v0']] = static
         ident = torch.arange(tile['P'], dtype=torch.int64, device=D.dev())
         rg = D.row_groups(ident, tile['row_offsets'])
-        return D.row_prior(rg, torch.as_tensor(gvar, device=D.dev()), torch.as_tensor(w_of, device=D.dev()),
+        return D.row_prior(rg, static[0], static[1],
                            torch.as_tensor(np.asarray(bv, dtype=np.float64), device=D.dev()),
                            torch.as_tensor(np.asarray(bw, dtype=np.float64), device=D.dev()), float(norm))
 

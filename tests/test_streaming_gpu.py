@@ -91,14 +91,19 @@ def test_streaming_sweep_matches_resident_population(N, V, tile, group_scoring):
         assert _index_of(pop, tup) is not None
 
 
-@pytest.mark.parametrize("N,p", [(2, 1), (3, 2), (17, 1), (35, 4), (64, 3), (65, 2), (200, 5), (700, 4), (2000, 4)])
-def test_score_groups_equals_row_scoring_and_oracle(N, p):
+@pytest.mark.parametrize("warp", [1, 0])
+@pytest.mark.parametrize("N,p", [(2, 1), (3, 2), (17, 1), (31, 2), (32, 6), (33, 3), (35, 4), (63, 9), (64, 3), (65, 2), (200, 5),
+                                 (700, 4), (2000, 4)])
+def test_score_groups_equals_row_scoring_and_oracle(N, p, warp):
     """mitre_score_groups (suffix sums along each group's sorted order) against the row kernels on the
     same tile, and against the C oracle on sampled candidates; ties and zero-inflated series included."""
     import torch
     import oracle
     from mitre_b200 import device as D, streaming
-    from oracle import detectors_oracle as DO
+    from mitre_b200._lib import lib
+    if N > 64 and not warp:
+        pytest.skip("the CTA kernel is the only one for N > 64")
+    lib().mitre_set_groups_warp(warp)          # N <= 64: warp per group (default) or CTA per group
     V = 3 if N > 300 else 7
     d, data = _case(N, V, seed=3 * N + p)
     sw = streaming.StreamingSweep(data, 1.0, 3, tmax=None, tile_variables=V)
@@ -124,6 +129,7 @@ def test_score_groups_equals_row_scoring_and_oracle(N, p):
     idx = np.unique(np.concatenate([[0, 1, P - 2, P - 1], rng.randint(0, P, size=20)]))
     rows = D.unpack_rows(tile['rows'][torch.as_tensor(idx, device=D.dev())], N).cpu().numpy().astype(bool)
     want = oracle.likelihoods_of_all_options(X, omega, (y - 0.5) / omega, (rows & mask).astype(float), 100.0)
+    lib().mitre_set_groups_warp(1)
     assert np.max(np.abs(a[idx] - want) / np.abs(want)) <= 1e-9
 
 

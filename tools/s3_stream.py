@@ -1,7 +1,8 @@
 """S3 (BASELINE configs[2] shape: N = 2000 subjects, T = 50, 12 intervals, mean + slope, full threshold
 grid) streamed in variable tiles (mitre_b200/streaming.py): per-tile detector evaluation + scoring +
-fused (max, sum-exp), then a two-stage draw.  usage: python tools/s3_stream.py [V] [tile_variables]
-Times V variables and extrapolates linearly to the configuration's 5000 (tiles are independent)."""
+fused (max, sum-exp), then a two-stage draw.  usage: python tools/s3_stream.py [V] [tile_variables] [shape=S3]
+Times V variables and extrapolates linearly to the configuration's full variable count (tiles are independent);
+with shape S5 (N = 35) it exercises the warp-per-group scoring kernel."""
 import json
 import sys
 import time
@@ -23,7 +24,9 @@ if WORLD > 1:      # torchrun: the tiles are dealt to the ranks
     dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
 V = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 TILE = int(sys.argv[2]) if len(sys.argv) > 2 else 32
-d = synthetic.make_shape("S3", seed=0, V=V)
+SHAPE = sys.argv[3] if len(sys.argv) > 3 else "S3"
+FULL_V = synthetic.SHAPES[SHAPE]["V"]
+d = synthetic.make_shape(SHAPE, seed=0, V=V)
 N = len(d["X"])
 data = R.Dataset(d["X"], d["T"], d["y"], ["v%d" % i for i in range(V)], d["variable_weights"],
                  d["experiment_start"], d["experiment_end"])
@@ -86,14 +89,14 @@ if RANK == 0:
   print(json.dumps(dict(
     detector_gibbs=dict(what="update one detector from its full conditional over all candidates + 10 omega/beta sweeps, "
                              "2 rules x 2 detectors", s_per_step=gibbs_s, steps_per_s=1.0 / gibbs_s,
-                        extrapolated_full_S3_s_per_step=gibbs_s * 5000 / V),
-    n_gpus=WORLD, N=N, V=V, tile_variables=TILE, tiles=len(sw.tiles), windows=len(sw.windows), candidates=n,
+                        extrapolated_full_shape_s_per_step=gibbs_s * FULL_V / V),
+    n_gpus=WORLD, shape=SHAPE, N=N, V=V, tile_variables=TILE, tiles=len(sw.tiles), windows=len(sw.windows), candidates=n,
     packed_bytes_never_materialised=int(n) * 8 * ((N + 63) // 64),
     sweep_wall_s=sweep_s, evals_per_s=n / sweep_s,
     tile0=dict(candidates=tile['P'], detectors_ms=ev[0].elapsed_time(ev[1]), score_ms=ev[1].elapsed_time(ev[2])),
     draw_wall_s=draw_s, drawn=[int(t), int(k), str(tup)],
     log_total=log_total, max_rel_diff_vs_oracle=float(np.max(np.abs(got - want) / np.abs(want))),
-    extrapolated_full_S3=dict(variables=5000, candidates=int(n * 5000 / V), n_gpus=WORLD,
-                              sweep_s=sweep_s * 5000 / V))))
+    extrapolated_full_shape=dict(variables=FULL_V, candidates=int(n * FULL_V / V), n_gpus=WORLD,
+                                 sweep_s=sweep_s * FULL_V / V))))
 if WORLD > 1:
     dist.destroy_process_group()
