@@ -118,13 +118,17 @@ int mitre_score_all_stats(void *stream, const uint64_t *packed_truth, int64_t P,
  * float64[G, N-1], K int32[G], row_offsets int64[G+1] as produced by mitre_detector_values /
  * _thresholds / _row_offsets (or mitre_detectors_fused); out float64[row_offsets[G]].
  * mask / X / omega / kappa / workspace / status as for mitre_score_all.  N <= 65535.
+ * group_prior float64[G] or NULL: added to every candidate of the group (a primitive's log-prior
+ * depends only on its window and variable, logit_rules.py:424-457), so that `out` holds the
+ * log-weights directly and no per-candidate prior vector is needed.
  * N <= 64: one warp per group (64-key bitonic sort over shuffles); larger N: one CTA per group
  * (mitre_set_groups_warp(0) forces the CTA kernel; test hook). */
 int mitre_set_groups_warp(int enable);
 int mitre_score_groups(void *stream, const double *values, const double *thresholds, const int32_t *K,
                        const int64_t *row_offsets, int64_t G, const uint64_t *mask, const double *X,
                        const double *omega, const double *kappa, int N, int p, double sigma2,
-                       void *workspace, size_t workspace_bytes, double *out, int32_t *status);
+                       void *workspace, size_t workspace_bytes, const double *group_prior, double *out,
+                       int32_t *status);
 
 /*
  * Drop-in compatibility form with the reference's exact arguments, all HOST pointers

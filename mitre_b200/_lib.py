@@ -41,7 +41,7 @@ SIGNATURES = {
                                 c_void_p]),
     "mitre_score_groups": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_int, c_int, c_double, c_void_p, c_size_t, c_void_p,
-                                   c_void_p]),
+                                   c_void_p, c_void_p]),
     "mitre_score_all_stats": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_int, c_int, c_double, c_void_p, c_size_t, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]),

@@ -761,7 +761,8 @@ template <int EP>
 __global__ void __launch_bounds__(256)
 score_groups_kernel(const double *__restrict__ values, const double *__restrict__ thresholds,
                     const int32_t *__restrict__ K, const int64_t *__restrict__ row_offsets, int64_t G, int N,
-                    int NP2, const double *__restrict__ ws, double *__restrict__ out, int32_t *status)
+                    int NP2, const double *__restrict__ ws, const double *__restrict__ group_prior,
+                    double *__restrict__ out, int32_t *status)
 {
     extern __shared__ __align__(16) uint32_t gkeys[];          // [NP2] (rank << 16 | subject), sorted in place
     double *warp_tot = reinterpret_cast<double *>(gkeys + NP2);  // [8][EP]
@@ -837,6 +838,7 @@ score_groups_kernel(const double *__restrict__ values, const double *__restrict_
 #pragma unroll
         for (int e = 0; e < EP; ++e) tot[e] = total[e];
         double *og = out + row_offsets[g];
+        const double gp = group_prior ? group_prior[g] : 0.0;
         for (int j = j1 - 1; j >= j0; --j) {
             const uint32_t key = gkeys[j];
             const double *qi = q + (size_t)(key & 0xffffu) * EP;
@@ -848,8 +850,8 @@ score_groups_kernel(const double *__restrict__ values, const double *__restrict_
                 double below[EP];
 #pragma unroll
                 for (int e = 0; e < EP; ++e) below[e] = tot[e] - suf[e];
-                og[2 * k] = finish_candidate<EP>(suf, C0, inv_s2, s2, bad);
-                og[2 * k + 1] = finish_candidate<EP>(below, C0, inv_s2, s2, bad);
+                og[2 * k] = finish_candidate<EP>(suf, C0, inv_s2, s2, bad) + gp;
+                og[2 * k + 1] = finish_candidate<EP>(below, C0, inv_s2, s2, bad) + gp;
             }
         }
         __syncthreads();
@@ -865,7 +867,8 @@ template <int EP>
 __global__ void __launch_bounds__(256)
 score_groups_warp_kernel(const double *__restrict__ values, const double *__restrict__ thresholds,
                          const int32_t *__restrict__ K, const int64_t *__restrict__ row_offsets, int64_t G, int N,
-                         const double *__restrict__ ws, double *__restrict__ out, int32_t *status)
+                         const double *__restrict__ ws, const double *__restrict__ group_prior,
+                         double *__restrict__ out, int32_t *status)
 {
     extern __shared__ __align__(16) double sq[];       // [N][EP]
     __shared__ double2 logtab[kLogTab];
@@ -942,6 +945,7 @@ score_groups_warp_kernel(const double *__restrict__ values, const double *__rest
         }
         // candidates at rank boundaries
         double *og = out + row_offsets[g];
+        const double gp = group_prior ? group_prior[g] : 0.0;
         const int r0 = (int)(key[0] >> 6), r1 = (int)(key[1] >> 6);
         const int prev0 = __shfl_up_sync(0xffffffffu, r0, 1);            // rank at position lane - 1
         const int last0 = __shfl_sync(0xffffffffu, r0, 31);              // rank at position 31
@@ -957,8 +961,8 @@ score_groups_warp_kernel(const double *__restrict__ values, const double *__rest
                 double below[EP];
 #pragma unroll
                 for (int e = 0; e < EP; ++e) below[e] = tot[e] - suf[h][e];
-                og[2 * k] = finish_tab<EP>(suf[h], inv_s2, C1, logtab, bad);
-                og[2 * k + 1] = finish_tab<EP>(below, inv_s2, C1, logtab, bad);
+                og[2 * k] = finish_tab<EP>(suf[h], inv_s2, C1, logtab, bad) + gp;
+                og[2 * k + 1] = finish_tab<EP>(below, inv_s2, C1, logtab, bad) + gp;
             }
         }
     }
@@ -967,8 +971,8 @@ score_groups_warp_kernel(const double *__restrict__ values, const double *__rest
 
 template <int EP>
 static int launch_groups(cudaStream_t st, const double *values, const double *thresholds, const int32_t *K,
-                         const int64_t *row_offsets, int64_t G, int N, const double *ws, double *out,
-                         int32_t *status)
+                         const int64_t *row_offsets, int64_t G, int N, const double *ws, const double *group_prior,
+                         double *out, int32_t *status)
 {
     if (N <= 64 && g_groups_warp) {
         auto wkern = score_groups_warp_kernel<EP>;
@@ -978,7 +982,8 @@ static int launch_groups(cudaStream_t st, const double *values, const double *th
         int64_t blocks = (int64_t)sm_count() * (per_sm > 0 ? per_sm : 1);
         const int64_t need = ceil_div64(G, 8);
         if (need < blocks) blocks = need;
-        wkern<<<(unsigned)blocks, 256, wsmem, st>>>(values, thresholds, K, row_offsets, G, N, ws, out, status);
+        wkern<<<(unsigned)blocks, 256, wsmem, st>>>(values, thresholds, K, row_offsets, G, N, ws, group_prior, out,
+                                                    status);
         MITRE_LAUNCH_CHECK();
         return MITRE_OK;
     }
@@ -992,7 +997,8 @@ static int launch_groups(cudaStream_t st, const double *values, const double *th
     MITRE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
     int64_t blocks = (int64_t)sm_count() * (per_sm > 0 ? per_sm : 1);
     if (G < blocks) blocks = G;
-    kern<<<(unsigned)blocks, 256, smem, st>>>(values, thresholds, K, row_offsets, G, N, NP2, ws, out, status);
+    kern<<<(unsigned)blocks, 256, smem, st>>>(values, thresholds, K, row_offsets, G, N, NP2, ws, group_prior, out,
+                                              status);
     MITRE_LAUNCH_CHECK();
     return MITRE_OK;
 }
@@ -1713,8 +1719,8 @@ extern "C" int mitre_score_all_stats(void *stream, const uint64_t *packed_truth,
 extern "C" int mitre_score_groups(void *stream, const double *values, const double *thresholds,
                                   const int32_t *K, const int64_t *row_offsets, int64_t G, const uint64_t *mask,
                                   const double *X, const double *omega, const double *kappa, int N, int p,
-                                  double sigma2, void *workspace, size_t workspace_bytes, double *out,
-                                  int32_t *status)
+                                  double sigma2, void *workspace, size_t workspace_bytes,
+                                  const double *group_prior, double *out, int32_t *status)
 {
     if (G < 0 || N <= 1 || p <= 0 || !X || !omega || !kappa || !workspace) return MITRE_ERR_INVALID;
     if (G > 0 && (!values || !thresholds || !K || !row_offsets || !out)) return MITRE_ERR_INVALID;
@@ -1728,7 +1734,7 @@ extern "C" int mitre_score_groups(void *stream, const double *values, const doub
     if (G == 0) return MITRE_OK;
     switch (ep_for(p)) {
 #define MITRE_EP_CASE(E) \
-    case E: return launch_groups<E>(st, values, thresholds, K, row_offsets, G, N, ws, out, status);
+    case E: return launch_groups<E>(st, values, thresholds, K, row_offsets, G, N, ws, group_prior, out, status);
         MITRE_EP_CASE(4)
         MITRE_EP_CASE(6)
         MITRE_EP_CASE(8)

@@ -177,10 +177,10 @@ def score_all_stats(packed, N, X, omega, kappa, sigma2, mask=None, buffers=None,
 
 
 def score_groups(values, thresholds, K, row_offsets, P, X, omega, kappa, sigma2, mask=None, buffers=None,
-                 out=None):
-    """Log-likelihood of every candidate of G groups in ENUMERATION order, from the detector values
-    (mitre_score_groups: suffix sums along each group's sorted order; no truth rows).
-    Returns (out float64[P], status)."""
+                 out=None, group_prior=None):
+    """Log-likelihood (+ group_prior[g], if given) of every candidate of G groups in ENUMERATION order,
+    from the detector values (mitre_score_groups: suffix sums along each group's sorted order; no
+    truth rows).  Returns (out float64[P], status)."""
     G, N = values.shape
     X = _dev_f64(X)
     omega = _dev_f64(omega)
@@ -193,7 +193,7 @@ def score_groups(values, thresholds, K, row_offsets, P, X, omega, kappa, sigma2,
     ws = buffers.workspace
     check(lib().mitre_score_groups(_stream(), _p(values), _p(thresholds), _p(K), _p(row_offsets), G, _p(mask),
                                    _p(X), _p(omega), _p(kappa), int(N), int(p), float(sigma2), _p(ws), ws.numel(),
-                                   _p(out), _p(buffers.status)), "mitre_score_groups")
+                                   _p(group_prior), _p(out), _p(buffers.status)), "mitre_score_groups")
     return out, buffers.status
 
 

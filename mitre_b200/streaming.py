@@ -158,8 +158,19 @@ class StreamingSweep:
         import torch
         from . import device as D
         bv, bw, norm = prior_tables
+        static = self._tile_static_tables(tile)
+        ident = torch.arange(tile['P'], dtype=torch.int64, device=D.dev())
+        rg = D.row_groups(ident, tile['row_offsets'])
+        return D.row_prior(rg, static[0], static[1],
+                           torch.as_tensor(np.asarray(bv, dtype=np.float64), device=D.dev()),
+                           torch.as_tensor(np.asarray(bw, dtype=np.float64), device=D.dev()), float(norm))
+
+    def _tile_static_tables(self, tile):
+        """(variable, window) of every group of the tile as device index tensors: geometry only."""
+        import torch
+        from . import device as D
         static = self._tile_static.get(tile['v0'])
-        if static is None:      # group -> (variable, window) of this tile: geometry only, kept across sweeps
+        if static is None:
             gb = tile['group_base']
             nt = 1 + self.ok_slope.astype(np.int64)
             w_of = np.repeat(np.arange(len(self.windows), dtype=np.int32), np.diff(gb))
@@ -167,11 +178,40 @@ class StreamingSweep:
             gvar = (tile['v0'] + within // nt[w_of]).astype(np.int32)
             static = (torch.as_tensor(gvar, device=D.dev()), torch.as_tensor(w_of, device=D.dev()))
             self._tile_static[tile['v0']] = static
-        ident = torch.arange(tile['P'], dtype=torch.int64, device=D.dev())
-        rg = D.row_groups(ident, tile['row_offsets'])
-        return D.row_prior(rg, static[0], static[1],
-                           torch.as_tensor(np.asarray(bv, dtype=np.float64), device=D.dev()),
-                           torch.as_tensor(np.asarray(bw, dtype=np.float64), device=D.dev()), float(norm))
+        return static
+
+    def _weights_tile(self, tile, X, omega, kappa, sigma2, mask, prior_tables, deltas=None):
+        """log-weights (likelihood + prior + sparse corrections) of a built tile and their
+        (max, sum-exp): what sweep / draw / log_weight consume.  With group scoring the prior enters
+        per GROUP inside the scoring launch (it depends only on window and variable), so no
+        per-candidate prior vector exists."""
+        import torch
+        from . import device as D
+        if not self.group_scoring:
+            out, status, stats, prior = self._score_tile(tile, X, omega, kappa, sigma2, mask, prior_tables, deltas)
+            return (out if prior is None else out + prior), status, stats
+        P = tile['P']
+        p = int(np.shape(X)[1])
+        if self._buffers is None or self._buffers.out.shape[0] < P or self._buffers.p != p:
+            self._buffers = D.ScoreBuffers(max(P, 1), self.N, p)
+            self._buffers.p = p
+            self._draw = D.DrawBuffers(max(P, 1))
+        gp = None
+        if prior_tables is not None:
+            bv, bw, norm = prior_tables
+            gvar, w_of = self._tile_static_tables(tile)
+            gp = (torch.as_tensor(np.asarray(bv, dtype=np.float64), device=D.dev())[gvar.long()] +
+                  torch.as_tensor(np.asarray(bw, dtype=np.float64), device=D.dev())[w_of.long()] - float(norm))
+        d_mask = None if mask is None else torch.as_tensor(D.pack_mask(np.asarray(mask, dtype=bool)), device=D.dev())
+        out, status = D.score_groups(tile['values'], tile['thresholds'], tile['K'], tile['row_offsets'], P, X, omega,
+                                     kappa, sigma2, mask=d_mask, buffers=self._buffers, out=self._buffers.out[:P],
+                                     group_prior=gp)
+        mine = [(k, dv) for (t, k), dv in (deltas or {}).items() if self.tiles[t][0] == tile['v0']]
+        if mine:
+            idx = torch.as_tensor([k for k, _ in mine], dtype=torch.int64, device=D.dev())
+            out[idx] += torch.as_tensor([dv for _, dv in mine], dtype=torch.float64, device=D.dev())
+        stats = D.weight_stats(out, None, buffers=self._draw)
+        return out, status, stats
 
     def _score_tile(self, tile, X, omega, kappa, sigma2, mask, prior_tables, deltas=None):
         import torch
@@ -216,7 +256,7 @@ class StreamingSweep:
             counts[t] = tile['P']
             if tile['P'] == 0:
                 continue
-            out, status, stats, _ = self._score_tile(tile, X, omega, kappa, sigma2, mask, prior_tables, deltas)
+            out, status, stats = self._weights_tile(tile, X, omega, kappa, sigma2, mask, prior_tables, deltas)
             pairs[t] = stats
             status_all = status
             del tile, out
@@ -244,8 +284,8 @@ class StreamingSweep:
         result = [None]
         if t % self.ws == self.rank:                           # the tile's owner redraws inside it
             tile = self.build_tile(t)
-            out, status, stats, prior = self._score_tile(tile, X, omega, kappa, sigma2, mask, prior_tables, deltas)
-            k = int(D.draw_index(out, prior, u_local, stabilise=True, buffers=self._draw, reuse_stats=True).item())
+            w, status, stats = self._weights_tile(tile, X, omega, kappa, sigma2, mask, prior_tables, deltas)
+            k = int(D.draw_index(w, None, u_local, stabilise=True, buffers=self._draw, reuse_stats=True).item())
             k = min(k, tile['P'] - 1)
             result = [(t, k, self.describe(tile, k))]
         if self.ws > 1:
@@ -261,8 +301,8 @@ class StreamingSweep:
         reverse-move probabilities of add/remove need, logit_rules.py:1168-1170)."""
         X, omega, kappa, sigma2, mask, prior_tables, deltas = self._sweep_args
         tile = self.build_tile(t)
-        out, status, stats, prior = self._score_tile(tile, X, omega, kappa, sigma2, mask, prior_tables, deltas)
-        w = float(out[k].item()) + (float(prior[k].item()) if prior is not None else 0.0)
+        wts, status, stats = self._weights_tile(tile, X, omega, kappa, sigma2, mask, prior_tables, deltas)
+        w = float(wts[k].item())
         _, _, log_total = owner_of_marker(self.tile_stats, 0.5)
         return w, w - log_total
 

@@ -54,8 +54,9 @@ ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
 ev[0].record()
 tile = sw.build_tile(RANK % len(sw.tiles))
 ev[1].record()
-out, status, stats, prior = sw._score_tile(tile, X, omega, y - 0.5, 100.0, mask, (bv, bw, 0.0))
+wts, status, stats = sw._weights_tile(tile, X, omega, y - 0.5, 100.0, mask, (bv, bw, 0.0))
 ev[2].record()
+out, status, stats, prior = sw._score_tile(tile, X, omega, y - 0.5, 100.0, mask, (bv, bw, 0.0))
 out = out.clone()          # the sweep's output buffer is reused by draw()
 torch.cuda.synchronize()
 t0 = time.perf_counter()
