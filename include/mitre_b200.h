@@ -90,6 +90,8 @@ size_t mitre_score_workspace_bytes(int N, int p);
 int mitre_set_large_table_min_rows(int64_t rows);
 int mitre_set_split_tables(int enable);
 int mitre_set_wide_tables(int enable);   /* N > 64: 1 (default) byte tables in L2, 0 one fetch per set bit */
+int mitre_set_dedupe(int mode);          /* large tables, N <= 64: 1 (default) score each run of equal rows once;
+                                            2 the same with four lanes per 64-byte table entry; 0 off */
 int mitre_score_all(void *stream, const uint64_t *packed_truth, int64_t P, int W64,
                     const uint64_t *mask, const double *X, const double *omega,
                     const double *kappa, int N, int p, double sigma2, void *workspace,
@@ -98,7 +100,9 @@ int mitre_score_all(void *stream, const uint64_t *packed_truth, int64_t P, int W
 /*
  * Same sweep, additionally reducing (max, sum exp(w - max)) of w = out (+ log_prior, float64[P] or
  * NULL) into stats[2] in the scoring kernel's epilogue (N <= 64; for N > 64 a second pass over
- * `out` using stats_workspace of mitre_draw_workspace_bytes(P) bytes).  log-sum-exp =
+ * `out` using stats_workspace of mitre_draw_workspace_bytes(P) bytes).  When stats_workspace is given
+ * it also receives the per-128-candidate (max, sum-exp) pairs mitre_draw_from_tiles consumes, so the
+ * draw that follows needs no second pass over the P weights.  log-sum-exp =
  * stats[0] + log(stats[1]): what the add/remove moves need (logit_rules.py:959, 1064) and the
  * 16-byte pair ranks exchange in the two-stage multi-GPU draw.
  */
@@ -291,8 +295,10 @@ int mitre_selftest_divide(void *stream, const double *a, const int32_t *n, int64
  *   behaviour; stabilise = 1: shift = max w (stats is then computed first and must be non-NULL);
  *   stabilise = 2: shift = stats[0] as the caller left it (mitre_score_all_stats / mitre_weight_stats
  *   over the same weights), saving the extra pass.
- *   The cumulative sum is hierarchical, not np.cumsum's strict left-to-right order: the drawn
- *   index can differ from the reference only when u*total is within rounding of a partial sum.
+ *   Two-level: candidates are cut into tiles of 128 whose masses (max, sum exp(w - max)) locate the
+ *   tile holding the marker; inside that tile the cumulative sum is the reference's strict
+ *   left-to-right order.  The drawn index can differ from np.cumsum's only when u*total lies within
+ *   rounding (~1e-16 relative) of a partial sum.
  */
 size_t mitre_draw_workspace_bytes(int64_t P);
 int mitre_weight_stats(void *stream, const double *a, const double *b, int64_t P, double *stats,
@@ -300,6 +306,12 @@ int mitre_weight_stats(void *stream, const double *a, const double *b, int64_t P
 int mitre_draw_index(void *stream, const double *a, const double *b, int64_t P, double u,
                      int stabilise, double *stats, int64_t *index_out, void *workspace,
                      size_t workspace_bytes);
+/* Same draw without the pass over the weights: `workspace` still holds the per-tile pairs that
+ * mitre_score_all_stats(..., stats_workspace = workspace, ...) left there for exactly these weights
+ * (a = out, b = log_prior).  stabilise 0 / non-zero as for mitre_draw_index (non-zero: shift = stats[0]). */
+int mitre_draw_from_tiles(void *stream, const double *a, const double *b, int64_t P, double u,
+                          int stabilise, const double *stats, int64_t *index_out, void *workspace,
+                          size_t workspace_bytes);
 
 /* ---- primitive prior on the device: replaces the O(P) host evaluation of flat_prior ------------
  *

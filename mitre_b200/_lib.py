@@ -36,6 +36,7 @@ SIGNATURES = {
     "mitre_set_split_tables": (c_int, [c_int]),
     "mitre_set_groups_warp": (c_int, [c_int]),
     "mitre_set_wide_tables": (c_int, [c_int]),
+    "mitre_set_dedupe": (c_int, [c_int]),
     "mitre_score_all": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_int, c_int, c_double, c_void_p, c_size_t, c_void_p,
                                 c_void_p]),
@@ -84,6 +85,8 @@ SIGNATURES = {
                                    c_size_t]),
     "mitre_draw_index": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_double, c_int, c_void_p,
                                  c_void_p, c_void_p, c_size_t]),
+    "mitre_draw_from_tiles": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_double, c_int, c_void_p,
+                                      c_void_p, c_void_p, c_size_t]),
 }
 
 _lib = None

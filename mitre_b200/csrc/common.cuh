@@ -114,9 +114,44 @@ __device__ __forceinline__ void st_stream_f64(double *p, double v)
 {
     asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
+__device__ __forceinline__ ulonglong2 ld_stream_u64x2(const ulonglong2 *p)
+{
+    ulonglong2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double2 ld_stream_f64x2(const double2 *p)
+{
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream_f64x2(double2 *p, double a, double b)
+{
+    asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+}
 __device__ __forceinline__ void st_stream_u64(uint64_t *p, uint64_t v)
 {
     asm volatile("st.global.L1::no_allocate.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// ---- draw workspace layout (doubles), shared by scoring.cu (writer of the per-tile pairs) and
+// draw.cu (reader):  [partials 2*kStatsBlocks][misc 2][pairs 2*ntiles][chunk sums nchunks]
+//   pairs[t] = (max, sum exp(w - max)) of the kDrawTileRows candidates [t*128, t*128+128)
+//   chunk c  = kDrawChunkTiles consecutive tiles
+constexpr int kStatsBlocks = 592;       // 148 SMs x 4
+constexpr int kDrawTileRows = 128;      // one warp pass of the scoring kernel (4 rows per lane)
+constexpr int kDrawChunkTiles = 256;
+__host__ __device__ inline int64_t draw_ntiles(int64_t P) { return (P + kDrawTileRows - 1) / kDrawTileRows; }
+__host__ __device__ inline int64_t draw_nchunks(int64_t P)
+{
+    return (draw_ntiles(P) + kDrawChunkTiles - 1) / kDrawChunkTiles;
+}
+__host__ __device__ inline size_t draw_off_pairs() { return 2 * (size_t)kStatsBlocks + 2; }
+__host__ __device__ inline size_t draw_off_chunks(int64_t P) { return draw_off_pairs() + 2 * (size_t)draw_ntiles(P); }
+__host__ __device__ inline size_t draw_ws_doubles(int64_t P)
+{
+    return draw_off_chunks(P) + (size_t)draw_nchunks(P);
 }
 
 // Order-preserving map double -> uint64 (for finite values and infinities; -0.0 < +0.0 is

@@ -17,7 +17,6 @@
 
 namespace mitre {
 
-constexpr int kDrawTile = 2048;
 
 __device__ __forceinline__ double weight_at(const double *__restrict__ a, const double *__restrict__ b,
                                             int64_t i)
@@ -87,69 +86,80 @@ stats_final_kernel(const double *__restrict__ part, int nparts, double *__restri
     if (threadIdx.x == 0) { stats[0] = sm[0]; stats[1] = ss[0]; }
 }
 
-// Inclusive scan of one 2048-element tile of exp(w - shift); returns this thread's 8 inclusive
-// values in inc[] and the tile total through smem.
-__device__ __forceinline__ void tile_scan(const double *__restrict__ a, const double *__restrict__ b, int64_t P,
-                                          int64_t tile, double shift, double (&inc)[8], double *swarp,
-                                          double *tile_total)
-{
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int64_t i0 = tile * kDrawTile + (int64_t)threadIdx.x * 8;
-    double run = 0.0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const double e = (i0 + j < P) ? exp(weight_at(a, b, i0 + j) - shift) : 0.0;
-        run += e;
-        inc[j] = run;
-    }
-    double winc = run;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        const double t = __shfl_up_sync(0xffffffffu, winc, off);
-        if (lane >= off) winc += t;
-    }
-    if (lane == 31) swarp[wid] = winc;
-    __syncthreads();
-    double base = winc - run;
-    double tot = 0.0;
-    for (int w = 0; w < 8; ++w) {
-        if (w < wid) base += swarp[w];
-        tot += swarp[w];
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) inc[j] += base;
-    if (threadIdx.x == 0) *tile_total = tot;
-    __syncthreads();
-}
-
+// ---- per-tile pairs ---------------------------------------------------------------------------------
+// pairs[t] = (max, sum exp(w - max)) over the kDrawTileRows candidates of tile t.  The large-table
+// scoring kernel writes these itself (scoring.cu, score_w1d_kernel); every other producer of weights
+// gets them from this pass: one warp per tile, four consecutive candidates per lane.
 __global__ void __launch_bounds__(256)
-draw_tile_sums_kernel(const double *__restrict__ a, const double *__restrict__ b, int64_t P,
-                      const double *__restrict__ stats, int stabilise, double *__restrict__ tile_sums)
+tile_pairs_kernel(const double *__restrict__ a, const double *__restrict__ b, int64_t P,
+                  double *__restrict__ pairs)
 {
-    __shared__ double swarp[8];
-    __shared__ double tot;
-    double inc[8];
-    const double shift = stabilise ? stats[0] : 0.0;
-    tile_scan(a, b, P, blockIdx.x, shift, inc, swarp, &tot);
-    if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+    const int lane = threadIdx.x & 31;
+    const int64_t ntiles = draw_ntiles(P);
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < ntiles; t += nwarps) {
+        const int64_t k0 = t * kDrawTileRows + 4 * lane;
+        double w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[i] = (k0 + i < P) ? weight_at(a, b, k0 + i) : -INFINITY;
+        double m = fmax(fmax(w[0], w[1]), fmax(w[2], w[3]));
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+        double sum = 0.0;
+        if (m > -INFINITY && m < INFINITY) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double d = w[i] - m;
+                sum += (d == d) ? exp(d) : 0.0;       // NaN weights (flagged rows) carry no mass
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        if (lane == 0) reinterpret_cast<double2 *>(pairs)[t] = make_double2(m, sum);
+    }
 }
 
-// single CTA: locate the tile the marker falls in by narrowing [lo, hi) 256-fold per round (each
-// thread sums one contiguous run of tile sums, thread 0 walks the 256 run sums left to right), then
-// rescan that tile and count.  A single thread walking all P/2048 tile sums, as the first version
-// did, costs 14 ms at P = 2.9e8.
+// mass of tile t in units of exp(shift)
+__device__ __forceinline__ double tile_term(const double *__restrict__ pairs, int64_t t, double shift)
+{
+    const double2 ms = reinterpret_cast<const double2 *>(pairs)[t];
+    return ms.y > 0.0 ? ms.y * exp(ms.x - shift) : 0.0;
+}
+
+// chunk_sums[c] = mass of the kDrawChunkTiles tiles of chunk c, fixed summation order
+__global__ void __launch_bounds__(kDrawChunkTiles)
+draw_chunk_sums_kernel(const double *__restrict__ pairs, int64_t ntiles, const double *__restrict__ stats,
+                       int stabilise, double *__restrict__ chunk_sums)
+{
+    __shared__ double sred[kDrawChunkTiles];
+    const double shift = stabilise ? stats[0] : 0.0;
+    const int64_t t = (int64_t)blockIdx.x * kDrawChunkTiles + threadIdx.x;
+    sred[threadIdx.x] = t < ntiles ? tile_term(pairs, t, shift) : 0.0;
+    __syncthreads();
+    for (int s = kDrawChunkTiles / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sred[threadIdx.x] += sred[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) chunk_sums[blockIdx.x] = sred[0];
+}
+
+// Single CTA.  (1) locate the chunk the marker falls in by narrowing [lo, hi) 256-fold per round
+// (each thread sums one contiguous run of chunk sums, thread 0 walks the 256 run sums left to
+// right); (2) walk the chunk's 256 tile masses left to right; (3) resolve the 128 candidates of
+// that tile with a strict left-to-right cumulative sum, the reference's own order
+// (rules.py:1261-1264: np.cumsum, #{p < marker}).
 __global__ void __launch_bounds__(256)
 draw_select_kernel(const double *__restrict__ a, const double *__restrict__ b, int64_t P,
-                   const double *__restrict__ stats, int stabilise, double *__restrict__ tile_sums,
-                   int64_t ntiles, double u, int64_t *__restrict__ index_out)
+                   const double *__restrict__ stats, int stabilise, const double *__restrict__ pairs,
+                   const double *__restrict__ chunk_sums, double u, int64_t *__restrict__ index_out)
 {
-    __shared__ double swarp[8];
-    __shared__ double tot;
-    __shared__ long long s_tile;
+    __shared__ long long s_sel;
     __shared__ double s_before, s_marker;
     __shared__ double s_run[256];
+    const double shift = stabilise ? stats[0] : 0.0;
+    const int64_t ntiles = draw_ntiles(P), nchunks = draw_nchunks(P);
     {
-        int64_t lo = 0, hi = ntiles;
+        int64_t lo = 0, hi = nchunks;
         double before = 0.0;
         bool have_marker = false;
         while (hi - lo > 1 || !have_marker) {
@@ -158,7 +168,7 @@ draw_select_kernel(const double *__restrict__ a, const double *__restrict__ b, i
             const int64_t i0 = lo + (int64_t)threadIdx.x * c;
             const int64_t i1 = (i0 + c < hi) ? i0 + c : hi;
             double sum = 0.0;
-            for (int64_t i = i0; i < i1; ++i) sum += tile_sums[i];
+            for (int64_t i = i0; i < i1; ++i) sum += chunk_sums[i];
             s_run[threadIdx.x] = sum;
             __syncthreads();
             if (threadIdx.x == 0) {
@@ -168,7 +178,7 @@ draw_select_kernel(const double *__restrict__ a, const double *__restrict__ b, i
                     s_marker = u * total;
                 }
                 const double marker = s_marker;
-                const int used = (int)((n + c - 1) / c);      // runs that hold at least one tile
+                const int used = (int)((n + c - 1) / c);      // runs that hold at least one chunk
                 double run = before;
                 int sel = used - 1;
                 for (int k = 0; k < used; ++k) {
@@ -176,38 +186,63 @@ draw_select_kernel(const double *__restrict__ a, const double *__restrict__ b, i
                     if (!(nxt < marker) || k == used - 1) { sel = k; break; }
                     run = nxt;
                 }
-                s_tile = sel;
+                s_sel = sel;
                 s_before = run;
             }
             __syncthreads();
             have_marker = true;
-            const int64_t nlo = lo + (int64_t)s_tile * c;
+            const int64_t nlo = lo + (int64_t)s_sel * c;
             hi = (nlo + c < hi) ? nlo + c : hi;
             lo = nlo;
             before = s_before;
             __syncthreads();
         }
-        if (threadIdx.x == 0) s_tile = lo;
-    }
-    __syncthreads();
-    const long long sel = s_tile;
-    double inc[8];
-    const double shift = stabilise ? stats[0] : 0.0;
-    tile_scan(a, b, P, sel, shift, inc, swarp, &tot);
-    int c = 0;
-    const int64_t i0 = sel * kDrawTile + (int64_t)threadIdx.x * 8;
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-        if (i0 + j < P && (s_before + inc[j]) < s_marker) ++c;
-    // block sum of c
-    __shared__ int scount[256];
-    scount[threadIdx.x] = c;
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-        if (threadIdx.x < s) scount[threadIdx.x] += scount[threadIdx.x + s];
+        // the chunk's tiles
+        const int64_t t0 = lo * kDrawChunkTiles;
+        const int64_t t = t0 + threadIdx.x;
+        s_run[threadIdx.x] = t < ntiles ? tile_term(pairs, t, shift) : 0.0;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int used = (int)((ntiles - t0 < kDrawChunkTiles) ? (ntiles - t0) : kDrawChunkTiles);
+            const double marker = s_marker;
+            double run = before;
+            int sel = used - 1;
+            for (int k = 0; k < used; ++k) {
+                const double nxt = run + s_run[k];
+                if (!(nxt < marker) || k == used - 1) { sel = k; break; }
+                run = nxt;
+            }
+            s_sel = t0 + sel;
+            s_before = run;
+        }
         __syncthreads();
     }
-    if (threadIdx.x == 0) *index_out = sel * kDrawTile + scount[0];
+    const int64_t tile = s_sel;
+    const int64_t k0 = tile * kDrawTileRows;
+    __syncthreads();
+    if (threadIdx.x < kDrawTileRows) {
+        const int64_t k = k0 + threadIdx.x;
+        double e = 0.0;
+        if (k < P) {
+            const double d = weight_at(a, b, k) - shift;
+            e = (d == d) ? exp(d) : 0.0;
+        }
+        s_run[threadIdx.x] = e;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int n = (int)((P - k0 < kDrawTileRows) ? (P - k0) : kDrawTileRows);
+        const double marker = s_marker;
+        double cum = s_before;
+        int count = 0;
+        for (int i = 0; i < n; ++i) {
+            cum += s_run[i];
+            count += (cum < marker) ? 1 : 0;
+        }
+        int64_t idx = k0 + count;
+        if (idx > P - 1) idx = P - 1;
+        *index_out = idx;
+    }
 }
 
 // ---- primitive prior on the device (flat_prior, logit_rules.py:424-457) ---------------------------
@@ -242,7 +277,16 @@ row_prior_kernel(const int32_t *__restrict__ row_group, int64_t P, const int32_t
     }
 }
 
-constexpr int kStatsBlocks = 592;   // 148 SMs x 4
+int launch_tile_pairs(cudaStream_t st, const double *a, const double *b, int64_t P, double *pairs)
+{
+    int64_t blocks = ceil_div64(draw_ntiles(P), 8);
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    tile_pairs_kernel<<<(unsigned)blocks, 256, 0, st>>>(a, b, P, pairs);
+    MITRE_LAUNCH_CHECK();
+    return MITRE_OK;
+}
 
 }  // namespace mitre
 
@@ -251,8 +295,7 @@ using namespace mitre;
 extern "C" size_t mitre_draw_workspace_bytes(int64_t P)
 {
     if (P < 0) return 0;
-    const size_t ntiles = (size_t)ceil_div64(P > 0 ? P : 1, kDrawTile);
-    return sizeof(double) * (2 * (size_t)kStatsBlocks + 2 + ntiles);
+    return sizeof(double) * draw_ws_doubles(P > 0 ? P : 1);
 }
 
 extern "C" int mitre_weight_stats(void *stream, const double *a, const double *b, int64_t P, double *stats,
@@ -271,6 +314,21 @@ extern "C" int mitre_weight_stats(void *stream, const double *a, const double *b
     return MITRE_OK;
 }
 
+static int draw_select(cudaStream_t st, const double *a, const double *b, int64_t P, double u, int stabilise,
+                       const double *stats, int64_t *index_out, double *ws)
+{
+    const int64_t nchunks = draw_nchunks(P);
+    if (nchunks > 0x7fffffffll) return MITRE_ERR_UNSUPPORTED;
+    const double *pairs = ws + draw_off_pairs();
+    double *chunk_sums = ws + draw_off_chunks(P);
+    draw_chunk_sums_kernel<<<(unsigned)nchunks, kDrawChunkTiles, 0, st>>>(pairs, draw_ntiles(P), stats, stabilise,
+                                                                         chunk_sums);
+    MITRE_LAUNCH_CHECK();
+    draw_select_kernel<<<1, 256, 0, st>>>(a, b, P, stats, stabilise, pairs, chunk_sums, u, index_out);
+    MITRE_LAUNCH_CHECK();
+    return MITRE_OK;
+}
+
 extern "C" int mitre_draw_index(void *stream, const double *a, const double *b, int64_t P, double u,
                                 int stabilise, double *stats, int64_t *index_out, void *workspace,
                                 size_t workspace_bytes)
@@ -283,14 +341,20 @@ extern "C" int mitre_draw_index(void *stream, const double *a, const double *b, 
         int rc = mitre_weight_stats(stream, a, b, P, stats, workspace, workspace_bytes);
         if (rc != MITRE_OK) return rc;
     }
-    const int64_t ntiles = ceil_div64(P, kDrawTile);
-    if (ntiles > 0x7fffffffll) return MITRE_ERR_UNSUPPORTED;
-    double *tile_sums = static_cast<double *>(workspace) + 2 * kStatsBlocks + 2;
-    draw_tile_sums_kernel<<<(unsigned)ntiles, 256, 0, st>>>(a, b, P, stats, stabilise, tile_sums);
-    MITRE_LAUNCH_CHECK();
-    draw_select_kernel<<<1, 256, 0, st>>>(a, b, P, stats, stabilise, tile_sums, ntiles, u, index_out);
-    MITRE_LAUNCH_CHECK();
-    return MITRE_OK;
+    double *ws = static_cast<double *>(workspace);
+    int rc = launch_tile_pairs(st, a, b, P, ws + draw_off_pairs());
+    if (rc != MITRE_OK) return rc;
+    return draw_select(st, a, b, P, u, stabilise, stats, index_out, ws);
+}
+
+extern "C" int mitre_draw_from_tiles(void *stream, const double *a, const double *b, int64_t P, double u,
+                                     int stabilise, const double *stats, int64_t *index_out, void *workspace,
+                                     size_t workspace_bytes)
+{
+    if (P <= 0 || !a || !index_out || !workspace) return MITRE_ERR_INVALID;
+    if (stabilise && !stats) return MITRE_ERR_INVALID;
+    if (workspace_bytes < mitre_draw_workspace_bytes(P)) return MITRE_ERR_WORKSPACE;
+    return draw_select(as_stream(stream), a, b, P, u, stabilise, stats, index_out, static_cast<double *>(workspace));
 }
 
 extern "C" int mitre_row_groups(void *stream, const int64_t *perm, int64_t P, const int64_t *row_offsets,

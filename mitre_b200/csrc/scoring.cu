@@ -538,22 +538,25 @@ __host__ __device__ inline size_t tables16_doubles(int N, int EP)
 
 // entry (table t, pattern x): sum of q_i over subjects i = 16 t + j whose pattern bit (bits-1-j)
 // is set, in ascending subject order.
+// `stride` doubles per entry: EP (packed, one lane reads a whole entry) or 8 (64-byte entries whose
+// 16-byte quarters are read by four cooperating lanes, score_w1d_kernel); components >= EP are zero.
 __global__ void __launch_bounds__(256)
-score_build_tables16_kernel(const double *__restrict__ ws, int N, int EP, double *__restrict__ tables)
+score_build_tables16_kernel(const double *__restrict__ ws, int N, int EP, int stride, double *__restrict__ tables)
 {
     const double *q = ws + kHdr;
     const int nt = n_tables16(N);
     size_t base = 0;
     for (int t = 0; t < nt; ++t) {
         const int bits = table16_bits(N, t);
-        const size_t count = ((size_t)1 << bits) * EP;
+        const size_t count = ((size_t)1 << bits) * stride;
         for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < count;
              idx += (size_t)gridDim.x * blockDim.x) {
-            const int e = (int)(idx % EP);
-            const unsigned pat = (unsigned)(idx / EP);
+            const int e = (int)(idx % stride);
+            const unsigned pat = (unsigned)(idx / stride);
             double acc = 0.0;
-            for (int j = 0; j < bits; ++j)
-                if ((pat >> (bits - 1 - j)) & 1) acc += q[(size_t)(table16_start(N, t) + j) * EP + e];
+            if (e < EP)
+                for (int j = 0; j < bits; ++j)
+                    if ((pat >> (bits - 1 - j)) & 1) acc += q[(size_t)(table16_start(N, t) + j) * EP + e];
             tables[base + idx] = acc;
         }
         base += count;
@@ -1276,6 +1279,290 @@ score_w1g4_kernel(const uint64_t *__restrict__ rows, int64_t P, const double *__
 }
 
 // ---------------------------------------------------------------------------------------------
+// Duplicate-aware kernel (default for large lexsorted tables).  In a lexsorted candidate table
+// equal rows are adjacent, and they are the rule, not the exception: a subject's abundance level
+// persists over time, so the rank order of the subjects by a variable's window mean repeats from
+// window to window and with it the truth rows (S5 shape: 81 % of the rows equal their predecessor,
+// ~27 distinct rows per 128).  The reference exploits the same thing -- a candidate identical to
+// its predecessor has divergence index N and costs nothing (efficient_likelihoods.pyx:70-101).
+//
+// A warp takes a tile of 128 consecutive rows (4 per lane, two 16-byte loads), flags the rows that
+// differ from their predecessor, compacts those D distinct rows into shared memory with a warp
+// prefix sum, scores them, and every lane reads back the values of its four rows.
+//
+// Scoring the distinct rows: what bounds the per-row kernels is the L1 wavefront rate of the
+// divergent table lookups -- one lane fetching a 48-byte entry is three 16-byte loads, each a
+// separate pass over up to 32 different cache lines (~2 cycles per line per instruction).  Here the
+// entries are 64 bytes (one half line) and FOUR lanes fetch one entry with ONE load instruction:
+// a warp instruction covers 8 rows and touches 8 lines instead of 32.  Four such sub-rounds load
+// 32 rows; a 4x4 transpose over shuffles inside every group of four lanes then gives each lane all
+// the components of one row, and the epilogue (Schur complement, table log / reciprocal) runs once
+// for 32 rows.
+//
+// STATS: per tile (max, sum exp(w - max)) of w = loglik + log_prior -- max by warp reduction, one
+// exp per candidate against the tile max, no running rescale -- written as the pair the draw
+// consumes (draw.cu) and merged into the CTA's partial.  Deterministic for a given grid.
+// ---------------------------------------------------------------------------------------------
+static int g_dedupe = 1;
+constexpr int kCoopStride = 8;      // doubles per table entry (64 bytes)
+
+// 4x4 transpose of double2 elements inside each group of four lanes: a[r] of lane j <-> a[j] of lane r
+__device__ __forceinline__ double2 shfl_xor_d2(double2 v, int m)
+{
+    return make_double2(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
+}
+__device__ __forceinline__ void transpose4(double2 (&a)[4], int j)
+{
+    {
+        const bool odd = j & 1;
+        const double2 x = shfl_xor_d2(odd ? a[0] : a[1], 1), y = shfl_xor_d2(odd ? a[2] : a[3], 1);
+        if (odd) { a[0] = x; a[2] = y; } else { a[1] = x; a[3] = y; }
+    }
+    {
+        const bool hi = j & 2;
+        const double2 x = shfl_xor_d2(hi ? a[0] : a[2], 2), y = shfl_xor_d2(hi ? a[1] : a[3], 2);
+        if (hi) { a[0] = x; a[1] = y; } else { a[2] = x; a[3] = y; }
+    }
+}
+
+template <int EP, bool STATS, bool COOP>
+__global__ void __launch_bounds__(256)
+score_w1d_kernel(const uint64_t *__restrict__ rows, int64_t P, const double *__restrict__ ws, int N,
+                 const double *__restrict__ tables, double *__restrict__ out, int32_t *status,
+                 const double *__restrict__ log_prior, double *__restrict__ stat_partials,
+                 double *__restrict__ tile_pairs)
+{
+    static_assert(EP <= kCoopStride, "entries are 64 bytes");
+    __shared__ double2 logtab[kLogTab];
+    __shared__ double exptab[kExpTab];
+    __shared__ __align__(16) unsigned long long sbuf[8][kDrawTileRows];
+    build_math_tables(logtab, exptab);
+    __syncthreads();
+    const double inv_s2 = ws[1], C1 = ws[3];
+    const int nt = n_tables16(N);
+    const double2 *tb[4];
+    int shift[4];
+    unsigned msk[4];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int g = lane >> 2, j = lane & 3;      // group of four lanes, quarter of the entry
+    {
+        size_t base = 0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int bits = t < nt ? table16_bits(N, t) : 0;
+            tb[t] = reinterpret_cast<const double2 *>(tables + base) + (COOP ? j : 0);
+            shift[t] = 64 - (t < nt ? table16_start(N, t) : 0) - bits;
+            msk[t] = (1u << bits) - 1u;
+            base += ((size_t)1 << bits) * (COOP ? kCoopStride : EP);
+        }
+    }
+    const int last_shift = shift[nt - 1];
+    const int lead_bits = 64 - last_shift - table16_bits(N, nt - 1);   // subjects covered by the leading tables
+    unsigned long long *sb = sbuf[wid];
+    const int64_t ntiles = draw_ntiles(P);
+    const int64_t nwarps = (int64_t)gridDim.x * 8;
+    const ulonglong2 *rows2 = reinterpret_cast<const ulonglong2 *>(rows);
+    bool bad = false;
+    MaxSum run = {-INFINITY, 0.0};
+
+    // this lane's four rows of a tile; past the end of the table the last row repeats (no new distinct rows)
+    auto load_rows = [&](int64_t tile, uint64_t (&r)[4]) {
+        const int64_t k0 = tile * kDrawTileRows + 4 * lane;
+        if (k0 + 3 < P) {
+            const ulonglong2 a = ld_stream_u64x2(rows2 + (k0 >> 1)), b = ld_stream_u64x2(rows2 + (k0 >> 1) + 1);
+            r[0] = a.x; r[1] = a.y; r[2] = b.x; r[3] = b.y;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) r[i] = rows[(k0 + i < P) ? (k0 + i) : (P - 1)];
+        }
+    };
+
+    int64_t t = (int64_t)blockIdx.x * 8 + wid;
+    uint64_t rn[4] = {0, 0, 0, 0};
+    if (t < ntiles) load_rows(t, rn);
+    for (; t < ntiles; t += nwarps) {
+        const uint64_t r[4] = {rn[0], rn[1], rn[2], rn[3]};
+        if (t + nwarps < ntiles) load_rows(t + nwarps, rn);     // next tile's rows in flight
+        const int64_t k0 = t * kDrawTileRows + 4 * lane;
+        const bool full = k0 + 3 < P;
+        const uint64_t prev = __shfl_up_sync(0xffffffffu, r[3], 1);
+        const int h0 = (lane == 0) || (r[0] != prev);
+        const int h1 = r[1] != r[0], h2 = r[2] != r[1], h3 = r[3] != r[2];
+        const int c = h0 + h1 + h2 + h3;
+        int incl = c;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += y;
+        }
+        const int D = __shfl_sync(0xffffffffu, incl, 31);
+        int i0 = incl - c + h0 - 1, i1 = i0 + h1, i2 = i1 + h2, i3 = i2 + h3;
+        __syncwarp();                                   // the previous tile's read-back is over
+        if (h0) sb[i0] = r[0];
+        if (h1) sb[i1] = r[1];
+        if (h2) sb[i2] = r[2];
+        if (h3) sb[i3] = r[3];
+        __syncwarp();
+        if (!COOP && D > 64) {
+            // few duplicates in this tile: no compaction; every lane scores its own four rows, the leading
+            // lookups shared between them (as score_w1g4_kernel)
+            const uint64_t diff = (r[0] ^ r[1]) | (r[0] ^ r[2]) | (r[0] ^ r[3]);
+            const bool share = lead_bits == 0 || (diff >> (64 - lead_bits)) == 0;
+            double prefix[EP];
+#pragma unroll
+            for (int e = 0; e < EP; ++e) prefix[e] = 0.0;
+            if (share) {
+#pragma unroll
+                for (int tt = 0; tt < 3; ++tt)
+                    if (tt < nt - 1)
+                        lut_add_g<EP>(prefix, reinterpret_cast<const double *>(tb[tt]) +
+                                                  (size_t)((unsigned)(r[0] >> shift[tt]) & msk[tt]) * EP);
+            }
+            double v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                double acc[EP];
+#pragma unroll
+                for (int e = 0; e < EP; ++e) acc[e] = prefix[e];
+                if (!share) {
+#pragma unroll
+                    for (int tt = 0; tt < 3; ++tt)
+                        if (tt < nt - 1)
+                            lut_add_g<EP>(acc, reinterpret_cast<const double *>(tb[tt]) +
+                                                   (size_t)((unsigned)(r[i] >> shift[tt]) & msk[tt]) * EP);
+                }
+                lut_add_g<EP>(acc, reinterpret_cast<const double *>(tb[nt - 1]) +
+                                       (size_t)((unsigned)(r[i] >> last_shift) & msk[nt - 1]) * EP);
+                v[i] = finish_tab<EP>(acc, inv_s2, C1, logtab, bad);
+            }
+            // park the values where the common read-back below finds them
+            i0 = 4 * lane; i1 = i0 + 1; i2 = i0 + 2; i3 = i0 + 3;
+            sb[4 * lane + 0] = (unsigned long long)__double_as_longlong(v[0]);
+            sb[4 * lane + 1] = (unsigned long long)__double_as_longlong(v[1]);
+            sb[4 * lane + 2] = (unsigned long long)__double_as_longlong(v[2]);
+            sb[4 * lane + 3] = (unsigned long long)__double_as_longlong(v[3]);
+        } else if (!COOP) {
+            // one lane per distinct row: the whole (packed, EP-double) entry of every table
+            for (int jj = lane; jj < D; jj += 32) {
+                const uint64_t rr = sb[jj];
+                double acc[EP];
+#pragma unroll
+                for (int e = 0; e < EP; ++e) acc[e] = 0.0;
+#pragma unroll
+                for (int tt = 0; tt < 4; ++tt)
+                    if (tt < nt)
+                        lut_add_g<EP>(acc, reinterpret_cast<const double *>(tb[tt]) +
+                                               (size_t)((unsigned)(rr >> shift[tt]) & msk[tt]) * EP);
+                sb[jj] = (unsigned long long)__double_as_longlong(finish_tab<EP>(acc, inv_s2, C1, logtab, bad));
+            }
+        }
+        if (COOP) {
+            // leading tables: when every row of the tile agrees on the leading subjects (lexsorted neighbours
+            // nearly always do) their entries are fetched once per tile, one quarter per lane
+            const uint64_t first = __shfl_sync(0xffffffffu, r[0], 0);
+            const uint64_t lead_mask = lead_bits ? (~0ull << (64 - lead_bits)) : 0ull;
+            const bool uniform =
+                __all_sync(0xffffffffu, ((((r[0] ^ first) | (r[1] ^ first)) | ((r[2] ^ first) | (r[3] ^ first))) & lead_mask) == 0);
+            double2 lead = make_double2(0.0, 0.0);
+            if (uniform) {
+#pragma unroll
+                for (int tt = 0; tt < 3; ++tt) {
+                    if (tt < nt - 1) {
+                        const double2 v2 = __ldg(tb[tt] + (size_t)((unsigned)(first >> shift[tt]) & msk[tt]) * (kCoopStride / 2));
+                        lead.x += v2.x;
+                        lead.y += v2.y;
+                    }
+                }
+            }
+            for (int base = 0; base < D; base += 32) {
+                double2 a[4];
+#pragma unroll
+                for (int sr = 0; sr < 4; ++sr) {
+                    a[sr] = lead;
+                    const int idx = base + 4 * g + sr;       // after the transpose lane L holds row base + L
+                    const uint64_t rr = sb[idx < D ? idx : D - 1];
+                    if (!uniform) {
+#pragma unroll
+                        for (int tt = 0; tt < 3; ++tt) {
+                            if (tt < nt - 1) {
+                                const double2 v2 = __ldg(tb[tt] + (size_t)((unsigned)(rr >> shift[tt]) & msk[tt]) * (kCoopStride / 2));
+                                a[sr].x += v2.x;
+                                a[sr].y += v2.y;
+                            }
+                        }
+                    }
+                    const double2 v2 = __ldg(tb[nt - 1] + (size_t)((unsigned)(rr >> last_shift) & msk[nt - 1]) * (kCoopStride / 2));
+                    a[sr].x += v2.x;
+                    a[sr].y += v2.y;
+                }
+                transpose4(a, j);
+                double acc[EP];
+#pragma unroll
+                for (int e = 0; e < EP; ++e) acc[e] = (e & 1) ? a[e >> 1].y : a[e >> 1].x;
+                const double val = finish_tab<EP>(acc, inv_s2, C1, logtab, bad);
+                __syncwarp();                               // every lane has read its rows of this batch
+                if (base + lane < D) sb[base + lane] = (unsigned long long)__double_as_longlong(val);
+            }
+        }
+        __syncwarp();
+        double v[4];
+        v[0] = __longlong_as_double((long long)sb[i0]);
+        v[1] = __longlong_as_double((long long)sb[i1]);
+        v[2] = __longlong_as_double((long long)sb[i2]);
+        v[3] = __longlong_as_double((long long)sb[i3]);
+        if (STATS) {
+            double w[4] = {v[0], v[1], v[2], v[3]};
+            if (full) {
+                if (log_prior) {
+                    const double2 *lp2 = reinterpret_cast<const double2 *>(log_prior);
+                    const double2 a = ld_stream_f64x2(lp2 + (k0 >> 1)), b = ld_stream_f64x2(lp2 + (k0 >> 1) + 1);
+                    w[0] += a.x; w[1] += a.y; w[2] += b.x; w[3] += b.y;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (k0 + i >= P) w[i] = -INFINITY;
+                    else if (log_prior) w[i] += log_prior[k0 + i];
+                }
+            }
+            double m = fmax(fmax(w[0], w[1]), fmax(w[2], w[3]));
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+            double sum = 0.0;
+            if (m > -INFINITY && m < INFINITY) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) sum += exp_nonpos(w[i] - m, exptab);
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+            if (lane == 0 && tile_pairs) reinterpret_cast<double2 *>(tile_pairs)[t] = make_double2(m, sum);
+            run = ms_merge(run, MaxSum{m, sum});
+        }
+        if (full) {
+            double2 *o2 = reinterpret_cast<double2 *>(out) + (k0 >> 1);
+            st_stream_f64x2(o2, v[0], v[1]);
+            st_stream_f64x2(o2 + 1, v[2], v[3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (k0 + i < P) out[k0 + i] = v[i];
+        }
+    }
+    if (bad && status) atomicOr(reinterpret_cast<unsigned int *>(status), MITRE_STATUS_BAD_SCHUR);
+    if (STATS) {
+        __shared__ double sm[8], ss[8];
+        if (lane == 0) { sm[wid] = run.m; ss[wid] = run.s; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            MaxSum x = {sm[0], ss[0]};
+            for (int w8 = 1; w8 < 8; ++w8) x = ms_merge(x, MaxSum{sm[w8], ss[w8]});
+            stat_partials[2 * blockIdx.x] = x.m;
+            stat_partials[2 * blockIdx.x + 1] = x.s;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Split tables: the LAST `LB` subjects' subset-sum table lives in shared memory, the leading
 // N - LB subjects keep 16-subject tables in global memory.  score_w1g4_kernel fetches one 48-byte
 // entry of a 3 MB table per candidate from L2 (divergent: one L1 tag per lane per 16 bytes and
@@ -1525,19 +1812,49 @@ static int launch_w1r4(cudaStream_t st, const uint64_t *rows, int64_t P, double 
 
 template <int EP>
 static int launch_w1g(cudaStream_t st, const uint64_t *rows, int64_t P, double *ws, int N, double *out,
-                      int32_t *status, const double *log_prior, double *stats)
+                      int32_t *status, const double *log_prior, double *stats, double *tile_pairs, bool *pairs_done)
 {
     double *partials = ws + kHdr + (size_t)N * EP;
     double *tables = partials + 2 * kMaxStatCtas;
-    const size_t entries = tables16_doubles(N, EP);
+    const bool quad = EP <= 8 && P >= 1024 &&
+                      ((reinterpret_cast<uintptr_t>(rows) | reinterpret_cast<uintptr_t>(out)) & 31) == 0;
+    const bool dedupe = quad && g_dedupe &&
+                        ((reinterpret_cast<uintptr_t>(log_prior) | reinterpret_cast<uintptr_t>(tile_pairs)) & 15) == 0;
+    const bool coop = dedupe && g_dedupe == 2;
+    const int stride = coop ? kCoopStride : EP;
+    const size_t entries = tables16_doubles(N, stride);
     int64_t bblocks = ceil_div64((int64_t)entries, 256);
     if (bblocks > 8 * sm_count()) bblocks = 8 * sm_count();
-    score_build_tables16_kernel<<<(unsigned)bblocks, 256, 0, st>>>(ws, N, EP, tables);
+    score_build_tables16_kernel<<<(unsigned)bblocks, 256, 0, st>>>(ws, N, EP, stride, tables);
     MITRE_LAUNCH_CHECK();
     int per_sm = 1;
     int64_t blocks = 0;
-    const bool quad = EP <= 8 && P >= 1024 &&
-                      ((reinterpret_cast<uintptr_t>(rows) | reinterpret_cast<uintptr_t>(out)) & 31) == 0;
+    if (dedupe) {
+#define MITRE_D_LAUNCH(STATSV)                                                                           \
+    {                                                                                                    \
+        auto kern = coop ? score_w1d_kernel<EP <= 8 ? EP : 8, STATSV, true>                              \
+                         : score_w1d_kernel<EP <= 8 ? EP : 8, STATSV, false>;                            \
+        MITRE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));            \
+        if (per_sm < 1) return MITRE_ERR_UNSUPPORTED;                                                    \
+        blocks = (int64_t)sm_count() * per_sm;                                                           \
+        const int64_t need = ceil_div64(draw_ntiles(P), 8);                                              \
+        if (need < blocks) blocks = need;                                                                \
+        if (blocks > kMaxStatCtas) blocks = kMaxStatCtas;                                                \
+        kern<<<(unsigned)blocks, 256, 0, st>>>(rows, P, ws, N, tables, out, status, log_prior, partials, \
+                                               tile_pairs);                                              \
+        MITRE_LAUNCH_CHECK();                                                                            \
+    }
+        if (stats) {
+            MITRE_D_LAUNCH(true)
+            score_stats_final_kernel<<<1, 256, 0, st>>>(partials, (int)blocks, stats);
+            MITRE_LAUNCH_CHECK();
+            *pairs_done = tile_pairs != nullptr;
+        } else {
+            MITRE_D_LAUNCH(false)
+        }
+#undef MITRE_D_LAUNCH
+        return MITRE_OK;
+    }
 #define MITRE_G_LAUNCH(STATSV)                                                                           \
     {                                                                                                    \
         auto kern = quad ? score_w1g4_kernel<EP <= 8 ? EP : 8, STATSV> : score_w1g_kernel<EP, STATSV>;   \
@@ -1598,7 +1915,8 @@ static int launch_wide(cudaStream_t st, const uint64_t *rows, int64_t P, int W64
 
 template <int EP>
 static int launch_ep(cudaStream_t st, const uint64_t *rows, int64_t P, int W64, double *ws, int N, double *out,
-                     int32_t *status, const double *log_prior, double *stats, bool *stats_done)
+                     int32_t *status, const double *log_prior, double *stats, bool *stats_done, double *tile_pairs,
+                     bool *pairs_done)
 {
     if (W64 == 1) {
         *stats_done = true;
@@ -1608,7 +1926,7 @@ static int launch_ep(cudaStream_t st, const uint64_t *rows, int64_t P, int W64, 
             const bool aligned = ((reinterpret_cast<uintptr_t>(rows) | reinterpret_cast<uintptr_t>(out)) & 31) == 0;
             if (g_split_tables && EP <= 8 && aligned)
                 return launch_w1s4<(EP <= 8 ? EP : 8)>(st, rows, P, ws, N, out, status, log_prior, stats);
-            return launch_w1g<EP>(st, rows, P, ws, N, out, status, log_prior, stats);
+            return launch_w1g<EP>(st, rows, P, ws, N, out, status, log_prior, stats, tile_pairs, pairs_done);
         }
         const bool aligned32 = ((reinterpret_cast<uintptr_t>(rows) | reinterpret_cast<uintptr_t>(out)) & 31) == 0;
         if (EP <= 8 && lut8 <= 100 * 1024 && aligned32 && P >= 64)
@@ -1628,8 +1946,9 @@ extern "C" size_t mitre_score_workspace_bytes(int N, int p)
 {
     if (N <= 0 || p <= 0 || p > MITRE_MAX_P) return 0;
     size_t n = (size_t)kHdr + (size_t)N * ep_for(p) + 2 * (size_t)kMaxStatCtas;
-    if (N <= 64) {   // tables of the large-table kernels (either layout)
-        const size_t a = tables16_doubles(N, ep_for(p)), b = split_tables_doubles(N, ep_for(p));
+    if (N <= 64) {   // tables of the large-table kernels (any layout)
+        const int stride = ep_for(p) > kCoopStride ? ep_for(p) : kCoopStride;
+        const size_t a = tables16_doubles(N, stride), b = split_tables_doubles(N, ep_for(p));
         n += a > b ? a : b;
     } else {
         n += tables8_doubles(N, ep_for(p));                // byte tables of score_wide8_kernel
@@ -1666,6 +1985,16 @@ extern "C" int mitre_set_wide_tables(int enable)
 extern "C" int mitre_weight_stats(void *stream, const double *a, const double *b, int64_t P, double *stats,
                                   void *workspace, size_t workspace_bytes);
 extern "C" size_t mitre_draw_workspace_bytes(int64_t P);
+namespace mitre {
+int launch_tile_pairs(cudaStream_t st, const double *a, const double *b, int64_t P, double *pairs);   // draw.cu
+}
+
+extern "C" int mitre_set_dedupe(int mode)
+{
+    if (mode < 0 || mode > 2) return MITRE_ERR_INVALID;
+    g_dedupe = mode;
+    return MITRE_OK;
+}
 
 extern "C" int mitre_score_all_stats(void *stream, const uint64_t *packed_truth, int64_t P, int W64,
                                      const uint64_t *mask, const double *X, const double *omega,
@@ -1681,17 +2010,21 @@ extern "C" int mitre_score_all_stats(void *stream, const uint64_t *packed_truth,
     if (!(sigma2 > 0.0)) return MITRE_ERR_INVALID;
     if (workspace_bytes < mitre_score_workspace_bytes(N, p)) return MITRE_ERR_WORKSPACE;
     if (log_prior && !stats) return MITRE_ERR_INVALID;
+    if (stats_workspace && stats_workspace_bytes < mitre_draw_workspace_bytes(P)) return MITRE_ERR_WORKSPACE;
     cudaStream_t st = as_stream(stream);
     double *ws = static_cast<double *>(workspace);
     score_setup_kernel<<<1, 256, 0, st>>>(X, omega, kappa, mask, N, p, sigma2, ws, status);
     MITRE_LAUNCH_CHECK();
     if (P == 0) return MITRE_OK;
-    bool stats_done = false;
+    // per-tile (max, sum-exp) pairs for mitre_draw_from_tiles, when the caller passes a draw workspace
+    double *tile_pairs = (stats && stats_workspace) ? static_cast<double *>(stats_workspace) + draw_off_pairs() : nullptr;
+    bool stats_done = false, pairs_done = false;
     int rc = MITRE_ERR_UNSUPPORTED;
     switch (ep_for(p)) {
 #define MITRE_EP_CASE(E)                                                                                  \
     case E:                                                                                               \
-        rc = launch_ep<E>(st, packed_truth, P, W64, ws, N, out, status, log_prior, stats, &stats_done);   \
+        rc = launch_ep<E>(st, packed_truth, P, W64, ws, N, out, status, log_prior, stats, &stats_done,    \
+                          tile_pairs, &pairs_done);                                                       \
         break;
         MITRE_EP_CASE(4)
         MITRE_EP_CASE(6)
@@ -1710,9 +2043,11 @@ extern "C" int mitre_score_all_stats(void *stream, const uint64_t *packed_truth,
     if (rc != MITRE_OK) return rc;
     if (stats && !stats_done) {
         // wide path: separate reduction over the scored slice
-        if (!stats_workspace || stats_workspace_bytes < mitre_draw_workspace_bytes(P)) return MITRE_ERR_WORKSPACE;
-        return mitre_weight_stats(stream, out, log_prior, P, stats, stats_workspace, stats_workspace_bytes);
+        if (!stats_workspace) return MITRE_ERR_WORKSPACE;
+        rc = mitre_weight_stats(stream, out, log_prior, P, stats, stats_workspace, stats_workspace_bytes);
+        if (rc != MITRE_OK) return rc;
     }
+    if (tile_pairs && !pairs_done) return launch_tile_pairs(st, out, log_prior, P, tile_pairs);
     return MITRE_OK;
 }
 

@@ -386,12 +386,19 @@ def weight_stats(a, b=None, buffers=None):
     return buffers.stats
 
 
-def draw_index(a, b, u, stabilise=False, buffers=None, reuse_stats=False):
+def draw_index(a, b, u, stabilise=False, buffers=None, reuse_stats=False, reuse_tiles=False):
     """#{cumsum(exp(w)) < u * total} (rules.py:1261-1264) as an int64[1] device tensor.
     stabilise: subtract max(w) before exp; reuse_stats: buffers.stats already holds (max, sum-exp) of
-    exactly these weights (e.g. from score_all_stats), so the extra pass over w is skipped."""
+    exactly these weights (e.g. from score_all_stats), so the extra pass over w is skipped;
+    reuse_tiles: buffers.workspace also still holds the per-tile pairs score_all_stats left for exactly
+    these weights (a = out, b = log_prior), so NO pass over the P weights is made at all."""
     P = a.shape[0]
     buffers = buffers or DrawBuffers(P)
+    if reuse_tiles:
+        check(lib().mitre_draw_from_tiles(_stream(), _p(a), _p(b), P, float(u), 1 if stabilise else 0,
+                                          _p(buffers.stats), _p(buffers.index), _p(buffers.workspace),
+                                          buffers.workspace.numel()), "mitre_draw_from_tiles")
+        return buffers.index
     mode = (2 if reuse_stats else 1) if stabilise else 0
     check(lib().mitre_draw_index(_stream(), _p(a), _p(b), P, float(u), mode,
                                  _p(buffers.stats), _p(buffers.index), _p(buffers.workspace),
