@@ -41,6 +41,7 @@ extern "C" {
 #define MITRE_STATUS_BASE_NOT_PD 1u   /* base system I/sigma^2 + X'OmegaX not positive definite */
 #define MITRE_STATUS_BAD_SCHUR 2u     /* a candidate's Schur complement was <= 0 or non-finite  */
 #define MITRE_STATUS_COV_NOT_PD 4u    /* dense covariance not positive definite                 */
+#define MITRE_STATUS_COMM_TIMEOUT 8u  /* sharded draw: a peer's pair / the owner's index never arrived */
 
 #define MITRE_MAX_P 24                /* columns of the base design matrix X the kernels accept */
 
@@ -312,6 +313,44 @@ int mitre_draw_index(void *stream, const double *a, const double *b, int64_t P, 
 int mitre_draw_from_tiles(void *stream, const double *a, const double *b, int64_t P, double u,
                           int stabilise, const double *stats, int64_t *index_out, void *workspace,
                           size_t workspace_bytes);
+
+/* ---- sharded draw: one problem's candidates in contiguous slices over the GPUs of one box ---------
+ *
+ * Reference precedent: _likelihood_worker's [start, stop) slices of the candidate table
+ * (logit_rules.py:21-60); the consumer is the same choose_from_relative_probabilities draw over ALL
+ * candidates (logit_rules.py:861-863, rules.py:1261-1264).  Every rank scores its slice with
+ * mitre_score_all_stats (stats_workspace = its draw workspace, so the per-tile pairs are there), calls
+ * mitre_sharded_chunk_sums, and then either
+ *   mitre_sharded_draw    does both exchanges itself over NVLink peer memory inside one kernel: every
+ *                         rank stores its (max, sum-exp) pair into every peer's slot buffer, waits for
+ *                         all pairs of this step's sequence number, derives the common plan (total mass,
+ *                         marker, owner);
+ *                         the owner selects inside its slice and stores the global index into every
+ *                         peer's result slot.  index_out[0] = global index, stats_out = (M, total) with
+ *                         log-sum-exp over all ranks' weights = M + log(total).  Waits are bounded
+ *                         (MITRE_STATUS_COMM_TIMEOUT in *status, index -1).  ALL ranks must launch it,
+ *                         each on its own GPU.
+ *   mitre_sharded_select  the same selection with the exchanges left to the caller (NCCL): `gathered`
+ *                         float64[world, 2] = all ranks' pairs; non-owners write index -1 (all-reduce
+ *                         MAX of index_out afterwards).
+ * `step` is a DEVICE float64[2] = (u, seq): the uniform draw and the step's sequence number (an integer
+ * >= 1, strictly increasing, the same on all ranks for the same step) -- device-resident so that the
+ * whole step can be replayed as a CUDA graph with only a host->device copy of these 16 bytes changing.
+ * mitre_comm_create allocates the slot buffer other ranks write into and returns its 64-byte CUDA IPC
+ * handle in handle_out_host; mitre_comm_connect takes all ranks' handles (world x 64 bytes, rank order).
+ * world <= 16.  world == 1 works without IPC (a single-GPU run of the same code path).
+ */
+int mitre_comm_create(int world, int rank, void **comm_out_host, void *handle_out_host);
+int mitre_comm_connect(void *comm, const void *all_handles_host);
+int mitre_comm_destroy(void *comm);
+int mitre_sharded_chunk_sums(void *stream, int64_t P_local, const double *local_stats, void *workspace,
+                             size_t workspace_bytes);
+int mitre_sharded_draw(void *stream, void *comm, const double *step, const double *local_stats,
+                       const double *a, const double *b, int64_t P_local, int64_t start, void *workspace,
+                       size_t workspace_bytes, int64_t *index_out, double *stats_out, int32_t *status);
+int mitre_sharded_select(void *stream, int world, int rank, const double *step, const double *gathered,
+                         const double *a, const double *b, int64_t P_local, int64_t start, void *workspace,
+                         size_t workspace_bytes, int64_t *index_out, double *stats_out);
 
 /* ---- primitive prior on the device: replaces the O(P) host evaluation of flat_prior ------------
  *

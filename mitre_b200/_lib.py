@@ -20,6 +20,7 @@ MITRE_ERR_NOT_PD = -4
 STATUS_BASE_NOT_PD = 1
 STATUS_BAD_SCHUR = 2
 STATUS_COV_NOT_PD = 4
+STATUS_COMM_TIMEOUT = 8
 MAX_P = 24
 
 # name -> (restype, argtypes); every symbol include/mitre_b200.h declares
@@ -85,6 +86,14 @@ SIGNATURES = {
                                    c_size_t]),
     "mitre_draw_index": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_double, c_int, c_void_p,
                                  c_void_p, c_void_p, c_size_t]),
+    "mitre_comm_create": (c_int, [c_int, c_int, ctypes.POINTER(c_void_p), c_void_p]),
+    "mitre_comm_connect": (c_int, [c_void_p, c_void_p]),
+    "mitre_comm_destroy": (c_int, [c_void_p]),
+    "mitre_sharded_chunk_sums": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_size_t]),
+    "mitre_sharded_draw": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_i64, c_i64, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
+    "mitre_sharded_select": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64,
+                                     c_void_p, c_size_t, c_void_p, c_void_p]),
     "mitre_draw_from_tiles": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_double, c_int, c_void_p,
                                       c_void_p, c_void_p, c_size_t]),
 }

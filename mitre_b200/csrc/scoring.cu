@@ -29,8 +29,31 @@ namespace mitre {
 // workspace layout (doubles): header[8] then q[N][EP]
 //   header[0] = base log-likelihood C0, [1] = 1/sigma2, [2] = sigma2
 constexpr int kHdr = 8;
+constexpr int kTicketSlot = 6;         // header[6] (as uint32): ticket of the candidate kernel's last-CTA reduction
 constexpr int kMaxStatCtas = 2048;   // per-CTA (max, sum-exp) partials live at the end of the workspace
 __host__ __device__ inline int ep_for(int p) { return (p + 2 + 1) & ~1; }  // even, >= p+2
+
+// Table t covers subjects [table16_start, +table16_bits): the split is aligned to the LAST subject
+// (table 0 takes the N mod 16 remainder), because neighbouring rows of a lexsorted table differ in
+// their trailing subjects: all of a warp's divergent lookups then fall into the last table and the
+// leading tables are warp-uniform loads.
+__host__ __device__ inline int n_tables16(int N) { return (N + 15) >> 4; }
+__host__ __device__ inline int table16_bits(int N, int t)
+{
+    const int first = N - 16 * (n_tables16(N) - 1);
+    return t == 0 ? first : 16;
+}
+__host__ __device__ inline int table16_start(int N, int t)
+{
+    return t == 0 ? 0 : table16_bits(N, 0) + 16 * (t - 1);
+}
+__host__ __device__ inline size_t tables16_doubles(int N, int EP)
+{
+    size_t n = 0;
+    for (int t = 0; t < n_tables16(N); ++t) n += ((size_t)1 << table16_bits(N, t)) * EP;
+    return n;
+}
+
 
 // ---------------------------------------------------------------------------------------------
 // Table-driven log / reciprocal / exp for the per-candidate epilogue.  The stock fp64 log and
@@ -201,6 +224,33 @@ __device__ double base_system(const double *__restrict__ X, int ldx, const doubl
     return sred[0];
 }
 
+// q_i = (omega_i, r_i, w_i) of one subject (zeros outside the rule mask, NaN when the base system failed)
+__device__ __forceinline__ void subject_vector(const double *__restrict__ X, const double *__restrict__ omega,
+                                               const double *__restrict__ kappa, const uint64_t *__restrict__ mask,
+                                               int i, int p, int EP, const double *sA, const double *sb, int ok,
+                                               double *qi)
+{
+    const bool in_mask = (mask == nullptr) || (mask[i >> 6] & subject_bit(i));
+    if (!in_mask || !ok) {
+        for (int e = 0; e < EP; ++e) qi[e] = ok ? 0.0 : nan("");
+        return;
+    }
+    const double om = omega[i];
+    double w[MITRE_MAX_P];
+    double dot = 0.0;
+    for (int j = 0; j < p; ++j) {
+        double s = om * X[(size_t)i * p + j];
+        for (int k = 0; k < j; ++k) s -= sA[j * p + k] * w[k];
+        s /= sA[j * p + j];
+        w[j] = s;
+        dot += s * sb[j];
+    }
+    qi[0] = om;
+    qi[1] = kappa[i] - dot;
+    for (int j = 0; j < p; ++j) qi[2 + j] = w[j];
+    for (int e = p + 2; e < EP; ++e) qi[e] = 0.0;
+}
+
 __global__ void __launch_bounds__(256)
 score_setup_kernel(const double *__restrict__ X, const double *__restrict__ omega,
                    const double *__restrict__ kappa, const uint64_t *__restrict__ mask, int N, int p,
@@ -220,27 +270,58 @@ score_setup_kernel(const double *__restrict__ X, const double *__restrict__ omeg
         if (!s_ok && status) atomicOr(reinterpret_cast<unsigned int *>(status), MITRE_STATUS_BASE_NOT_PD);
     }
     double *q = ws + kHdr;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        const bool in_mask = (mask == nullptr) || (mask[i >> 6] & subject_bit(i));
-        double *qi = q + (size_t)i * EP;
-        if (!in_mask || !s_ok) {
-            for (int e = 0; e < EP; ++e) qi[e] = s_ok ? 0.0 : nan("");
-            continue;
+    for (int i = threadIdx.x; i < N; i += blockDim.x)
+        subject_vector(X, omega, kappa, mask, i, p, EP, sA, sb, s_ok, q + (size_t)i * EP);
+}
+
+// One launch for everything a large-table sweep needs before the candidate kernel: every CTA redoes the
+// (tiny) base system in shared memory and builds its share of the 16-subject subset-sum tables straight
+// from it; CTA 0 also writes the header and q to the workspace and clears the ticket of the candidate
+// kernel's final reduction.  Replaces score_setup_kernel + score_build_tables16_kernel (two dependent
+// launches, ~30 us) where the step itself is a few hundred microseconds (sharded sweeps).
+__global__ void __launch_bounds__(256)
+score_prepare16_kernel(const double *__restrict__ X, const double *__restrict__ omega,
+                       const double *__restrict__ kappa, const uint64_t *__restrict__ mask, int N, int p,
+                       double sigma2, double *__restrict__ ws, int32_t *status, int stride,
+                       double *__restrict__ tables)
+{
+    __shared__ double sA[MITRE_MAX_P * MITRE_MAX_P];
+    __shared__ double sb[MITRE_MAX_P];
+    __shared__ double sred[256];
+    __shared__ int s_ok;
+    extern __shared__ double sq[];                  // [N][EP]
+    const int EP = ep_for(p);
+    const double C0 = base_system(X, p, omega, kappa, N, p, sigma2, sA, sb, sred, &s_ok);
+    for (int i = threadIdx.x; i < N; i += blockDim.x)
+        subject_vector(X, omega, kappa, mask, i, p, EP, sA, sb, s_ok, sq + (size_t)i * EP);
+    __syncthreads();
+    if (blockIdx.x == 0) {
+        if (threadIdx.x == 0) {
+            ws[0] = C0;
+            ws[1] = 1.0 / sigma2;
+            ws[2] = sigma2;
+            ws[3] = C0 - 0.5 * log(sigma2);
+            *reinterpret_cast<unsigned int *>(ws + kTicketSlot) = 0u;
+            if (!s_ok && status) atomicOr(reinterpret_cast<unsigned int *>(status), MITRE_STATUS_BASE_NOT_PD);
         }
-        const double om = omega[i];
-        double w[MITRE_MAX_P];
-        double dot = 0.0;
-        for (int j = 0; j < p; ++j) {
-            double s = om * X[(size_t)i * p + j];
-            for (int k = 0; k < j; ++k) s -= sA[j * p + k] * w[k];
-            s /= sA[j * p + j];
-            w[j] = s;
-            dot += s * sb[j];
+        for (int i = threadIdx.x; i < N * EP; i += blockDim.x) ws[kHdr + i] = sq[i];
+    }
+    const int nt = n_tables16(N);
+    size_t base = 0;
+    for (int t = 0; t < nt; ++t) {
+        const int bits = table16_bits(N, t), start = table16_start(N, t);
+        const size_t count = ((size_t)1 << bits) * stride;
+        for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < count;
+             idx += (size_t)gridDim.x * blockDim.x) {
+            const int e = (int)(idx % stride);
+            const unsigned pat = (unsigned)(idx / stride);
+            double acc = 0.0;
+            if (e < EP)
+                for (int j = 0; j < bits; ++j)
+                    if ((pat >> (bits - 1 - j)) & 1) acc += sq[(start + j) * EP + e];
+            tables[base + idx] = acc;
         }
-        qi[0] = om;
-        qi[1] = kappa[i] - dot;
-        for (int j = 0; j < p; ++j) qi[2 + j] = w[j];
-        for (int e = p + 2; e < EP; ++e) qi[e] = 0.0;
+        base += count;
     }
 }
 
@@ -514,27 +595,6 @@ static int64_t g_large_table_min_rows = kLargeTableMinRows;
 static int g_groups_warp = 1;    // mitre_score_groups, N <= 64: 1 warp per group (default), 0 CTA per group
 static int g_wide_tables = 1;    // N > 64: 1 byte tables (score_wide8_kernel), 0 per-set-bit sums (score_wide_kernel)
 static int g_split_tables = 0;   // 1: last table in shared memory (score_w1s4_kernel), 0: score_w1g4_kernel (default)
-
-// Table t covers subjects [table16_start, +table16_bits): the split is aligned to the LAST subject
-// (table 0 takes the N mod 16 remainder), because neighbouring rows of a lexsorted table differ in
-// their trailing subjects: all of a warp's divergent lookups then fall into the last table and the
-// leading tables are warp-uniform loads.
-__host__ __device__ inline int n_tables16(int N) { return (N + 15) >> 4; }
-__host__ __device__ inline int table16_bits(int N, int t)
-{
-    const int first = N - 16 * (n_tables16(N) - 1);
-    return t == 0 ? first : 16;
-}
-__host__ __device__ inline int table16_start(int N, int t)
-{
-    return t == 0 ? 0 : table16_bits(N, 0) + 16 * (t - 1);
-}
-__host__ __device__ inline size_t tables16_doubles(int N, int EP)
-{
-    size_t n = 0;
-    for (int t = 0; t < n_tables16(N); ++t) n += ((size_t)1 << table16_bits(N, t)) * EP;
-    return n;
-}
 
 // entry (table t, pattern x): sum of q_i over subjects i = 16 t + j whose pattern bit (bits-1-j)
 // is set, in ascending subject order.
@@ -1330,7 +1390,7 @@ __global__ void __launch_bounds__(256)
 score_w1d_kernel(const uint64_t *__restrict__ rows, int64_t P, const double *__restrict__ ws, int N,
                  const double *__restrict__ tables, double *__restrict__ out, int32_t *status,
                  const double *__restrict__ log_prior, double *__restrict__ stat_partials,
-                 double *__restrict__ tile_pairs)
+                 double *__restrict__ tile_pairs, unsigned int *ticket, double *__restrict__ stats)
 {
     static_assert(EP <= kCoopStride, "entries are 64 bytes");
     __shared__ double2 logtab[kLogTab];
@@ -1550,7 +1610,8 @@ score_w1d_kernel(const uint64_t *__restrict__ rows, int64_t P, const double *__r
     }
     if (bad && status) atomicOr(reinterpret_cast<unsigned int *>(status), MITRE_STATUS_BAD_SCHUR);
     if (STATS) {
-        __shared__ double sm[8], ss[8];
+        __shared__ double sm[256], ss[256];
+        __shared__ int s_last;
         if (lane == 0) { sm[wid] = run.m; ss[wid] = run.s; }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -1558,6 +1619,32 @@ score_w1d_kernel(const uint64_t *__restrict__ rows, int64_t P, const double *__r
             for (int w8 = 1; w8 < 8; ++w8) x = ms_merge(x, MaxSum{sm[w8], ss[w8]});
             stat_partials[2 * blockIdx.x] = x.m;
             stat_partials[2 * blockIdx.x + 1] = x.s;
+            // the CTA that takes the last ticket merges all partials (in index order: the result does not
+            // depend on which CTA that is) -- no separate reduction launch
+            __threadfence();
+            s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            MaxSum acc = {-INFINITY, 0.0};
+            for (int i = threadIdx.x; i < (int)gridDim.x; i += 256)
+                acc = ms_merge(acc, MaxSum{__ldcg(stat_partials + 2 * i), __ldcg(stat_partials + 2 * i + 1)});
+            sm[threadIdx.x] = acc.m; ss[threadIdx.x] = acc.s;
+            __syncthreads();
+            for (int s2 = 128; s2 > 0; s2 >>= 1) {
+                if (threadIdx.x < s2) {
+                    const MaxSum x = ms_merge(MaxSum{sm[threadIdx.x], ss[threadIdx.x]},
+                                              MaxSum{sm[threadIdx.x + s2], ss[threadIdx.x + s2]});
+                    sm[threadIdx.x] = x.m; ss[threadIdx.x] = x.s;
+                }
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) {
+                stats[0] = sm[0];
+                stats[1] = ss[0];
+                *ticket = 0u;
+            }
         }
     }
 }
@@ -1810,6 +1897,16 @@ static int launch_w1r4(cudaStream_t st, const uint64_t *rows, int64_t P, double 
     return MITRE_OK;
 }
 
+// The duplicate-aware kernel: 4 rows per lane as two 16-byte loads, entries of at most 8 doubles.
+static bool dedupe_eligible(int EP, int64_t P, const uint64_t *rows, const double *out, const double *log_prior,
+                            const double *tile_pairs)
+{
+    return g_dedupe && EP <= 8 && P >= 1024 &&
+           ((reinterpret_cast<uintptr_t>(rows) | reinterpret_cast<uintptr_t>(out)) & 31) == 0 &&
+           ((reinterpret_cast<uintptr_t>(log_prior) | reinterpret_cast<uintptr_t>(tile_pairs)) & 15) == 0;
+}
+static double *tables16_ptr(double *ws, int N, int EP) { return ws + kHdr + (size_t)N * EP + 2 * kMaxStatCtas; }
+
 template <int EP>
 static int launch_w1g(cudaStream_t st, const uint64_t *rows, int64_t P, double *ws, int N, double *out,
                       int32_t *status, const double *log_prior, double *stats, double *tile_pairs, bool *pairs_done)
@@ -1818,15 +1915,16 @@ static int launch_w1g(cudaStream_t st, const uint64_t *rows, int64_t P, double *
     double *tables = partials + 2 * kMaxStatCtas;
     const bool quad = EP <= 8 && P >= 1024 &&
                       ((reinterpret_cast<uintptr_t>(rows) | reinterpret_cast<uintptr_t>(out)) & 31) == 0;
-    const bool dedupe = quad && g_dedupe &&
-                        ((reinterpret_cast<uintptr_t>(log_prior) | reinterpret_cast<uintptr_t>(tile_pairs)) & 15) == 0;
+    const bool dedupe = dedupe_eligible(EP, P, rows, out, log_prior, tile_pairs);
     const bool coop = dedupe && g_dedupe == 2;
     const int stride = coop ? kCoopStride : EP;
-    const size_t entries = tables16_doubles(N, stride);
-    int64_t bblocks = ceil_div64((int64_t)entries, 256);
-    if (bblocks > 8 * sm_count()) bblocks = 8 * sm_count();
-    score_build_tables16_kernel<<<(unsigned)bblocks, 256, 0, st>>>(ws, N, EP, stride, tables);
-    MITRE_LAUNCH_CHECK();
+    if (!dedupe) {      // the duplicate-aware path got its tables from score_prepare16_kernel
+        const size_t entries = tables16_doubles(N, stride);
+        int64_t bblocks = ceil_div64((int64_t)entries, 256);
+        if (bblocks > 8 * sm_count()) bblocks = 8 * sm_count();
+        score_build_tables16_kernel<<<(unsigned)bblocks, 256, 0, st>>>(ws, N, EP, stride, tables);
+        MITRE_LAUNCH_CHECK();
+    }
     int per_sm = 1;
     int64_t blocks = 0;
     if (dedupe) {
@@ -1841,13 +1939,12 @@ static int launch_w1g(cudaStream_t st, const uint64_t *rows, int64_t P, double *
         if (need < blocks) blocks = need;                                                                \
         if (blocks > kMaxStatCtas) blocks = kMaxStatCtas;                                                \
         kern<<<(unsigned)blocks, 256, 0, st>>>(rows, P, ws, N, tables, out, status, log_prior, partials, \
-                                               tile_pairs);                                              \
+                                               tile_pairs, reinterpret_cast<unsigned int *>(ws + kTicketSlot), \
+                                               stats);                                                   \
         MITRE_LAUNCH_CHECK();                                                                            \
     }
         if (stats) {
             MITRE_D_LAUNCH(true)
-            score_stats_final_kernel<<<1, 256, 0, st>>>(partials, (int)blocks, stats);
-            MITRE_LAUNCH_CHECK();
             *pairs_done = tile_pairs != nullptr;
         } else {
             MITRE_D_LAUNCH(false)
@@ -2013,11 +2110,20 @@ extern "C" int mitre_score_all_stats(void *stream, const uint64_t *packed_truth,
     if (stats_workspace && stats_workspace_bytes < mitre_draw_workspace_bytes(P)) return MITRE_ERR_WORKSPACE;
     cudaStream_t st = as_stream(stream);
     double *ws = static_cast<double *>(workspace);
-    score_setup_kernel<<<1, 256, 0, st>>>(X, omega, kappa, mask, N, p, sigma2, ws, status);
-    MITRE_LAUNCH_CHECK();
-    if (P == 0) return MITRE_OK;
     // per-tile (max, sum-exp) pairs for mitre_draw_from_tiles, when the caller passes a draw workspace
     double *tile_pairs = (stats && stats_workspace) ? static_cast<double *>(stats_workspace) + draw_off_pairs() : nullptr;
+    const int EPr = ep_for(p);
+    if (P > 0 && W64 == 1 && P >= g_large_table_min_rows && !g_split_tables &&
+        dedupe_eligible(EPr, P, packed_truth, out, log_prior, tile_pairs)) {
+        // base system + tables in one launch
+        const int stride = g_dedupe == 2 ? kCoopStride : EPr;
+        score_prepare16_kernel<<<2 * sm_count(), 256, sizeof(double) * (size_t)N * EPr, st>>>(
+            X, omega, kappa, mask, N, p, sigma2, ws, status, stride, tables16_ptr(ws, N, EPr));
+    } else {
+        score_setup_kernel<<<1, 256, 0, st>>>(X, omega, kappa, mask, N, p, sigma2, ws, status);
+    }
+    MITRE_LAUNCH_CHECK();
+    if (P == 0) return MITRE_OK;
     bool stats_done = false, pairs_done = false;
     int rc = MITRE_ERR_UNSUPPORTED;
     switch (ep_for(p)) {

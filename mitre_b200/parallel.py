@@ -170,6 +170,179 @@ class ShardedScorer:
         return two_stage_draw(stats, local_draw, self.start, u, self.group, stabilise)
 
 
+class ShardedSweep:
+    """One problem's candidate sweep and proposal draw over the ranks of a process group: the sampler's
+    detector update (logit_rules.py:851-863) with the candidate table cut into contiguous slices, one per
+    GPU (_likelihood_worker's [start, stop) slices, logit_rules.py:21-60).
+
+    Per step every rank runs, on its own stream and with no host involvement in between:
+        H2D of the sweep inputs (X, omega, kappa, mask; KBs) and of (u, seq)
+        mitre_score_all_stats on its slice   -> log-likelihoods, (max, sum-exp) of lik + prior, tile pairs
+        mitre_sharded_chunk_sums
+        the exchange + draw                   -> the global index and log-sum-exp on EVERY rank
+    exchange='p2p'   mitre_sharded_draw: both exchanges inside one kernel over NVLink peer memory
+                     (CUDA IPC); the whole step is captured once as a CUDA graph and replayed
+    exchange='nccl'  all-gather of the pairs, mitre_sharded_select, all-reduce MAX of the index
+    Nothing P-long ever leaves a GPU; 16 bytes per rank go out, 16 bytes come back.
+
+    local_rows int64[n, 1] CUDA (this rank's slice of the lexsorted table), local_prior float64[n] or
+    None, P the global candidate count, start the slice's first global index."""
+
+    def __init__(self, local_rows, local_prior, P, N, start, group=None, exchange='p2p', max_p=None,
+                 use_graph=True):
+        import ctypes
+        from . import device as D
+        from ._lib import lib, check, MAX_P
+        self.D, self.group = D, group
+        self.ws, self.rank = world(group)
+        self.P, self.N, self.start = int(P), int(N), int(start)
+        self.rows, self.prior = local_rows, local_prior
+        self.n = int(local_rows.shape[0])
+        self.W64 = D.words_for(N)
+        self.max_p = MAX_P if max_p is None else int(max_p)
+        dev = local_rows.device
+        self.buffers = D.ScoreBuffers(max(self.n, 1), self.N, self.max_p)
+        self.draw = D.DrawBuffers(max(self.n, 1))
+        n_small = self.N * self.max_p + 2 * self.N + self.W64
+        self.h_small = torch.zeros(n_small + 2, dtype=torch.float64).pin_memory()   # ..., u, seq
+        self.d_small = torch.zeros(n_small + 2, dtype=torch.float64, device=dev)
+        self.d_step = self.d_small[n_small:]
+        self.d_res = torch.zeros(4, dtype=torch.float64, device=dev)    # index (int64 bits), M, total, status
+        self.h_res = torch.zeros(4, dtype=torch.float64).pin_memory()
+        self._empty_stats = torch.tensor([-np.inf, 0.0], dtype=torch.float64, device=dev)
+        self.gathered = torch.zeros(2 * self.ws, dtype=torch.float64, device=dev)
+        self.seq = 0
+        self.exchange = exchange
+        self.comm = None
+        self._graph = None
+        self._graph_p = None
+        self.use_graph = use_graph
+        if exchange == 'p2p':
+            comm = ctypes.c_void_p()
+            handle = ctypes.create_string_buffer(64)
+            check(lib().mitre_comm_create(self.ws, self.rank, ctypes.byref(comm), handle), "mitre_comm_create")
+            handles = [None] * self.ws
+            if self.ws > 1:
+                dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            else:
+                handles = [bytes(handle.raw)]
+            check(lib().mitre_comm_connect(comm, ctypes.c_char_p(b"".join(handles))), "mitre_comm_connect")
+            self.comm = comm
+            if self.ws > 1:
+                dist.barrier(group=group)
+        elif exchange != 'nccl':
+            raise ValueError("exchange must be 'p2p' or 'nccl'")
+
+    def close(self):
+        from ._lib import lib
+        if self.comm is not None:
+            torch.cuda.synchronize()
+            lib().mitre_comm_destroy(self.comm)
+            self.comm = None
+
+    # -- host staging ---------------------------------------------------------------------------------
+    def stage(self, X, omega, kappa, mask_bool, u):
+        """Write one step's inputs into the pinned buffer (no CUDA call)."""
+        N, W64, mp = self.N, self.W64, self.max_p
+        X = np.asarray(X, dtype=np.float64)
+        p = X.shape[1]
+        if p > mp:
+            raise ValueError('design matrix has %d columns; this sweep was sized for %d' % (p, mp))
+        h = self.h_small.numpy()
+        h[:N * p] = X.reshape(-1)
+        o = N * mp
+        h[o:o + N] = omega
+        h[o + N:o + 2 * N] = kappa
+        h[o + 2 * N:o + 2 * N + W64] = self.D.pack_mask(mask_bool).view(np.float64)
+        self.seq += 1
+        h[o + 2 * N + W64] = u
+        h[o + 2 * N + W64 + 1] = float(self.seq)
+        return p
+
+    def _views(self, p):
+        N, W64, o = self.N, self.W64, self.N * self.max_p
+        d = self.d_small
+        return (d[:N * p].view(N, p), d[o:o + N], d[o + N:o + 2 * N],
+                d[o + 2 * N:o + 2 * N + W64].view(dtype=torch.int64))
+
+    # -- device work of one step (stream-ordered, no synchronisation) ----------------------------------
+    def _launch(self, p, sigma2):
+        from ._lib import lib, check
+        D = self.D
+        _p, _s = D._p, D._stream
+        self.d_small.copy_(self.h_small, non_blocking=True)
+        dX, dom, dka, dmask = self._views(p)
+        out = self.buffers.out[:self.n]
+        if self.n:
+            D.score_all_stats(self.rows, self.N, dX, dom, dka, sigma2, mask=dmask, buffers=self.buffers,
+                              out=out, log_prior=self.prior, draw_buffers=self.draw)
+        else:
+            self.draw.stats.copy_(self._empty_stats)
+        wsb = self.draw.workspace
+        check(lib().mitre_sharded_chunk_sums(_s(), self.n, _p(self.draw.stats), _p(wsb), wsb.numel()),
+              "mitre_sharded_chunk_sums")
+        idx_out = self.d_res[:1].view(torch.int64)
+        if self.exchange == 'p2p':
+            check(lib().mitre_sharded_draw(_s(), self.comm, _p(self.d_step), _p(self.draw.stats), _p(out),
+                                           _p(self.prior), self.n, self.start, _p(wsb), wsb.numel(), _p(idx_out),
+                                           _p(self.d_res[1:3]), _p(self.buffers.status)), "mitre_sharded_draw")
+        else:
+            if self.ws > 1:
+                dist.all_gather_into_tensor(self.gathered, self.draw.stats, group=self.group)
+            else:
+                self.gathered.copy_(self.draw.stats)
+            check(lib().mitre_sharded_select(_s(), self.ws, self.rank, _p(self.d_step), _p(self.gathered), _p(out),
+                                             _p(self.prior), self.n, self.start, _p(wsb), wsb.numel(), _p(idx_out),
+                                             _p(self.d_res[1:3])), "mitre_sharded_select")
+            if self.ws > 1:
+                dist.all_reduce(idx_out, op=dist.ReduceOp.MAX, group=self.group)
+        self.d_res[3:].copy_(self.buffers.status)      # status word rides along with the result
+        self.h_res.copy_(self.d_res, non_blocking=True)
+        return out
+
+    def launch(self, p, sigma2):
+        """Enqueue one step (inputs already staged).  p2p: replayed as a CUDA graph after the first call."""
+        if self.exchange == 'p2p' and self.use_graph:
+            if self._graph is None or self._graph_p != (p, float(sigma2)):
+                # warm-up outside capture (lazy module loading, attribute setting), then capture
+                self._launch(p, sigma2)
+                torch.cuda.current_stream().synchronize()
+                self._redo_seq()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._launch(p, sigma2)
+                self._graph, self._graph_p = g, (p, float(sigma2))
+                # the captured launch has not run: the staged step is still pending
+            self._graph.replay()
+        else:
+            self._launch(p, sigma2)
+
+    def _redo_seq(self):
+        """The warm-up consumed this step's sequence number on every rank; stage the next one."""
+        o = self.N * self.max_p + 2 * self.N + self.W64
+        self.seq += 1
+        self.h_small.numpy()[o + 1] = float(self.seq)
+
+    def result(self):
+        """(global index, log-sum-exp over all candidates) of the last launched step (synchronises; one
+        32-byte device->host copy carries index, pair and status)."""
+        torch.cuda.current_stream().synchronize()
+        r = self.h_res.numpy()
+        status = int(r[3])
+        if status:
+            self.buffers.status.zero_()
+            if status & 8:
+                raise RuntimeError('sharded draw: a peer rank did not answer within the time limit')
+            raise np.linalg.LinAlgError('Matrix is not positive definite (status flags %d)' % status)
+        idx = int(r[:1].view(np.int64)[0])
+        return idx, (float(r[1] + np.log(r[2])) if r[2] > 0 else -np.inf)
+
+    def step(self, X, omega, kappa, mask_bool, u, sigma2):
+        p = self.stage(X, omega, kappa, mask_bool, u)
+        self.launch(p, sigma2)
+        return self.result()
+
+
 # ---- variable-sharded population build (SURVEY 8e, row "Detector evaluation") ------------------
 #
 # Every (window, variable, type) group depends only on its variable's series (rules.py:585-599),

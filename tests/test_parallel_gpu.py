@@ -210,3 +210,112 @@ def test_streaming_sweep_two_gpus_matches_one():
         assert abs(res["all"][0] - res["solo"][0]) <= 1e-12 * abs(res["solo"][0])
         assert res["all"][2] == res["solo"][2]
     assert out[0][1]["all"] == out[1][1]["all"]
+
+
+# ---- ShardedSweep: score + (max, sum-exp) exchange + owner draw + index back, on every rank -----------
+
+def _sweep_case(P=300007, seed=77):
+    """A lexsorted table with runs of equal rows, a prior with -inf entries, sweep inputs."""
+    from tests.golden import make_golden as MG
+    rng = np.random.RandomState(seed)
+    c = MG.scoring_inputs(seed=seed, N=35, p=4, P=8)
+    distinct = rng.rand(P // 6, 35) > 0.5
+    rows = distinct[rng.randint(distinct.shape[0], size=P)]
+    rows = rows[np.lexsort(np.rot90(rows))]
+    prior = rng.normal(-12, 2, size=P)
+    prior[::13] = -np.inf
+    return c, rows, prior
+
+
+def _sweep_reference(c, rows, prior, us):
+    """Single-table answer: log-likelihoods, log-sum-exp and np.cumsum draw of lik + prior."""
+    import torch
+    from mitre_b200 import device as D
+    packed = D.pack_rows(rows)
+    mask = torch.as_tensor(D.pack_mask(c["mask"]), device=D.dev())
+    out, status = D.score_all(packed, 35, c["X"], c["omega"], c["y"] - 0.5, 100.0, mask=mask)
+    D.raise_on_status(status)
+    w = out.cpu().numpy() + prior
+    cum = np.cumsum(np.exp(w - w.max()))
+    lse = float(w.max() + np.log(cum[-1]))
+    return packed, out.clone(), [int(np.sum(cum < u * cum[-1])) for u in us], lse
+
+
+US = [0.0, 0.07, 0.31, 0.5, 0.64, 0.98, 0.999999]
+
+
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+def test_sharded_sweep_single_rank(exchange):
+    """world = 1: the whole sharded step (CUDA graph replay in p2p mode) against numpy's cumsum draw."""
+    import torch
+    from mitre_b200 import device as D, parallel as PL
+    from mitre_b200._lib import lib
+    c, rows, prior = _sweep_case()
+    for min_rows in (0, 4 << 20):        # duplicate-aware large-table kernel / shared-memory-table kernel
+        lib().mitre_set_large_table_min_rows(min_rows)
+        try:
+            packed, out, want, lse = _sweep_reference(c, rows, prior, US)
+            sw = PL.ShardedSweep(packed, torch.as_tensor(prior, device=D.dev()), packed.shape[0], 35, 0,
+                                 exchange=exchange, max_p=4)
+            for u, k in zip(US, want):
+                idx, log_total = sw.step(c["X"], c["omega"], c["y"] - 0.5, c["mask"], u, 100.0)
+                assert idx == k, (exchange, u, idx, k)
+                assert abs(log_total - lse) < 1e-10
+            assert torch.equal(sw.buffers.out[:sw.n], out)
+            sw.close()
+        finally:
+            lib().mitre_set_large_table_min_rows(4 << 20)
+
+
+def _sweep_worker(rank, ws, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=ws, device_id=torch.device("cuda", rank))
+    try:
+        from mitre_b200 import device as D, parallel as PL
+        from mitre_b200._lib import lib
+        lib().mitre_set_large_table_min_rows(0)
+        c, rows, prior = _sweep_case()
+        packed, out, want, lse = _sweep_reference(c, rows, prior, US)
+        P = packed.shape[0]
+        a, b = PL.shard_bounds(P, ws, rank)
+        res = {}
+        for exchange in ("p2p", "nccl"):
+            sw = PL.ShardedSweep(packed[a:b].contiguous(), torch.as_tensor(prior[a:b], device=D.dev()), P, 35, a,
+                                 exchange=exchange, max_p=4)
+            got = [sw.step(c["X"], c["omega"], c["y"] - 0.5, c["mask"], u, 100.0) for u in US]
+            same = bool(torch.equal(sw.buffers.out[:sw.n], out[a:b]))
+            sw.close()
+            res[exchange] = (got, same)
+        q.put((rank, res, want, lse))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_sweep_two_gpus():
+    """2 ranks, both exchange modes: every rank ends every step with the index np.cumsum gives on the whole
+    table and the global log-sum-exp; slice log-likelihoods are bit-identical to the whole-table sweep."""
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ws = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sweep_worker, args=(r, ws, port, q)) for r in range(ws)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=300) for _ in range(ws)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, res, want, lse in out:
+        for exchange, (got, same) in res.items():
+            assert same, (rank, exchange)
+            assert [g[0] for g in got] == want, (rank, exchange, got, want)
+            for _, log_total in got:
+                assert abs(log_total - lse) < 1e-10
