@@ -4,26 +4,34 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path
 
-Workload (config.workload = "S5-primitive-sweep", BASELINE.json configs[4]): N = 35 subjects,
-V = 10,000 aggregated variables, n_intervals = 24 with unrestricted window length (300 windows),
-mean + slope detectors, full threshold grid  ->  ~4.08e8 candidate primitives per GPU, packed
-3.3 GB -- far larger than the 126 MB L2, so no flush is needed between steps.  The table is
-built on the GPU by this repo's detector kernels from synthetic series of that shape.
+Workload (config.workload = "S5-primitive-sweep", BASELINE.json configs[4]): ONE problem of N = 35
+subjects, V = 10,000 aggregated variables, n_intervals = 24 with unrestricted window length, mean +
+slope detectors, full threshold grid -> 2.9e8 candidate primitives (2.35 GB packed, plus 2.35 GB of
+log-prior and 2.35 GB of log-likelihoods per sweep: far larger than the 126 MB L2, so no flush is needed
+between steps).  The table is built on the GPU by this repo's detector kernels from synthetic series of
+that shape.
 
-A step = one scoring sweep over ALL candidates (one `likelihoods_of_all_options` call of the
-MCMC update_primitives move, logit_rules.py:851): base rule list of 3 rules + constant (p = 4),
-fresh omega.
+A step = one detector-update sweep of the sampler over ALL candidates (update_primitives,
+logit_rules.py:794-881: likelihoods_of_all_options + primitive prior + proposal draw): base rule list of 3
+rules + constant (p = 4), base system + subset-sum tables, log-likelihood of every candidate, (max,
+sum-exp) of likelihood + log-prior, proposal draw -- the drawn index and the log-sum-exp are the step's
+result.
 
-  value     evals/s with the sweep inputs already resident in HBM (kernel time only)
-  e2e       evals/s through LogisticRuleModel.likelihoods_of_all_options-equivalent staging:
-            every step copies (X, omega, kappa, mask) from pinned host memory to the device and
-            the P log-likelihoods back to pinned host memory
-  roofline  dominant kernel score_w1_kernel: algorithmic bytes 16 B/candidate (8 B packed row in,
-            8 B log-likelihood out) / its launch time; peak = MEASURED_PEAKS.json hbm_gbs
-  N > 1     weak scaling: every rank owns a full 10,000-variable shard of candidates (different
-            series seed), receives the same sweep inputs, scores its shard, and all ranks
-            all-gather the 16-byte (max, sum-exp) pair of their log-weights over NCCL -- the
-            exchange step of the two-stage proposal draw.
+  value     evals/s of that step with its inputs resident in HBM, device-timed (CUDA events)
+  e2e       the same step through the public call (mitre_b200.parallel.ShardedSweep.step): sweep inputs
+            from pinned host memory every step, drawn index + log-sum-exp + status back to pinned host
+            memory; e2e_full_vector (N = 1) is the reference-signature call that returns all P
+            log-likelihoods to the host (LogisticRuleModel.likelihoods_of_all_options, PCIe-bound)
+  roofline  the step's candidate kernel (score_w1d_kernel, stats variant): algorithmic bytes 24
+            B/candidate (8 B packed row + 8 B log-prior in, 8 B log-likelihood out) / its launch time;
+            peak = MEASURED_PEAKS.json hbm_gbs
+  N > 1     STRONG scaling: the same 10,000-variable problem, built by all ranks together
+            (ShardedPopulation: detectors sharded by variable), its lexsorted candidates cut into N
+            contiguous slices (the reference's own _likelihood_worker precedent, logit_rules.py:21-60).
+            Every rank scores its slice; the 16-byte (max, sum-exp) pairs and the drawn index travel
+            INSIDE the timed step (--exchange p2p: stores into peer memory over NVLink from the draw
+            kernel; --exchange nccl: all-gather + all-reduce).  parity_check: every rank also builds
+            the whole problem alone and verifies rows, log-likelihoods, log-sum-exp and drawn indices.
 """
 import argparse
 import json
@@ -49,11 +57,15 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--variables", type=int, default=10000, help="variables per GPU (S5: 10000)")
+    ap.add_argument("--variables", type=int, default=10000, help="variables of the problem (S5: 10000)")
     ap.add_argument("--rules", type=int, default=3, help="rules in the base rule list (p = rules+1)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: how the (max, sum-exp) pairs and the drawn index travel")
+    ap.add_argument("--check", default="auto", choices=["auto", "on", "off"],
+                    help="sharded == single-GPU parity check on every rank (auto: on for N > 1)")
     return ap.parse_args()
 
 
@@ -147,12 +159,14 @@ def fp64_roofline(D, P, kernel_ms):
             "peak_instr_tops": peak / 2.0, "frac_of_instr_peak": achieved / (peak / 2.0)}
 
 
-def ncu_traffic_per_launch(P):
-    """dram bytes per launch of score_w1_kernel from the committed ncu capture, scaled to P."""
-    path = os.path.join(ROOT, "profiles", "score_w1_traffic.json")
+def ncu_traffic_per_launch(P, which):
+    """dram bytes per launch of the step's candidate kernel: bytes per candidate from the committed ncu
+    --set full capture of the same kernel at the full S5 size (profiles/score_w1d_traffic.json), times the
+    candidates of this launch.  Not measured in this run (bench.py never runs under a profiler)."""
+    path = os.path.join(ROOT, "profiles", "score_w1d_traffic.json")
     try:
         rec = json.load(open(path))
-        return float(rec["dram_bytes_per_candidate"]) * P
+        return float(rec[which]["dram_bytes_per_candidate"]) * P
     except Exception:
         return None
 
@@ -248,7 +262,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": "S5-primitive-sweep", "subjects": N, "variables_sampled": V_s,
                    "candidates_per_step": int(P_s), "base_columns_p": args.rules + 1},
@@ -333,9 +347,64 @@ def detector_bytes(pop, data):
     return 8 * data.n_variables * S + 8 * S + int(np.sum(8 * N + 8 * K + 2 * K * 8 * W64))
 
 
+def build_sharded(args, torch):
+    """ONE S5 problem (args.variables variables in total) built by all ranks together: detectors by
+    variable, one exchange for the global order, every rank keeps its contiguous slice of the sorted
+    candidate table (mitre_b200.parallel.ShardedPopulation)."""
+    from mitre_b200 import parallel as PL, rules as R, synthetic
+    d = synthetic.make_shape("S5", seed=args.seed, V=args.variables)
+    data = R.Dataset(d["X"], d["T"], d["y"], ["v%d" % i for i in range(args.variables)], d["variable_weights"],
+                     d["experiment_start"], d["experiment_end"])
+    t0 = time.perf_counter()
+    spop = PL.ShardedPopulation(data, d["tmin"], d["N_intervals"], d["tmax"])
+    torch.cuda.synchronize()
+    return data, spop, time.perf_counter() - t0
+
+
+def global_prior(P, seed, dev, torch, lo, hi):
+    """A log-prior over all P candidates, a pure function of the global index: every rank generates the
+    same vector and keeps its slice."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed + 7)
+    full = torch.randn(P, dtype=torch.float64, device=dev, generator=g) - math.log(max(P, 1))
+    out = full[lo:hi].clone()
+    del full
+    return out
+
+
+def parity_check(args, torch, D, PL, sw, state, P, N, us):
+    """Sharded == single table (run on EVERY rank, N > 1): this rank builds the whole problem by itself,
+    scores it in one sweep and checks (a) its slice of the sharded table is that slice of the whole table,
+    bit for bit, (b) so are its log-likelihoods, (c) the index every sharded step drew is the index the
+    single-table draw gives for the same u, (d) the exchanged log-sum-exp is the single-table one."""
+    data, pop, _ = build_population(args, 0, torch)
+    if len(pop) != P:
+        return "candidate count differs: %d vs %d" % (len(pop), P)
+    a, b = sw.start, sw.start + sw.n
+    if not torch.equal(pop.packed_truth[a:b], sw.rows):
+        return "slice rows differ from the single-GPU table"
+    dev = D.dev()
+    prior = global_prior(P, args.seed, dev, torch, 0, P)
+    buffers, draw = D.ScoreBuffers(P, N, args.rules + 1), D.DrawBuffers(P)
+    dmask = torch.as_tensor(D.pack_mask(state["mask"]), device=dev)
+    out, status, st = D.score_all_stats(pop.packed_truth, N, state["X"], state["omega"], state["kappa"], SIGMA2,
+                                        mask=dmask, buffers=buffers, log_prior=prior, draw_buffers=draw)
+    D.raise_on_status(status)
+    if not torch.equal(out[a:b], sw.buffers.out[:sw.n]):
+        return "slice log-likelihoods differ from the single-GPU sweep"
+    lse = float(st[0] + torch.log(st[1]))
+    for u, (idx, log_total) in us:
+        want = int(D.draw_index(out, prior, u, stabilise=True, buffers=draw, reuse_tiles=True).item())
+        if idx != want:
+            return "draw differs at u=%r: sharded %d, single %d" % (u, idx, want)
+        if abs(log_total - lse) > 1e-10 * abs(lse):
+            return "log-sum-exp differs: %r vs %r" % (log_total, lse)
+    return "ok"
+
+
 def run_b200(args):
     import torch
-    from mitre_b200 import device as D
+    from mitre_b200 import device as D, parallel as PL
     from mitre_b200._lib import lib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -350,204 +419,238 @@ def run_b200(args):
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
-
-    data, pop, build_marks = build_population(args, rank, torch)
-    N = data.n_subjects
-    P = len(pop)
-    W64 = D.words_for(N)
-    packed = pop.packed_truth
     p = args.rules + 1
+
+    # ---- ONE problem; at N > 1 its candidates are sharded over the ranks (strong scaling) ----
+    pop, build_marks, shard_build_s = None, None, None
+    if world == 1:
+        data, pop, build_marks = build_population(args, 0, torch)
+        N, P = data.n_subjects, len(pop)
+        local_rows, start = pop.packed_truth, 0
+        n_windows = len(pop.windows)
+    else:
+        data, spop, shard_build_s = build_sharded(args, torch)
+        N, P = data.n_subjects, spop.P
+        local_rows, start = spop.local_rows, spop.start
+        n_windows = len(spop.windows)
+        spop.local_population = None
+        torch.cuda.empty_cache()
+    n_local = int(local_rows.shape[0])
+    W64 = D.words_for(N)
+    prior = global_prior(P, args.seed, dev, torch, start, start + n_local)
 
     # identical sweep inputs on every rank (the broadcast of the base system, KBs)
     def row_sampler(rng):
-        return pop._truth_row(int(rng.randint(P)))
+        k = int(rng.randint(n_local))
+        return np.array([(int(local_rows[k, 0]) >> (63 - i)) & 1 for i in range(N)], dtype=bool)
     state = sweep_state(N, args.rules, row_sampler, args.seed + 1) if rank == 0 else None
     if world > 1:
         box = [state]
         dist.broadcast_object_list(box, src=0)
         state = box[0]
 
-    buffers = D.ScoreBuffers(P, N, p)
-    n_small = N * p + 2 * N + W64
-    h_small = torch.empty(n_small, dtype=torch.float64).pin_memory()
-    hs = h_small.numpy()
-    hs[:N * p] = state["X"].reshape(-1)
-    hs[N * p:N * p + N] = state["omega"]
-    hs[N * p + N:N * p + 2 * N] = state["kappa"]
-    hs[N * p + 2 * N:] = D.pack_mask(state["mask"]).view(np.float64)
-    d_small = torch.empty(n_small, dtype=torch.float64, device=dev)
-    d_small.copy_(h_small)
-    dX = d_small[:N * p].view(N, p)
-    dom = d_small[N * p:N * p + N]
-    dka = d_small[N * p + N:N * p + 2 * N]
-    dmask = d_small[N * p + 2 * N:].view(dtype=torch.int64)
-    h_out = torch.empty(P, dtype=torch.float64).pin_memory()
-    draw = D.DrawBuffers(P)
-    gathered = torch.empty(2 * world, dtype=torch.float64, device=dev)
-    empty_rows = packed[:0]
-
-    def sweep():
-        # the timed step is the same at every N: each rank scores its own shard, nothing is exchanged
-        out, _ = D.score_all(packed, N, dX, dom, dka, SIGMA2, mask=dmask, buffers=buffers)
-        return out
-
-    def sweep_with_exchange():
-        # what the sampler's two-stage draw adds (parallel.py): (max, sum-exp) of the shard reduced in the
-        # scoring kernel's epilogue, then a 16-byte-per-rank all-gather
-        out, _, st = D.score_all_stats(packed, N, dX, dom, dka, SIGMA2, mask=dmask, buffers=buffers,
-                                       draw_buffers=draw)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, st)
-        return out
-
-    def setup_only():
-        D.score_all(empty_rows, N, dX, dom, dka, SIGMA2, mask=dmask, buffers=buffers)
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- value: inputs resident in HBM ----
-    for _ in range(max(args.warmup, 3)):
-        sweep()
+    sw = PL.ShardedSweep(local_rows, prior, P, N, start, exchange=args.exchange, max_p=p)
+    rng_u = np.random.RandomState(args.seed + 11)      # the same uniforms on every rank
+
+    def stage():
+        return sw.stage(state["X"], state["omega"], state["kappa"], state["mask"], float(rng_u.rand()))
+
+    # ---- value: the step with its inputs resident in HBM, device-timed ----
+    # step = prepare (base system + tables) -> score the slice + (max, sum-exp) + tile pairs -> chunk sums ->
+    #        exchange of the pairs, owner's draw, index back (one kernel over NVLink peer memory)
+    stage()
+    sw.launch(p, SIGMA2, copies=True)       # inputs into HBM once
+    sw.result()
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        sw.launch(p, SIGMA2, copies=False)
     barrier()
     with ClockSampler(local_rank) as clocks:
-        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        start.record()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
         for _ in range(args.steps):
-            sweep()
-        end.record()
+            sw.launch(p, SIGMA2, copies=False)
+        ev1.record()
         barrier()
-        ms_total = start.elapsed_time(end)
-    ms_step = ms_total / args.steps
-    D.raise_on_status(buffers.status)
+        ms_step = ev0.elapsed_time(ev1) / args.steps
+    if int(sw.buffers.status.item()):
+        raise SystemExit("status flags %d after the timed region" % int(sw.buffers.status.item()))
 
-    # ---- e2e: host buffers in, host buffer out, every step ----
-    def e2e_step():
-        d_small.copy_(h_small, non_blocking=True)
-        out = sweep()
-        h_out.copy_(out, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-
+    # ---- e2e: the same step through ShardedSweep.step -- host inputs in (pinned), index + log-sum-exp back ----
+    drawn = []
     for _ in range(2):
-        e2e_step()
+        stage(); sw.launch(p, SIGMA2); sw.result()
     barrier()
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, min(args.steps, 20))
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        e2e_step()
+        stage()
+        u = float(sw.h_small[-1])
+        sw.launch(p, SIGMA2)
+        drawn.append((u, sw.result()))
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
 
-    # ---- the sampler's own end-to-end sweep (logit_rules.py:1052-1066 with device_draw=True): the P-long
-    # vectors never leave the device; host buffers in, the drawn candidate index and log-total out ----
-    g = torch.Generator(device=dev)
-    g.manual_seed(args.seed + 7)
-    d_prior = torch.randn(P, dtype=torch.float64, device=dev, generator=g) - math.log(max(P, 1))
-    h_idx = torch.empty(1, dtype=torch.int64).pin_memory()
-    h_stats = torch.empty(2, dtype=torch.float64).pin_memory()
+    # ---- the other exchange mode north_star names: all-gather of the log-weights themselves ----
+    dX, dom, dka, dmask = sw._views(p)
+    scorer_out = sw.buffers.out[:n_local]
 
-    def e2e_draw_step(u=0.37):
-        d_small.copy_(h_small, non_blocking=True)
-        out, _, st = D.score_all_stats(packed, N, dX, dom, dka, SIGMA2, mask=dmask, buffers=buffers,
-                                       log_prior=d_prior, draw_buffers=draw)
-        idx = D.draw_index(out, d_prior, u, stabilise=True, buffers=draw, reuse_stats=True)
-        h_idx.copy_(idx, non_blocking=True)
-        h_stats.copy_(st, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-
-    for _ in range(2):
-        e2e_draw_step()
+    def gather_step():
+        D.score_all(local_rows, N, dX, dom, dka, SIGMA2, mask=dmask, buffers=sw.buffers, out=scorer_out)
+        return PL.allgather_loglik(scorer_out, P) if world > 1 else scorer_out
+    gather_step()
     barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_draw_step()
-    barrier()
-    e2e_draw_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
-    del d_prior
-
-    # the variant with the last subjects' table in shared memory, for comparison
-    lib().mitre_set_split_tables(1)
-    split_tables_ms = cuda_time_ms(torch, lambda: D.score_all(packed, N, dX, dom, dka, SIGMA2, mask=dmask,
-                                                              buffers=buffers), max(args.steps, 5))
-    lib().mitre_set_split_tables(0)
-
-    # kernel-only time of the dominant kernel: the step minus the (tiny) setup launch
-    setup_ms = cuda_time_ms(torch, setup_only, 50)
-    kernel_ms = cuda_time_ms(torch, lambda: D.score_all(packed, N, dX, dom, dka, SIGMA2, mask=dmask,
-                                                        buffers=buffers), max(args.steps, 5)) - setup_ms
-
-    # the sampler's exchange step, timed apart from the headline (same CUDA-event recipe)
-    barrier()
-    exch_ms = cuda_time_ms(torch, sweep_with_exchange, max(args.steps, 5))
+    gather_ms = cuda_time_ms(torch, gather_step, max(3, min(args.steps, 10)))
     barrier()
 
-    # ---- max over ranks, totals ----
-    t = torch.tensor([ms_step, e2e_ms, float(P), exch_ms, e2e_draw_ms], dtype=torch.float64, device=dev)
+    # ---- kernel-only times on this rank's slice (CUDA events), for the roofline ----
+    tiny = local_rows[:1024]
+    def stats_only():
+        D.score_all_stats(local_rows, N, dX, dom, dka, SIGMA2, mask=dmask, buffers=sw.buffers, out=scorer_out,
+                          log_prior=prior, draw_buffers=sw.draw)
+    def plain_only():
+        D.score_all(local_rows, N, dX, dom, dka, SIGMA2, mask=dmask, buffers=sw.buffers, out=scorer_out)
+    def prepare_only():
+        lib().mitre_set_large_table_min_rows(0)
+        D.score_all(tiny, N, dX, dom, dka, SIGMA2, mask=dmask, buffers=sw.buffers, out=scorer_out[:1024])
+        lib().mitre_set_large_table_min_rows(4 << 20)
+    reps = max(args.steps, 5)
+    stats_ms = cuda_time_ms(torch, stats_only, reps)
+    plain_ms = cuda_time_ms(torch, plain_only, reps)
+    prepare_ms = cuda_time_ms(torch, prepare_only, 50)
+    lib().mitre_set_dedupe(0)
+    plain_nodedupe_ms = cuda_time_ms(torch, plain_only, reps)
+    lib().mitre_set_dedupe(1)
+    dup_frac = float((local_rows[1:, 0] == local_rows[:-1, 0]).double().mean()) if n_local > 1 else 0.0
+    barrier()
+
+    # ---- parity of the sharded path against the single-GPU path, on every rank ----
+    check = "skipped"
+    if args.check == "on" or (args.check == "auto" and world > 1):
+        check = parity_check(args, torch, D, PL, sw, state, P, N, drawn)
+    # max over ranks / agreement
+    t = torch.tensor([ms_step, e2e_ms, gather_ms, 0.0 if check in ("ok", "skipped") else 1.0], dtype=torch.float64,
+                     device=dev)
     if world > 1:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms_step, e2e_ms, P_total, exch_ms = float(tmax[0]), float(tmax[1]), float(tsum[2]), float(tmax[3])
-        e2e_draw_ms = float(tmax[4])
-    else:
-        P_total = float(P)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        idx_t = torch.tensor([d[1][0] for d in drawn], dtype=torch.int64, device=dev)
+        lo_t, hi_t = idx_t.clone(), idx_t.clone()
+        dist.all_reduce(lo_t, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi_t, op=dist.ReduceOp.MAX)
+        if not torch.equal(lo_t, hi_t):
+            check = "ranks disagree on the drawn index"
+            t[3] = 1.0
+    ms_step, e2e_ms, gather_ms = float(t[0]), float(t[1]), float(t[2])
+    if float(t[3]) != 0.0 and check in ("ok", "skipped"):
+        check = "failed on another rank"
 
     if rank == 0:
         peak, peak_src = peaks()
-        achieved = 16.0 * P / (kernel_ms * 1e-3) / 1e9
-        det_bytes = detector_bytes(pop, data)
-        det_ms = build_marks.get("detector_kernel_ms", build_marks["values"] + build_marks["thresholds_rows"])
+        # the candidate kernel's launch time INCLUDING its prepare launch (base system + tables, ~10 us): the
+        # two are timed together because a back-to-back loop of the small launch alone is host-bound
+        kern_stats_ms = stats_ms
+        kern_plain_ms = plain_ms
+        achieved = 24.0 * n_local / (kern_stats_ms * 1e-3) / 1e9
         line = {
-            "metric": METRIC, "value": P_total / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "metric": METRIC, "value": P / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": warm, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": "S5-primitive-sweep", "subjects": N, "variables_per_gpu": args.variables,
-                       "windows": len(pop.windows), "candidates_per_gpu": int(P),
-                       "base_columns_p": p, "l2_policy": "inputs (3.3 GB/GPU) exceed the 126 MB L2",
-                       "exchange": "none: candidate shards are independent (see sampler_exchange)"},
-            "sampler_exchange": {"what": "scoring with the (max, sum-exp) reduction fused into the epilogue + "
-                                         "all-gather of one 16-byte pair per rank (two-stage draw)",
-                                 "ms_per_step": exch_ms, "value": P_total / (exch_ms * 1e-3), "unit": UNIT,
-                                 "bytes_on_wire_per_rank": 16 if world > 1 else 0},
-            "e2e": {"value": P_total / (e2e_ms * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": int(n_small * 8), "d2h_bytes_per_step": int(P * 8),
-                    "ms_per_step": e2e_ms},
-            "e2e_sampler_sweep": {"what": "host inputs -> scoring + log-prior + (max, sum-exp) -> on-device draw -> "
-                                          "drawn index and stats back to pinned host memory (the sampler's "
-                                          "device_draw sweep; the P-long vectors stay in HBM)",
-                                  "value": P_total / (e2e_draw_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_draw_ms,
-                                  "h2d_bytes_per_step": int(n_small * 8), "d2h_bytes_per_step": 24},
-            "gpu_launches": int(args.steps * 3),
+            "config": {"workload": "S5-primitive-sweep", "subjects": N, "variables": args.variables,
+                       "windows": n_windows, "candidates": int(P), "candidates_per_gpu": n_local,
+                       "base_columns_p": p,
+                       "step": "one detector-update sweep of ONE problem: base system + tables, log-likelihood of "
+                               "every candidate of the rank's slice, (max, sum-exp) of likelihood + log-prior, "
+                               "exchange, proposal draw, index on every rank",
+                       "exchange": ("p2p: each rank stores its 16-byte (max, sum-exp) pair into every peer's memory and "
+                                    "the owner of the marker stores the drawn index back, inside one kernel over "
+                                    "NVLink (CUDA IPC peer memory, no NCCL in the step)" if args.exchange == "p2p" else
+                                    "nccl: all-gather of the 16-byte (max, sum-exp) pairs + all-reduce(MAX) of the index"),
+                       "l2_policy": "per-GPU inputs exceed the 126 MB L2 at N <= 8 (>= 0.88 GB per step)",
+                       "duplicate_rows_fraction": dup_frac},
+            "parity_check": check,
+            "e2e": {"value": P / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(sw.h_small.numel() * 8), "d2h_bytes_per_step": 32,
+                    "what": "ShardedSweep.step: host (pinned) sweep inputs -> device, the step above, drawn index "
+                            "+ log-sum-exp + status back to pinned host memory, every step"},
+            "allgather_loglik": {"what": "plain scoring of the slice + NCCL all-gather of the fp64 log-weights so that "
+                                         "every rank holds likelihoods[P] (the reference's data flow, "
+                                         "logit_rules.py:861-863)",
+                                 "ms_per_step": gather_ms, "value": P / (gather_ms * 1e-3), "unit": UNIT,
+                                 "bytes_gathered_per_rank": int(8 * P) if world > 1 else 0},
+            "gpu_launches": int(args.steps * 4),
             "clocks": clocks.summary(),
-            "roofline": {"kernel": "score_w1g4_kernel", "step_ms_with_last_table_in_smem": split_tables_ms, "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                         "traffic": ncu_traffic_per_launch(P), "kernel_ms": kernel_ms,
-                         "setup_ms": setup_ms, "algorithmic_bytes_per_candidate": 16,
-                         "fp64": fp64_roofline(D, P, kernel_ms)},
-            "detector_eval": {"groups": int(pop._G), "algorithmic_bytes": det_bytes,
-                              "ms": det_ms, "achieved_gbs": det_bytes / (det_ms * 1e-3) / 1e9,
-                              "frac_of_hbm_peak": det_bytes / (det_ms * 1e-3) / 1e9 / peak,
-                              "kernel": build_marks.get("detector_kernel", "phase-by-phase kernels + host"),
-                              "single_fused_kernel_ms": build_marks.get("detector_single_kernel_ms"),
-                              "host_phase_ms": {"values": build_marks["values"],
-                                                "thresholds_rows": build_marks["thresholds_rows"],
-                                                "lexsort": build_marks["lexsort"]},
-                              "build_wall_s": build_marks["wall_s"]},
+            "roofline": {"kernel": "score_w1d_kernel<6,stats> (the step's candidate kernel)", "bound": "hbm",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "kernel_ms": kern_stats_ms, "prepare_launch_ms_upper_bound": prepare_ms,
+                         "algorithmic_bytes_per_candidate": 24,
+                         "traffic": ncu_traffic_per_launch(n_local, "stats"),
+                         "traffic_source": "profiles/score_w1d_traffic.json (ncu --set full capture of this kernel at "
+                                           "the full S5 size, bytes per candidate) x candidates of this launch",
+                         "plain_kernel": {"kernel": "score_w1d_kernel<6,plain> (mitre_score_all)", "kernel_ms": kern_plain_ms,
+                                          "algorithmic_bytes_per_candidate": 16,
+                                          "achieved": 16.0 * n_local / (kern_plain_ms * 1e-3) / 1e9,
+                                          "frac": 16.0 * n_local / (kern_plain_ms * 1e-3) / 1e9 / peak,
+                                          "traffic": ncu_traffic_per_launch(n_local, "plain"),
+                                          "without_duplicate_awareness_ms": plain_nodedupe_ms},
+                         "fp64": fp64_roofline(D, n_local, kern_stats_ms)},
         }
+        if shard_build_s is not None:
+            line["sharded_build_s"] = shard_build_s
+        if world == 1:
+            det_bytes = detector_bytes(pop, data)
+            det_ms = build_marks.get("detector_kernel_ms", build_marks["values"] + build_marks["thresholds_rows"])
+            line["detector_eval"] = {
+                "groups": int(pop._G), "algorithmic_bytes": det_bytes, "ms": det_ms,
+                "achieved_gbs": det_bytes / (det_ms * 1e-3) / 1e9,
+                "frac_of_hbm_peak": det_bytes / (det_ms * 1e-3) / 1e9 / peak,
+                "kernel": build_marks.get("detector_kernel", "phase-by-phase kernels + host"),
+                "slope_groups_flagged": build_marks.get("slope_flagged"),
+                "host_phase_ms": {"values": build_marks["values"], "thresholds_rows": build_marks["thresholds_rows"],
+                                  "lexsort": build_marks["lexsort"]},
+                "build_wall_s": build_marks["wall_s"]}
+            line["e2e_full_vector"] = e2e_full_vector(args, torch, D, pop, state, N, P)
+            if not args.no_cpu_baseline:
+                line["cpu_baseline"] = cpu_baseline(args, pop, state, N, P, torch, D)
+        print_line = line
+    sw.close()
+    if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args, pop, state, N, P, torch, D)
-            del pop, packed
+            del pop, local_rows, sw, prior
             torch.cuda.empty_cache()
-            line["mcmc"] = mcmc_samples_per_sec(args)
-        print(json.dumps(line))
+            print_line["mcmc"] = mcmc_samples_per_sec(args)
+        print(json.dumps(print_line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def e2e_full_vector(args, torch, D, pop, state, N, P):
+    """The reference-facing call a user of the drop-in makes, LogisticRuleModel.likelihoods_of_all_options:
+    host inputs in, ALL P log-likelihoods back in host memory (2.35 GB per sweep over PCIe)."""
+    from mitre_b200 import logit_rules as LR, rules as R
+    model = LR.LogisticRuleModel.__new__(LR.LogisticRuleModel)
+    model.data, model.rule_population = pop.data, pop
+    model.prior_coefficient_variance = SIGMA2
+    model._device_state = None
+    # the public call takes a rule list + position; drive it with the staged X / mask of the bench state
+    model._sweep_inputs = lambda rl, i, j: (state["X"], state["mask"])
+    for _ in range(2):
+        model.likelihoods_of_all_options(None, state["omega"], 0, 0)
+    steps = 5
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out = model.likelihoods_of_all_options(None, state["omega"], 0, 0)
+    ms = 1e3 * (time.perf_counter() - t0) / steps
+    return {"what": "LogisticRuleModel.likelihoods_of_all_options: pinned host inputs -> device, sweep, float64[P] "
+                    "back to host memory", "value": P / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+            "d2h_bytes_per_step": int(8 * P), "finite": bool(np.isfinite(out[:1000]).all())}
 
 
 def cpu_baseline(args, pop, state, N, P, torch, D):

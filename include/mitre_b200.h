@@ -333,9 +333,9 @@ int mitre_draw_from_tiles(void *stream, const double *a, const double *b, int64_
  *   mitre_sharded_select  the same selection with the exchanges left to the caller (NCCL): `gathered`
  *                         float64[world, 2] = all ranks' pairs; non-owners write index -1 (all-reduce
  *                         MAX of index_out afterwards).
- * `step` is a DEVICE float64[2] = (u, seq): the uniform draw and the step's sequence number (an integer
- * >= 1, strictly increasing, the same on all ranks for the same step) -- device-resident so that the
- * whole step can be replayed as a CUDA graph with only a host->device copy of these 16 bytes changing.
+ * `u` (the uniform draw) and `seq` are DEVICE float64[1]: seq is the step's sequence number, an integer
+ * >= 1 that the caller initialises to the same value on all ranks and the kernel itself advances by one
+ * per launch -- device-resident so that the whole step can be replayed as a CUDA graph.
  * mitre_comm_create allocates the slot buffer other ranks write into and returns its 64-byte CUDA IPC
  * handle in handle_out_host; mitre_comm_connect takes all ranks' handles (world x 64 bytes, rank order).
  * world <= 16.  world == 1 works without IPC (a single-GPU run of the same code path).
@@ -345,10 +345,10 @@ int mitre_comm_connect(void *comm, const void *all_handles_host);
 int mitre_comm_destroy(void *comm);
 int mitre_sharded_chunk_sums(void *stream, int64_t P_local, const double *local_stats, void *workspace,
                              size_t workspace_bytes);
-int mitre_sharded_draw(void *stream, void *comm, const double *step, const double *local_stats,
+int mitre_sharded_draw(void *stream, void *comm, const double *u, double *seq, const double *local_stats,
                        const double *a, const double *b, int64_t P_local, int64_t start, void *workspace,
                        size_t workspace_bytes, int64_t *index_out, double *stats_out, int32_t *status);
-int mitre_sharded_select(void *stream, int world, int rank, const double *step, const double *gathered,
+int mitre_sharded_select(void *stream, int world, int rank, const double *u, const double *gathered,
                          const double *a, const double *b, int64_t P_local, int64_t start, void *workspace,
                          size_t workspace_bytes, int64_t *index_out, double *stats_out);
 

@@ -90,7 +90,7 @@ SIGNATURES = {
     "mitre_comm_connect": (c_int, [c_void_p, c_void_p]),
     "mitre_comm_destroy": (c_int, [c_void_p]),
     "mitre_sharded_chunk_sums": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_size_t]),
-    "mitre_sharded_draw": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+    "mitre_sharded_draw": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_i64, c_i64, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "mitre_sharded_select": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64,
                                      c_void_p, c_size_t, c_void_p, c_void_p]),

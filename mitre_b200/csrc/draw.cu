@@ -148,9 +148,47 @@ draw_chunk_sums_kernel(const double *__restrict__ pairs, int64_t ntiles, const d
 // Shared scratch of select_in_table (one CTA of 256 threads).
 struct SelectSmem {
     long long sel;
-    double before, marker;
+    double before, marker, total;
     double run[256];
 };
+
+// CTA-wide (256 threads): over the `used` leading values of sm.run, the first k whose inclusive prefix
+// before + run[0] + ... + run[k] is NOT < marker (the last one if none is), and the prefix preceding it.
+// Fixed-shape parallel scan (warp shuffles, then the 8 warp totals): deterministic, and the prefix it
+// returns is the one the decision was made with.  total_out (optional): before + everything.
+__device__ void select_run(SelectSmem &sm, int used, double before, double marker, double *total_out)
+{
+    __shared__ double wtot[8];
+    __shared__ int s_first[8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const double x = (int)threadIdx.x < used ? sm.run[threadIdx.x] : 0.0;
+    double inc = x;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const double y = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += y;
+    }
+    if (lane == 31) wtot[wid] = inc;
+    __syncthreads();
+    double base = before;
+    for (int w = 0; w < wid; ++w) base += wtot[w];
+    const double incl = base + inc;                     // inclusive prefix at this thread
+    const double prev = __shfl_up_sync(0xffffffffu, incl, 1);
+    const double excl = lane ? prev : base;             // the previous thread's inclusive prefix, bit for bit
+    if (total_out && threadIdx.x == 255) *total_out = incl;
+    const bool hit = (int)threadIdx.x < used && !(incl < marker);
+    const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) s_first[wid] = ballot ? (wid * 32 + __ffs(ballot) - 1) : -1;
+    __syncthreads();
+    int sel = -1;
+    for (int w = 0; w < 8 && sel < 0; ++w) sel = s_first[w];
+    if (sel < 0) sel = used - 1;
+    if ((int)threadIdx.x == sel) {
+        sm.sel = sel;
+        sm.before = excl;
+    }
+    __syncthreads();
+}
 
 // CTA-wide selection (256 threads, all must call).  The table's candidates carry masses
 // scale * exp(w - shift_local) (chunk sums and tile pairs are relative to shift_local; scale rescales
@@ -173,38 +211,25 @@ __device__ int64_t select_in_table(const double *__restrict__ a, const double *_
     double before = before0;
     bool have_marker = false;
     __syncthreads();
+    if (threadIdx.x == 0) sm.marker = marker_in;
     while (hi - lo > 1 || !have_marker) {
         const int64_t n = hi - lo;
         const int64_t c = (n + 255) / 256;
         const int64_t i0 = lo + (int64_t)threadIdx.x * c;
         const int64_t i1 = (i0 + c < hi) ? i0 + c : hi;
         double sum = 0.0;
-        for (int64_t i = i0; i < i1; ++i) sum += chunk_sums[i];
+#pragma unroll 4
+        for (int64_t i = i0; i < i1; ++i) sum += __ldg(chunk_sums + i);
         sm.run[threadIdx.x] = sum * scale;
         __syncthreads();
-        if (threadIdx.x == 0) {
-            if (!have_marker) {
-                if (marker_in < 0.0) {
-                    double total = before0;
-                    for (int k = 0; k < 256; ++k) total += sm.run[k];
-                    sm.marker = u * total;
-                } else {
-                    sm.marker = marker_in;
-                }
-            }
-            const double marker = sm.marker;
-            const int used = (int)((n + c - 1) / c);      // runs that hold at least one chunk
-            double run = before;
-            int sel = used - 1;
-            for (int k = 0; k < used; ++k) {
-                const double nxt = run + sm.run[k];
-                if (!(nxt < marker) || k == used - 1) { sel = k; break; }
-                run = nxt;
-            }
-            sm.sel = sel;
-            sm.before = run;
+        const int used = (int)((n + c - 1) / c);      // runs that hold at least one chunk
+        if (!have_marker && marker_in < 0.0) {
+            // single table: marker = u * total, total by the same scan (marker = +inf selects nothing)
+            select_run(sm, used, before, INFINITY, &sm.total);
+            if (threadIdx.x == 0) sm.marker = u * sm.total;
+            __syncthreads();
         }
-        __syncthreads();
+        select_run(sm, used, before, sm.marker, nullptr);
         have_marker = true;
         const int64_t nlo = lo + (int64_t)sm.sel * c;
         hi = (nlo + c < hi) ? nlo + c : hi;
@@ -219,20 +244,12 @@ __device__ int64_t select_in_table(const double *__restrict__ a, const double *_
         sm.run[threadIdx.x] = t < ntiles ? tile_term(pairs, t, shift_local) * scale : 0.0;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    {
         const int used = (int)((ntiles - t0 < kDrawChunkTiles) ? (ntiles - t0) : kDrawChunkTiles);
-        const double marker = sm.marker;
-        double run = before;
-        int sel = used - 1;
-        for (int k = 0; k < used; ++k) {
-            const double nxt = run + sm.run[k];
-            if (!(nxt < marker) || k == used - 1) { sel = k; break; }
-            run = nxt;
-        }
-        sm.sel = t0 + sel;
-        sm.before = run;
+        select_run(sm, used, before, sm.marker, nullptr);
+        if (threadIdx.x == 0) sm.sel += t0;
+        __syncthreads();
     }
-    __syncthreads();
     const int64_t k0 = (int64_t)sm.sel * kDrawTileRows;
     const double tile_before = sm.before;
     __syncthreads();
@@ -381,7 +398,8 @@ __device__ DrawPlan make_plan(const double *m, const double *s, int world, doubl
 // out[0] = global index (as double bits of an int64 would not fit: out_index is separate),
 // out_stats[0] = M, out_stats[1] = total (log-sum-exp over all ranks = M + log total)
 __global__ void __launch_bounds__(256)
-sharded_draw_kernel(CommView cv, const double *__restrict__ step, const double *__restrict__ local_stats,
+sharded_draw_kernel(CommView cv, const double *__restrict__ u_ptr, double *__restrict__ seq_ptr,
+                    const double *__restrict__ local_stats,
                     const double *__restrict__ a, const double *__restrict__ b, int64_t P_local,
                     int64_t start, const double *__restrict__ pairs, const double *__restrict__ chunk_sums,
                     int64_t *__restrict__ index_out, double *__restrict__ stats_out, int32_t *status)
@@ -392,8 +410,8 @@ sharded_draw_kernel(CommView cv, const double *__restrict__ step, const double *
     __shared__ int s_fail;
     const int world = cv.world, rank = cv.rank;
     CommLayout *mine = cv.peer[rank];
-    const double u = step[0];
-    const unsigned long long seq = (unsigned long long)step[1];
+    const double u = u_ptr[0];
+    const unsigned long long seq = (unsigned long long)seq_ptr[0];
     const int par = (int)(seq & 1);
     if (threadIdx.x == 0) s_fail = 0;
     __syncthreads();
@@ -445,6 +463,7 @@ sharded_draw_kernel(CommView cv, const double *__restrict__ step, const double *
             *index_out = *reinterpret_cast<const volatile long long *>(&mine->result[par].index);
             stats_out[0] = plan.M;
             stats_out[1] = plan.total;
+            seq_ptr[0] = (double)(seq + 1);      // the next launch is the next step, on every rank
         } else {
             if (status) atomicOr(reinterpret_cast<unsigned int *>(status), MITRE_STATUS_COMM_TIMEOUT);
             *index_out = -1;
@@ -455,7 +474,7 @@ sharded_draw_kernel(CommView cv, const double *__restrict__ step, const double *
 // The same step with the exchanges done by the caller (NCCL all-gather of the pairs before, all-reduce
 // MAX of index_out after): gathered = float64[world, 2].  Non-owners write index -1.
 __global__ void __launch_bounds__(256)
-sharded_select_kernel(int world, int rank, const double *__restrict__ step, const double *__restrict__ gathered,
+sharded_select_kernel(int world, int rank, const double *__restrict__ u_ptr, const double *__restrict__ gathered,
                       const double *__restrict__ a, const double *__restrict__ b, int64_t P_local, int64_t start,
                       const double *__restrict__ pairs, const double *__restrict__ chunk_sums,
                       int64_t *__restrict__ index_out, double *__restrict__ stats_out)
@@ -463,7 +482,7 @@ sharded_select_kernel(int world, int rank, const double *__restrict__ step, cons
     __shared__ SelectSmem sm;
     __shared__ double s_m[kCommMaxWorld], s_s[kCommMaxWorld];
     __shared__ DrawPlan plan;
-    const double u = step[0];
+    const double u = u_ptr[0];
     if (threadIdx.x < world) {
         s_m[threadIdx.x] = gathered[2 * threadIdx.x];
         s_s[threadIdx.x] = gathered[2 * threadIdx.x + 1];
@@ -674,13 +693,13 @@ extern "C" int mitre_sharded_chunk_sums(void *stream, int64_t P_local, const dou
     return MITRE_OK;
 }
 
-extern "C" int mitre_sharded_draw(void *stream, void *comm, const double *step, const double *local_stats,
+extern "C" int mitre_sharded_draw(void *stream, void *comm, const double *u, double *seq, const double *local_stats,
                                   const double *a, const double *b, int64_t P_local, int64_t start,
                                   void *workspace, size_t workspace_bytes, int64_t *index_out, double *stats_out,
                                   int32_t *status)
 {
     Comm *c = static_cast<Comm *>(comm);
-    if (!c || !step || !local_stats || !index_out || !stats_out || P_local < 0) return MITRE_ERR_INVALID;
+    if (!c || !u || !seq || !local_stats || !index_out || !stats_out || P_local < 0) return MITRE_ERR_INVALID;
     if (P_local > 0 && (!a || !workspace || workspace_bytes < mitre_draw_workspace_bytes(P_local)))
         return MITRE_ERR_WORKSPACE;
     CommView cv;
@@ -688,7 +707,7 @@ extern "C" int mitre_sharded_draw(void *stream, void *comm, const double *step, 
     cv.rank = c->rank;
     for (int r = 0; r < kCommMaxWorld; ++r) cv.peer[r] = r < c->world ? c->peer[r] : nullptr;
     const double *ws = static_cast<const double *>(workspace);
-    sharded_draw_kernel<<<1, 256, 0, as_stream(stream)>>>(cv, step, local_stats, a, b, P_local, start,
+    sharded_draw_kernel<<<1, 256, 0, as_stream(stream)>>>(cv, u, seq, local_stats, a, b, P_local, start,
                                                           ws ? ws + draw_off_pairs() : nullptr,
                                                           ws ? ws + draw_off_chunks(P_local) : nullptr, index_out,
                                                           stats_out, status);
@@ -696,17 +715,17 @@ extern "C" int mitre_sharded_draw(void *stream, void *comm, const double *step, 
     return MITRE_OK;
 }
 
-extern "C" int mitre_sharded_select(void *stream, int world, int rank, const double *step, const double *gathered,
+extern "C" int mitre_sharded_select(void *stream, int world, int rank, const double *u, const double *gathered,
                                     const double *a, const double *b, int64_t P_local, int64_t start,
                                     void *workspace, size_t workspace_bytes, int64_t *index_out, double *stats_out)
 {
-    if (world < 1 || world > kCommMaxWorld || rank < 0 || rank >= world || !step || !gathered || !index_out || !stats_out ||
+    if (world < 1 || world > kCommMaxWorld || rank < 0 || rank >= world || !u || !gathered || !index_out || !stats_out ||
         P_local < 0)
         return MITRE_ERR_INVALID;
     if (P_local > 0 && (!a || !workspace || workspace_bytes < mitre_draw_workspace_bytes(P_local)))
         return MITRE_ERR_WORKSPACE;
     const double *ws = static_cast<const double *>(workspace);
-    sharded_select_kernel<<<1, 256, 0, as_stream(stream)>>>(world, rank, step, gathered, a, b, P_local, start,
+    sharded_select_kernel<<<1, 256, 0, as_stream(stream)>>>(world, rank, u, gathered, a, b, P_local, start,
                                                             ws ? ws + draw_off_pairs() : nullptr,
                                                             ws ? ws + draw_off_chunks(P_local) : nullptr, index_out,
                                                             stats_out);

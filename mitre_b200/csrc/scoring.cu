@@ -289,11 +289,16 @@ score_prepare16_kernel(const double *__restrict__ X, const double *__restrict__ 
     __shared__ double sb[MITRE_MAX_P];
     __shared__ double sred[256];
     __shared__ int s_ok;
-    extern __shared__ double sq[];                  // [N][EP]
+    extern __shared__ double sq[];                  // [N][EP], then the staged inputs X[N][p], omega[N], kappa[N]
     const int EP = ep_for(p);
-    const double C0 = base_system(X, p, omega, kappa, N, p, sigma2, sA, sb, sred, &s_ok);
+    // stage the sweep inputs once (one round of global latency instead of one per loop iteration)
+    double *sX = sq + (size_t)N * EP, *som = sX + (size_t)N * p, *ska = som + N;
+    for (int i = threadIdx.x; i < N * p; i += blockDim.x) sX[i] = X[i];
+    for (int i = threadIdx.x; i < N; i += blockDim.x) { som[i] = omega[i]; ska[i] = kappa[i]; }
+    __syncthreads();
+    const double C0 = base_system(sX, p, som, ska, N, p, sigma2, sA, sb, sred, &s_ok);
     for (int i = threadIdx.x; i < N; i += blockDim.x)
-        subject_vector(X, omega, kappa, mask, i, p, EP, sA, sb, s_ok, sq + (size_t)i * EP);
+        subject_vector(sX, som, ska, mask, i, p, EP, sA, sb, s_ok, sq + (size_t)i * EP);
     __syncthreads();
     if (blockIdx.x == 0) {
         if (threadIdx.x == 0) {
@@ -1386,7 +1391,7 @@ __device__ __forceinline__ void transpose4(double2 (&a)[4], int j)
 }
 
 template <int EP, bool STATS, bool COOP>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, STATS ? 3 : 4)
 score_w1d_kernel(const uint64_t *__restrict__ rows, int64_t P, const double *__restrict__ ws, int N,
                  const double *__restrict__ tables, double *__restrict__ out, int32_t *status,
                  const double *__restrict__ log_prior, double *__restrict__ stat_partials,
@@ -1456,52 +1461,14 @@ score_w1d_kernel(const uint64_t *__restrict__ rows, int64_t P, const double *__r
             if (lane >= off) incl += y;
         }
         const int D = __shfl_sync(0xffffffffu, incl, 31);
-        int i0 = incl - c + h0 - 1, i1 = i0 + h1, i2 = i1 + h2, i3 = i2 + h3;
+        const int i0 = incl - c + h0 - 1, i1 = i0 + h1, i2 = i1 + h2, i3 = i2 + h3;
         __syncwarp();                                   // the previous tile's read-back is over
         if (h0) sb[i0] = r[0];
         if (h1) sb[i1] = r[1];
         if (h2) sb[i2] = r[2];
         if (h3) sb[i3] = r[3];
         __syncwarp();
-        if (!COOP && D > 64) {
-            // few duplicates in this tile: no compaction; every lane scores its own four rows, the leading
-            // lookups shared between them (as score_w1g4_kernel)
-            const uint64_t diff = (r[0] ^ r[1]) | (r[0] ^ r[2]) | (r[0] ^ r[3]);
-            const bool share = lead_bits == 0 || (diff >> (64 - lead_bits)) == 0;
-            double prefix[EP];
-#pragma unroll
-            for (int e = 0; e < EP; ++e) prefix[e] = 0.0;
-            if (share) {
-#pragma unroll
-                for (int tt = 0; tt < 3; ++tt)
-                    if (tt < nt - 1)
-                        lut_add_g<EP>(prefix, reinterpret_cast<const double *>(tb[tt]) +
-                                                  (size_t)((unsigned)(r[0] >> shift[tt]) & msk[tt]) * EP);
-            }
-            double v[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                double acc[EP];
-#pragma unroll
-                for (int e = 0; e < EP; ++e) acc[e] = prefix[e];
-                if (!share) {
-#pragma unroll
-                    for (int tt = 0; tt < 3; ++tt)
-                        if (tt < nt - 1)
-                            lut_add_g<EP>(acc, reinterpret_cast<const double *>(tb[tt]) +
-                                                   (size_t)((unsigned)(r[i] >> shift[tt]) & msk[tt]) * EP);
-                }
-                lut_add_g<EP>(acc, reinterpret_cast<const double *>(tb[nt - 1]) +
-                                       (size_t)((unsigned)(r[i] >> last_shift) & msk[nt - 1]) * EP);
-                v[i] = finish_tab<EP>(acc, inv_s2, C1, logtab, bad);
-            }
-            // park the values where the common read-back below finds them
-            i0 = 4 * lane; i1 = i0 + 1; i2 = i0 + 2; i3 = i0 + 3;
-            sb[4 * lane + 0] = (unsigned long long)__double_as_longlong(v[0]);
-            sb[4 * lane + 1] = (unsigned long long)__double_as_longlong(v[1]);
-            sb[4 * lane + 2] = (unsigned long long)__double_as_longlong(v[2]);
-            sb[4 * lane + 3] = (unsigned long long)__double_as_longlong(v[3]);
-        } else if (!COOP) {
+        if (!COOP) {
             // one lane per distinct row: the whole (packed, EP-double) entry of every table
             for (int jj = lane; jj < D; jj += 32) {
                 const uint64_t rr = sb[jj];
@@ -2117,7 +2084,7 @@ extern "C" int mitre_score_all_stats(void *stream, const uint64_t *packed_truth,
         dedupe_eligible(EPr, P, packed_truth, out, log_prior, tile_pairs)) {
         // base system + tables in one launch
         const int stride = g_dedupe == 2 ? kCoopStride : EPr;
-        score_prepare16_kernel<<<2 * sm_count(), 256, sizeof(double) * (size_t)N * EPr, st>>>(
+        score_prepare16_kernel<<<2 * sm_count(), 256, sizeof(double) * ((size_t)N * (EPr + p + 2)), st>>>(
             X, omega, kappa, mask, N, p, sigma2, ws, status, stride, tables16_ptr(ws, N, EPr));
     } else {
         score_setup_kernel<<<1, 256, 0, st>>>(X, omega, kappa, mask, N, p, sigma2, ws, status);

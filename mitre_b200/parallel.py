@@ -204,18 +204,17 @@ class ShardedSweep:
         self.buffers = D.ScoreBuffers(max(self.n, 1), self.N, self.max_p)
         self.draw = D.DrawBuffers(max(self.n, 1))
         n_small = self.N * self.max_p + 2 * self.N + self.W64
-        self.h_small = torch.zeros(n_small + 2, dtype=torch.float64).pin_memory()   # ..., u, seq
-        self.d_small = torch.zeros(n_small + 2, dtype=torch.float64, device=dev)
-        self.d_step = self.d_small[n_small:]
+        self.h_small = torch.zeros(n_small + 1, dtype=torch.float64).pin_memory()   # X, omega, kappa, mask, u
+        self.d_small = torch.zeros(n_small + 1, dtype=torch.float64, device=dev)
+        self.d_u = self.d_small[n_small:]
+        self.d_seq = torch.ones(1, dtype=torch.float64, device=dev)   # advanced by the draw kernel itself
         self.d_res = torch.zeros(4, dtype=torch.float64, device=dev)    # index (int64 bits), M, total, status
         self.h_res = torch.zeros(4, dtype=torch.float64).pin_memory()
         self._empty_stats = torch.tensor([-np.inf, 0.0], dtype=torch.float64, device=dev)
         self.gathered = torch.zeros(2 * self.ws, dtype=torch.float64, device=dev)
-        self.seq = 0
         self.exchange = exchange
         self.comm = None
-        self._graph = None
-        self._graph_p = None
+        self._graphs = {}
         self.use_graph = use_graph
         if exchange == 'p2p':
             comm = ctypes.c_void_p()
@@ -254,9 +253,7 @@ class ShardedSweep:
         h[o:o + N] = omega
         h[o + N:o + 2 * N] = kappa
         h[o + 2 * N:o + 2 * N + W64] = self.D.pack_mask(mask_bool).view(np.float64)
-        self.seq += 1
         h[o + 2 * N + W64] = u
-        h[o + 2 * N + W64 + 1] = float(self.seq)
         return p
 
     def _views(self, p):
@@ -266,11 +263,12 @@ class ShardedSweep:
                 d[o + 2 * N:o + 2 * N + W64].view(dtype=torch.int64))
 
     # -- device work of one step (stream-ordered, no synchronisation) ----------------------------------
-    def _launch(self, p, sigma2):
+    def _launch(self, p, sigma2, copies=True):
         from ._lib import lib, check
         D = self.D
         _p, _s = D._p, D._stream
-        self.d_small.copy_(self.h_small, non_blocking=True)
+        if copies:
+            self.d_small.copy_(self.h_small, non_blocking=True)
         dX, dom, dka, dmask = self._views(p)
         out = self.buffers.out[:self.n]
         if self.n:
@@ -283,45 +281,44 @@ class ShardedSweep:
               "mitre_sharded_chunk_sums")
         idx_out = self.d_res[:1].view(torch.int64)
         if self.exchange == 'p2p':
-            check(lib().mitre_sharded_draw(_s(), self.comm, _p(self.d_step), _p(self.draw.stats), _p(out),
-                                           _p(self.prior), self.n, self.start, _p(wsb), wsb.numel(), _p(idx_out),
-                                           _p(self.d_res[1:3]), _p(self.buffers.status)), "mitre_sharded_draw")
+            check(lib().mitre_sharded_draw(_s(), self.comm, _p(self.d_u), _p(self.d_seq), _p(self.draw.stats),
+                                           _p(out), _p(self.prior), self.n, self.start, _p(wsb), wsb.numel(),
+                                           _p(idx_out), _p(self.d_res[1:3]), _p(self.buffers.status)),
+                  "mitre_sharded_draw")
         else:
             if self.ws > 1:
                 dist.all_gather_into_tensor(self.gathered, self.draw.stats, group=self.group)
             else:
                 self.gathered.copy_(self.draw.stats)
-            check(lib().mitre_sharded_select(_s(), self.ws, self.rank, _p(self.d_step), _p(self.gathered), _p(out),
+            check(lib().mitre_sharded_select(_s(), self.ws, self.rank, _p(self.d_u), _p(self.gathered), _p(out),
                                              _p(self.prior), self.n, self.start, _p(wsb), wsb.numel(), _p(idx_out),
                                              _p(self.d_res[1:3])), "mitre_sharded_select")
             if self.ws > 1:
                 dist.all_reduce(idx_out, op=dist.ReduceOp.MAX, group=self.group)
-        self.d_res[3:].copy_(self.buffers.status)      # status word rides along with the result
-        self.h_res.copy_(self.d_res, non_blocking=True)
+        if copies:
+            self.d_res[3:].copy_(self.buffers.status)      # status word rides along with the result
+            self.h_res.copy_(self.d_res, non_blocking=True)
         return out
 
-    def launch(self, p, sigma2):
-        """Enqueue one step (inputs already staged).  p2p: replayed as a CUDA graph after the first call."""
+    def launch(self, p, sigma2, copies=True):
+        """Enqueue one step.  copies=True: the step's inputs come from the pinned staging buffer (stage())
+        and the result goes back to pinned memory; copies=False: inputs as they are in HBM, result left on
+        the device.  p2p: captured once per (p, sigma2, copies) as a CUDA graph and replayed."""
         if self.exchange == 'p2p' and self.use_graph:
-            if self._graph is None or self._graph_p != (p, float(sigma2)):
-                # warm-up outside capture (lazy module loading, attribute setting), then capture
-                self._launch(p, sigma2)
+            key = (p, float(sigma2), bool(copies))
+            g = self._graphs.get(key)
+            if g is None:
+                # one plain run (module loading, function attributes), then capture; every rank takes this
+                # branch on the same call, so the extra step keeps the sequence numbers aligned
+                self._launch(p, sigma2, copies)
                 torch.cuda.current_stream().synchronize()
-                self._redo_seq()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    self._launch(p, sigma2)
-                self._graph, self._graph_p = g, (p, float(sigma2))
-                # the captured launch has not run: the staged step is still pending
-            self._graph.replay()
+                    self._launch(p, sigma2, copies)
+                self._graphs[key] = g
+            g.replay()
         else:
-            self._launch(p, sigma2)
-
-    def _redo_seq(self):
-        """The warm-up consumed this step's sequence number on every rank; stage the next one."""
-        o = self.N * self.max_p + 2 * self.N + self.W64
-        self.seq += 1
-        self.h_small.numpy()[o + 1] = float(self.seq)
+            self._launch(p, sigma2, copies)
 
     def result(self):
         """(global index, log-sum-exp over all candidates) of the last launched step (synchronises; one
