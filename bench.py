@@ -38,7 +38,6 @@ import json
 import math
 import os
 import sys
-import threading
 import time
 
 import numpy as np
@@ -73,47 +72,56 @@ def parse_args():
 # clocks sampling (pynvml) during the timed region
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons (NVML) sampled WHILE the timed region runs on the GPU: the host first
+    enqueues the whole region (asynchronous launches), then calls poll(done) which samples until done()
+    says the end event has completed.  Sampling from a second thread during the launch loop instead was
+    measured to stretch an 8-GPU, 7 ms region by a third (NVML calls of 8 processes contend with the
+    launch path)."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
                0x4: "sw_power_cap", 0x80: "hw_power_brake", 0x2: "applications_clocks_setting"}
 
     def __init__(self, index):
         self.samples, self.reasons, self.max_mhz = [], set(), None
-        self._stop = threading.Event()
-        self._thread = None
         try:
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.sample(keep=False)        # first call pays the lazy initialisation
         except Exception:
             self.nv = None
 
-    def _run(self):
-        while not self._stop.is_set():
+    def sample(self, keep=True):
+        if self.nv is None:
+            return
+        try:
+            mhz = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
             try:
-                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
-                try:
-                    r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                except Exception:
-                    r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            if keep:
+                self.samples.append(mhz)
                 for bit, name in self.REASONS.items():
                     if r & bit:
                         self.reasons.add(name)
-            except Exception:
-                pass
-            self._stop.wait(0.05)
+        except Exception:
+            pass
+
+    def poll(self, done, interval=0.002, limit=10000):
+        """Sample until done() is true (at least once)."""
+        for _ in range(limit):
+            self.sample()
+            if done():
+                break
+            time.sleep(interval)
 
     def __enter__(self):
-        if self.nv is not None:
-            self._thread = threading.Thread(target=self._run, daemon=True)
-            self._thread.start()
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        if self._thread is not None:
-            self._thread.join()
+        pass
 
     def summary(self):
         if not self.samples:
@@ -322,6 +330,7 @@ def build_population(args, rank, torch):
     pop.mine_rules()
     torch.cuda.synchronize()
     marks["wall_s"] = time.perf_counter() - t0
+    marks["slope_flagged"] = pop.slope_groups_flagged
     del pop.calculate_values, pop.update_base_rules, pop.sort_base_rules
     # kernel-only time of detector evaluation: re-launch the fused kernel on the prepared inputs
     from mitre_b200 import device as D
@@ -427,11 +436,13 @@ def run_b200(args):
         data, pop, build_marks = build_population(args, 0, torch)
         N, P = data.n_subjects, len(pop)
         local_rows, start = pop.packed_truth, 0
+        shard_bounds_all = [(0, P)]
         n_windows = len(pop.windows)
     else:
         data, spop, shard_build_s = build_sharded(args, torch)
         N, P = data.n_subjects, spop.P
         local_rows, start = spop.local_rows, spop.start
+        shard_bounds_all = spop.bounds
         n_windows = len(spop.windows)
         spop.local_population = None
         torch.cuda.empty_cache()
@@ -470,14 +481,16 @@ def run_b200(args):
     for _ in range(warm):
         sw.launch(p, SIGMA2, copies=False)
     barrier()
-    with ClockSampler(local_rank) as clocks:
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        for _ in range(args.steps):
-            sw.launch(p, SIGMA2, copies=False)
-        ev1.record()
-        barrier()
-        ms_step = ev0.elapsed_time(ev1) / args.steps
+    clocks = ClockSampler(local_rank)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        sw.launch(p, SIGMA2, copies=False)
+    ev1.record()
+    clocks.poll(ev1.query)                 # clocks / throttle reasons while the region executes
+    barrier()
+    ms_step = ev0.elapsed_time(ev1) / args.steps
     if int(sw.buffers.status.item()):
         raise SystemExit("status flags %d after the timed region" % int(sw.buffers.status.item()))
 
@@ -502,7 +515,7 @@ def run_b200(args):
 
     def gather_step():
         D.score_all(local_rows, N, dX, dom, dka, SIGMA2, mask=dmask, buffers=sw.buffers, out=scorer_out)
-        return PL.allgather_loglik(scorer_out, P) if world > 1 else scorer_out
+        return PL.allgather_loglik(scorer_out, P, bounds=shard_bounds_all) if world > 1 else scorer_out
     gather_step()
     barrier()
     gather_ms = cuda_time_ms(torch, gather_step, max(3, min(args.steps, 10)))
@@ -546,6 +559,12 @@ def run_b200(args):
             check = "ranks disagree on the drawn index"
             t[3] = 1.0
     ms_step, e2e_ms, gather_ms = float(t[0]), float(t[1]), float(t[2])
+    per_rank = torch.tensor([stats_ms, float(n_local), dup_frac], dtype=torch.float64, device=dev)
+    if world > 1:
+        all_ranks = torch.empty(3 * world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(all_ranks, per_rank)
+        per_rank = all_ranks
+    per_rank = per_rank.cpu().numpy().reshape(-1, 3)
     if float(t[3]) != 0.0 and check in ("ok", "skipped"):
         check = "failed on another rank"
 
@@ -574,6 +593,9 @@ def run_b200(args):
                        "l2_policy": "per-GPU inputs exceed the 126 MB L2 at N <= 8 (>= 0.88 GB per step)",
                        "duplicate_rows_fraction": dup_frac},
             "parity_check": check,
+            "per_rank": {"candidate_kernel_ms": [float(x) for x in per_rank[:, 0]],
+                         "candidates": [int(x) for x in per_rank[:, 1]],
+                         "duplicate_rows_fraction": [float(x) for x in per_rank[:, 2]]},
             "e2e": {"value": P / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(sw.h_small.numel() * 8), "d2h_bytes_per_step": 32,
                     "what": "ShardedSweep.step: host (pinned) sweep inputs -> device, the step above, drawn index "

@@ -275,7 +275,22 @@ int mitre_detectors_fused(void *stream, const double *series_t, int64_t vstride,
                           const double *wdt, int64_t ld, const int64_t *group_base,
                           const uint8_t *slope_ok, const int32_t *task_window,
                           const int8_t *task_type, int n_tasks_wt, int n_windows, int64_t G,
-                          double *values, double *thresholds, int32_t *K, uint64_t *rows_padded);
+                          double *values, double *thresholds, int32_t *K, uint64_t *rows_padded,
+                          const uint8_t *group_type, uint8_t *group_flags, int64_t *flagged);
+/* Slope guard band.  'slope' detector values come from a closed form here and from LAPACK gelsd in the
+ * reference (rules.py:110-114); the truth rows of a group depend only on the order and tie structure of
+ * its N values, so they are the reference's unless (a) two neighbours of the sorted values are unequal but
+ * closer than 1e-10 x the group's largest |value|, or (b) a subject's slope is exactly 0 while its window
+ * mean is not (a constant non-zero series: the reference returns +-1e-20 rounding noise there, not 0).
+ * Such groups are FLAGGED: group_type uint8[G] (0 = slope, 1 = average; a slope group is followed by its
+ * window's average group), group_flags uint8[G] (optional) <- 0/1, *flagged (device int64, optional) <-
+ * the number of flagged groups (needs group_flags).  mitre_detectors_fused does the check inside its own
+ * kernels when group_type is given (last three arguments; all NULL = off): the values kernel sees a
+ * subject's mean and slope together (b), the sort/emit kernel holds the sorted values (a);
+ * mitre_slope_guard is the same check as a separate pass over values float64[G, N], any N (the
+ * phase-by-phase path). */
+int mitre_slope_guard(void *stream, const double *values, int64_t G, int N, const uint8_t *group_type,
+                      uint8_t *group_flags, int64_t *flagged);
 int mitre_densify_perm(void *stream, const int64_t *perm_padded, int64_t P, int N,
                        const int64_t *row_offsets, int64_t *perm);
 int mitre_set_detector_split(int enable); /* tuning/test hook, see above */

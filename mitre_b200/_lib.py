@@ -71,7 +71,8 @@ SIGNATURES = {
     "mitre_window_lists": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_i64, c_i64] +
                            [c_void_p] * 7),
     "mitre_detectors_fused": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int] + [c_void_p] * 7 +
-                              [c_i64] + [c_void_p] * 4 + [c_int, c_int, c_i64] + [c_void_p] * 4),
+                              [c_i64] + [c_void_p] * 4 + [c_int, c_int, c_i64] + [c_void_p] * 7),
+    "mitre_slope_guard": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p, c_void_p]),
     "mitre_set_detector_split": (c_int, [c_int]),
     "mitre_selftest_divide": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p]),
     "mitre_densify_perm": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p]),

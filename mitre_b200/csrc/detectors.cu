@@ -266,6 +266,104 @@ thresholds_warp_kernel(const double *__restrict__ values, int64_t G, int N, doub
     }
 }
 
+// Slope guard band as a separate pass (fused_detectors.cuh explains the criterion): one warp per slope
+// group for N <= 64, one CTA per slope group beyond.
+constexpr double kGuard = 1e-10;
+
+__global__ void __launch_bounds__(256)
+slope_guard_warp_kernel(const double *__restrict__ values, int64_t G, int N, const uint8_t *__restrict__ group_type,
+                        uint8_t *__restrict__ group_flags, unsigned long long *__restrict__ flagged)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t kInf = ~0ull;
+    for (int64_t g = warp0; g < G; g += nwarps) {
+        if (group_type[g] != 0) {
+            if (lane == 0 && group_flags) group_flags[g] = 0;
+            continue;
+        }
+        const double *vg = values + g * N;
+        const double xa = lane < N ? vg[lane] : 0.0, xb = lane + 32 < N ? vg[lane + 32] : 0.0;
+        bool flag = false;
+        if (g + 1 < G) {       // zero slope, non-zero window mean: a constant non-zero series
+            if (lane < N && xa == 0.0) flag |= values[(g + 1) * N + lane] != 0.0;
+            if (lane + 32 < N && xb == 0.0) flag |= values[(g + 1) * N + lane + 32] != 0.0;
+        }
+        uint64_t a = lane < N ? f64_key(xa) : kInf;
+        uint64_t b = lane + 32 < N ? f64_key(xb) : kInf;
+        warp_sort64(a, b, lane);
+        const double va = key_f64(a), vb = key_f64(b);
+        double na = __shfl_down_sync(0xffffffffu, va, 1);
+        const double b0 = __shfl_sync(0xffffffffu, vb, 0);
+        if (lane == 31) na = b0;
+        const double nb = __shfl_down_sync(0xffffffffu, vb, 1);
+        // largest |value|: the sorted extremes (positions 0 and N-1)
+        const double first = __shfl_sync(0xffffffffu, va, 0);
+        const double last = (N - 1 < 32) ? __shfl_sync(0xffffffffu, va, (N - 1) & 31)
+                                         : __shfl_sync(0xffffffffu, vb, (N - 1 - 32) & 31);
+        const double scale = fmax(fabs(first), fabs(last));
+        if (lane < N - 1) flag |= (va != na) && (na - va) <= kGuard * scale;
+        if (lane + 32 < N - 1) flag |= (vb != nb) && (nb - vb) <= kGuard * scale;
+        const bool any = __any_sync(0xffffffffu, flag);
+        if (lane == 0) {
+            if (group_flags) group_flags[g] = any ? 1 : 0;
+            if (any && flagged) atomicAdd(flagged, 1ull);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+slope_guard_block_kernel(const double *__restrict__ values, int64_t G, int N, int npow2,
+                         const uint8_t *__restrict__ group_type, uint8_t *__restrict__ group_flags,
+                         unsigned long long *__restrict__ flagged)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *keys = reinterpret_cast<uint64_t *>(smem_raw);            // [npow2]
+    __shared__ int s_flag;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int64_t g = blockIdx.x; g < G; g += gridDim.x) {
+        if (group_type[g] != 0) {
+            if (tid == 0 && group_flags) group_flags[g] = 0;
+            continue;
+        }
+        const double *vg = values + g * N;
+        if (tid == 0) s_flag = 0;
+        bool flag = false;
+        for (int i = tid; i < npow2; i += nt) {
+            const double x = i < N ? vg[i] : 0.0;
+            keys[i] = i < N ? f64_key(x) : ~0ull;
+            if (i < N && x == 0.0 && g + 1 < G) flag |= values[(g + 1) * N + i] != 0.0;
+        }
+        __syncthreads();
+        for (int k = 2; k <= npow2; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < npow2; i += nt) {
+                    const int ixj = i ^ j;
+                    if (ixj > i) {
+                        const uint64_t x = keys[i], y = keys[ixj];
+                        const bool up = (i & k) == 0;
+                        if ((x > y) == up) { keys[i] = y; keys[ixj] = x; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        const double scale = fmax(fabs(key_f64(keys[0])), fabs(key_f64(keys[N - 1])));
+        for (int i = tid; i < N - 1; i += nt) {
+            const double a = key_f64(keys[i]), b = key_f64(keys[i + 1]);
+            flag |= (a != b) && (b - a) <= kGuard * scale;
+        }
+        if (flag) atomicOr(&s_flag, 1);
+        __syncthreads();
+        if (tid == 0) {
+            if (group_flags) group_flags[g] = s_flag ? 1 : 0;
+            if (s_flag && flagged) atomicAdd(flagged, 1ull);
+        }
+        __syncthreads();
+    }
+}
+
 // thresholds, any N: one CTA per group, bitonic sort in shared memory.
 __global__ void __launch_bounds__(256)
 thresholds_block_kernel(const double *__restrict__ values, int64_t G, int N, int npow2,
@@ -473,6 +571,56 @@ extern "C" int mitre_detector_values(void *stream, const double *series, int64_t
                                                              cap, use_tma, values);
     MITRE_LAUNCH_CHECK();
     return MITRE_OK;
+}
+
+namespace mitre {
+__global__ void __launch_bounds__(256)
+count_flags_kernel(const uint8_t *__restrict__ flags, int64_t G, unsigned long long *__restrict__ out)
+{
+    unsigned long long c = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < G; i += stride) c += flags[i] != 0;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+int launch_count_flags(cudaStream_t st, const uint8_t *group_flags, int64_t G, unsigned long long *flagged)
+{
+    if (G <= 0) return MITRE_OK;
+    count_flags_kernel<<<capped_grid(ceil_div64(G, 256), 4), 256, 0, st>>>(group_flags, G, flagged);
+    MITRE_LAUNCH_CHECK();
+    return MITRE_OK;
+}
+
+int launch_slope_guard(cudaStream_t st, const double *values, int64_t G, int N, const uint8_t *group_type,
+                       uint8_t *group_flags, unsigned long long *flagged)
+{
+    if (G <= 0 || N < 2) return MITRE_OK;
+    if (N <= 64) {
+        slope_guard_warp_kernel<<<capped_grid(ceil_div64(G, 8), 8), 256, 0, st>>>(values, G, N, group_type,
+                                                                                 group_flags, flagged);
+    } else {
+        int npow2 = 1;
+        while (npow2 < N) npow2 <<= 1;
+        const size_t smem = (size_t)npow2 * sizeof(uint64_t);
+        if (smem > smem_optin()) return MITRE_ERR_UNSUPPORTED;
+        auto kern = slope_guard_block_kernel;
+        MITRE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<capped_grid(G, 8), 256, smem, st>>>(values, G, N, npow2, group_type, group_flags, flagged);
+    }
+    MITRE_LAUNCH_CHECK();
+    return MITRE_OK;
+}
+}  // namespace mitre
+
+extern "C" int mitre_slope_guard(void *stream, const double *values, int64_t G, int N, const uint8_t *group_type,
+                                 uint8_t *group_flags, int64_t *flagged)
+{
+    if (G < 0 || N <= 0 || (G > 0 && (!values || !group_type))) return MITRE_ERR_INVALID;
+    if (flagged) MITRE_CUDA_TRY(cudaMemsetAsync(flagged, 0, sizeof(int64_t), as_stream(stream)));
+    return launch_slope_guard(as_stream(stream), values, G, N, group_type, group_flags,
+                              reinterpret_cast<unsigned long long *>(flagged));
 }
 
 extern "C" int mitre_detector_thresholds(void *stream, const double *values, int64_t G, int N,

@@ -5,6 +5,10 @@
 
 namespace mitre {
 int g_detector_split = 1;
+SlopeGuardArgs g_slope_guard = {nullptr, nullptr, nullptr};
+int launch_slope_guard(cudaStream_t st, const double *values, int64_t G, int N, const uint8_t *group_type,
+                       uint8_t *group_flags, unsigned long long *flagged);   // detectors.cu
+int launch_count_flags(cudaStream_t st, const uint8_t *group_flags, int64_t G, unsigned long long *flagged);
 int launch_fused_nb4(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V,
                      const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
                      const double *winv_n, const double *winv_sxx, const int32_t *widx,
@@ -134,15 +138,62 @@ extern "C" int mitre_window_lists(void *stream, const double *times, const int32
     return MITRE_OK;
 }
 
+static int detectors_fused_launch(void *stream, const double *series_t, int64_t vstride, int N, int V,
+                                  const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
+                                  const double *winv_n, const double *winv_sxx, const int32_t *widx,
+                                  const double *wdt, int64_t ld, const int64_t *group_base,
+                                  const uint8_t *slope_ok, const int32_t *task_window,
+                                  const int8_t *task_type, int n_tasks_wt, int n_windows, int64_t G,
+                                  double *values, double *thresholds, int32_t *K, uint64_t *rows_padded);
+
 extern "C" int mitre_detectors_fused(void *stream, const double *series_t, int64_t vstride, int N, int V,
                                      const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
                                      const double *winv_n, const double *winv_sxx, const int32_t *widx,
                                      const double *wdt, int64_t ld, const int64_t *group_base,
                                      const uint8_t *slope_ok, const int32_t *task_window,
                                      const int8_t *task_type, int n_tasks_wt, int n_windows, int64_t G,
-                                     double *values, double *thresholds, int32_t *K, uint64_t *rows_padded)
+                                     double *values, double *thresholds, int32_t *K, uint64_t *rows_padded,
+                                     const uint8_t *group_type, uint8_t *group_flags, int64_t *flagged)
 {
     if (N < 2 || N > 63) return MITRE_ERR_UNSUPPORTED;
+    if ((group_flags || flagged) && !group_type) return MITRE_ERR_INVALID;
+    if (flagged && !group_flags) return MITRE_ERR_INVALID;
+    // Slope guard band.  Default variants: the values kernel sees a subject's mean and slope together and
+    // flags constant non-zero series, the staged sort/emit kernel checks near-ties on the sorted values it
+    // already holds -- no extra pass.  The cross-check variants (single kernel, flat values, direct
+    // sort/emit) get the separate pass.
+    const bool want_guard = group_type && group_flags && G > 0;
+    const bool in_kernel = want_guard && (g_detector_split == 1 || g_detector_split == 3);
+    if (want_guard) MITRE_CUDA_TRY(cudaMemsetAsync(group_flags, 0, (size_t)G, as_stream(stream)));
+    if (flagged) MITRE_CUDA_TRY(cudaMemsetAsync(flagged, 0, sizeof(int64_t), as_stream(stream)));
+    struct GuardScope {
+        GuardScope(bool on, const uint8_t *t, uint8_t *f)
+        {
+            g_slope_guard = on ? SlopeGuardArgs{t, f, nullptr} : SlopeGuardArgs{nullptr, nullptr, nullptr};
+        }
+        ~GuardScope() { g_slope_guard = SlopeGuardArgs{nullptr, nullptr, nullptr}; }
+    } guard_scope(in_kernel, group_type, group_flags);
+    int rc = detectors_fused_launch(stream, series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld,
+                                    group_base, slope_ok, task_window, task_type, n_tasks_wt, n_windows, G, values,
+                                    thresholds, K, rows_padded);
+    if (rc != MITRE_OK) return rc;
+    if (want_guard && g_detector_split != 5) {
+        if (!in_kernel)
+            return launch_slope_guard(as_stream(stream), values, G, N, group_type, group_flags,
+                                      reinterpret_cast<unsigned long long *>(flagged));
+        if (flagged) return launch_count_flags(as_stream(stream), group_flags, G, reinterpret_cast<unsigned long long *>(flagged));
+    }
+    return MITRE_OK;
+}
+
+static int detectors_fused_launch(void *stream, const double *series_t, int64_t vstride, int N, int V,
+                                  const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
+                                  const double *winv_n, const double *winv_sxx, const int32_t *widx,
+                                  const double *wdt, int64_t ld, const int64_t *group_base,
+                                  const uint8_t *slope_ok, const int32_t *task_window,
+                                  const int8_t *task_type, int n_tasks_wt, int n_windows, int64_t G,
+                                  double *values, double *thresholds, int32_t *K, uint64_t *rows_padded)
+{
     if (V <= 0 || n_tasks_wt < 0 || vstride < V || ld <= 0) return MITRE_ERR_INVALID;
     if (n_tasks_wt == 0) return MITRE_OK;
     if (!series_t || !wlo || !wcnt || !wstart || !winv_n || !winv_sxx || !widx || !wdt || !group_base ||
@@ -181,7 +232,7 @@ extern "C" int mitre_detectors_fused(void *stream, const double *series_t, int64
             chunks = (n_windows + per_block - 1) / per_block;
             values_resident_kernel<<<dim3((unsigned)tiles, (unsigned)chunks), 32 * n_warps, smem, as_stream(stream)>>>(
                 series_t, vstride, N, V, n_windows, wlo, wcnt, wstart, winv_n, winv_sxx, wdt, ld, group_base,
-                slope_ok, per_block, values);
+                slope_ok, per_block, values, g_slope_guard.group_flags);
         } else {
             const int n_vtiles = (V + 31) / 32;
             const int64_t blocks = (int64_t)n_windows * n_vtiles;
@@ -191,7 +242,7 @@ extern "C" int mitre_detectors_fused(void *stream, const double *series_t, int64
             const size_t smem = sizeof(double) * 64 * (size_t)(N | 1);
             values_tile_kernel<<<(unsigned)blocks, 32 * n_warps, smem, as_stream(stream)>>>(
                 series_t, vstride, N, V, n_vtiles, wlo, wcnt, wstart, winv_n, winv_sxx, wdt, ld, group_base,
-                slope_ok, values);
+                slope_ok, values, g_slope_guard.group_flags);
         }
         MITRE_LAUNCH_CHECK();
     }

@@ -34,6 +34,31 @@ namespace mitre {
 
 extern int g_detector_split;  // see mitre_set_detector_split
 
+// ---- slope guard band (SURVEY hard part 1) ------------------------------------------------------------
+// 'slope' values come from a closed form here and from an SVD least-squares solve in the reference
+// (rules.py:110-114); they agree to ~1e-12 relative, and truth rows depend only on the ORDER and TIE
+// structure of a group's N values.  A group is flagged as "rows may differ from the reference" when
+//   * two neighbours of its sorted values are unequal but closer than kSlopeGuard x the group's
+//     largest |value| (their order is not certain), or
+//   * a subject's slope is exactly 0 while its window mean is not: a constant non-zero series, for
+//     which the reference returns LAPACK rounding noise (+-1e-20) instead of 0, i.e. a different tie
+//     structure against the all-zero series of other subjects.
+// group_type uint8[G]: 0 = slope, 1 = average (only slope groups are examined; a slope group g is
+// followed by its window's average group g + 1).  group_flags uint8[G] (optional) receives 0/1 per
+// group, *flagged is incremented once per flagged group.
+constexpr double kSlopeGuard = 1e-10;
+struct SlopeGuardArgs {
+    const uint8_t *group_type;
+    uint8_t *group_flags;
+    unsigned long long *flagged;
+};
+extern SlopeGuardArgs g_slope_guard;   // set by the extern "C" entry for the launch it is about to make
+
+__device__ __forceinline__ bool near_tie(double a, double b, double scale)   // a <= b: sorted neighbours
+{
+    return a != b && (b - a) <= kSlopeGuard * scale;
+}
+
 // ---- compile-time Batcher merge-exchange network for n inputs ------------------------------------
 template <int N>
 struct Network {
@@ -641,7 +666,7 @@ values_tile_kernel(const double *__restrict__ series_t, int64_t vstride, int N, 
                    const int32_t *__restrict__ wstart, const double *__restrict__ winv_n,
                    const double *__restrict__ winv_sxx, const double *__restrict__ wdt, int64_t ld,
                    const int64_t *__restrict__ group_base, const uint8_t *__restrict__ slope_ok,
-                   double *__restrict__ values)
+                   double *__restrict__ values, uint8_t *__restrict__ group_flags)
 {
     extern __shared__ double tile[];   // [32 * nt][Np], Np = N | 1
     const int w = blockIdx.x / n_vtiles, vt = blockIdx.x % n_vtiles;
@@ -660,7 +685,11 @@ values_tile_kernel(const double *__restrict__ series_t, int64_t vstride, int N, 
         window_stats_any(n, Column{px, vstride}, LdgVec{dts}, inv_n, __ldg(winv_sxx + w * N + s), nt == 2, mean,
                          slope);
         tile[(lane * nt + (nt - 1)) * Np + s] = mean;
-        if (nt == 2) tile[(lane * 2) * Np + s] = slope;
+        if (nt == 2) {
+            tile[(lane * 2) * Np + s] = slope;
+            // slope guard band: slope exactly 0 with a non-zero mean = constant non-zero series
+            if (group_flags && slope == 0.0 && mean != 0.0) group_flags[group_base[w] + (int64_t)v * 2] = 1;
+        }
     }
     __syncthreads();
     const int n_rows = min(32, V - v0) * nt;
@@ -729,7 +758,7 @@ values_resident_kernel(const double *__restrict__ series_t, int64_t vstride, int
                        const int32_t *__restrict__ wstart, const double *__restrict__ winv_n,
                        const double *__restrict__ winv_sxx, const double *__restrict__ wdt, int64_t ld,
                        const int64_t *__restrict__ group_base, const uint8_t *__restrict__ slope_ok,
-                       int windows_per_block, double *__restrict__ values)
+                       int windows_per_block, double *__restrict__ values, uint8_t *__restrict__ group_flags)
 {
     extern __shared__ __align__(16) double rsm[];
     __shared__ int next_subject[2];
@@ -781,7 +810,11 @@ values_resident_kernel(const double *__restrict__ series_t, int64_t vstride, int
             window_stats_any(ri.y, SmemCol32{ser + ri.x * 32 + lane}, SmemVec{dt + ri.z}, rd.x, rd.y, nt == 2, mean,
                              slope);
             st_lane[(nt - 1) * N + s] = mean;
-            if (nt == 2) st_lane[s] = slope;
+            if (nt == 2) {
+                st_lane[s] = slope;
+                // slope guard band: slope exactly 0 with a non-zero mean = constant non-zero series
+                if (group_flags && slope == 0.0 && mean != 0.0) group_flags[gb + (int64_t)vc * 2] = 1;
+            }
         }
         cp_async_wait_all();
         __syncthreads();
@@ -885,7 +918,7 @@ __host__ __device__ inline size_t sort_emit_stage_bytes(int N)
 template <int NB>
 __global__ void __launch_bounds__(kStageThreads, (NB <= 40) ? 6 : 3)
 sort_emit_staged_kernel(const double *__restrict__ values, int64_t G, int N, double *__restrict__ thresholds,
-                        int32_t *__restrict__ K, uint64_t *__restrict__ rows, int dry)
+                        int32_t *__restrict__ K, uint64_t *__restrict__ rows, int dry, SlopeGuardArgs sg)
 {
     extern __shared__ __align__(128) unsigned char stage_smem[];
     __shared__ uint64_t bar;
@@ -923,6 +956,21 @@ sort_emit_staged_kernel(const double *__restrict__ values, int64_t G, int N, dou
         int id[NB];
         // threads past the end of the last tile sort whatever the buffer holds; nothing of it is stored
         sort_group_key32<NB>(sval + tid * N, N, val, id);
+        if (sg.group_type && tid < cnt && sg.group_type[g0 + tid] == 0) {
+            // slope guard band, near-tie half: the sorted values are in registers (compile-time indices only:
+            // a run-time index would push val[] into local memory).  The constant-series half of the
+            // criterion is checked by the values kernel; group_flags was cleared before the launches.
+            double last = val[0];
+#pragma unroll
+            for (int k = 1; k < NB; ++k)
+                if (k == M) last = val[k];
+            const double tol = kSlopeGuard * fmax(fabs(val[0]), fabs(last));
+            bool flag = false;
+#pragma unroll
+            for (int k = 0; k < NB - 1; ++k)
+                if (k < M) flag |= (val[k] != val[k + 1]) && (val[k + 1] - val[k] <= tol);
+            if (flag) sg.group_flags[g0 + tid] = 1;
+        }
         if (tid == 0) bulk_wait_read0();   // the previous tile's thresholds have left their buffer
         __syncthreads();                   // every thread holds its values: their tile becomes the rows tile
         if (!dry) {
@@ -1004,7 +1052,8 @@ static int launch_sort_emit_staged(cudaStream_t st, const double *values, int64_
     const int64_t need = ceil_div64(G, kStageThreads);
     if (need < blocks) blocks = need;
     if (blocks < 1) blocks = 1;
-    kern<<<(unsigned)blocks, kStageThreads, smem, st>>>(values, G, N, thresholds, K, rows, g_detector_split == 5);
+    kern<<<(unsigned)blocks, kStageThreads, smem, st>>>(values, G, N, thresholds, K, rows, g_detector_split == 5,
+                                                        g_slope_guard);
     MITRE_LAUNCH_CHECK();
     return MITRE_OK;
 }

@@ -317,22 +317,39 @@ def window_lists(times, t_offsets, windows, vstride):
     return t
 
 
-def detectors_fused(series_t, N, V, lists, group_base, slope_ok, task_window, task_type, G):
+def detectors_fused(series_t, N, V, lists, group_base, slope_ok, task_window, task_type, G, group_type=None):
     """mitre_detectors_fused (values kernel + sort/emit kernel, no host round trip): values f64[G, N],
-    thresholds f64[G, N-1], K i32[G], rows_padded i64[G, 2(N-1)]."""
+    thresholds f64[G, N-1], K i32[G], rows_padded i64[G, 2(N-1)].  With group_type (uint8[G], 0 = slope)
+    also the slope guard band: returns additionally (group_flags uint8[G], flagged int64[1])."""
     L = 2 * (N - 1)
     values = torch.empty((G, N), dtype=F64, device=dev())
     thresholds = torch.empty((G, N - 1), dtype=F64, device=dev())
     K = torch.empty(G, dtype=I32, device=dev())
     rows = torch.empty((G, L), dtype=I64, device=dev())
+    flags = torch.empty(G, dtype=U8, device=dev()) if group_type is not None else None
+    flagged = torch.zeros(1, dtype=I64, device=dev()) if group_type is not None else None
     check(lib().mitre_detectors_fused(_stream(), _p(series_t), series_t.shape[1], int(N), int(V),
                                       _p(lists['lo']), _p(lists['cnt']), _p(lists['start']),
                                       _p(lists['inv_n']), _p(lists['inv_sxx']), _p(lists['idx']),
                                       _p(lists['dt']), lists['ld'], _p(group_base), _p(slope_ok),
                                       _p(task_window), _p(task_type), task_window.shape[0],
                                       lists['lo'].shape[0], int(G), _p(values),
-                                      _p(thresholds), _p(K), _p(rows)), "mitre_detectors_fused")
+                                      _p(thresholds), _p(K), _p(rows), _p(group_type), _p(flags), _p(flagged)),
+          "mitre_detectors_fused")
+    if group_type is not None:
+        return values, thresholds, K, rows, flags, flagged
     return values, thresholds, K, rows
+
+
+def slope_guard(values, group_type):
+    """Slope guard band over values f64[G, N] (any N): (group_flags uint8[G], flagged int64[1])."""
+    G, N = values.shape
+    flags = torch.zeros(G, dtype=U8, device=dev())
+    flagged = torch.zeros(1, dtype=I64, device=dev())
+    if G:
+        check(lib().mitre_slope_guard(_stream(), _p(values), G, N, _p(group_type), _p(flags), _p(flagged)),
+              "mitre_slope_guard")
+    return flags, flagged
 
 
 def selftest_divide(a, n):

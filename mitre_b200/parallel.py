@@ -40,17 +40,43 @@ def all_shard_bounds(P, world_size):
     return [shard_bounds(P, world_size, r) for r in range(world_size)]
 
 
+def balanced_bounds(sorted_rows, world_size, tile=128, extra_round_cost=0.5):
+    """Slice bounds [(start, stop)] * world_size that balance the WORK of the duplicate-aware scoring kernel
+    instead of the row count.  The kernel scores the D distinct rows of a 128-row tile in ceil(D / 32)
+    rounds, so a tile costs about 1 + extra_round_cost * (ceil(D / 32) - 1); the share of tiles needing a
+    second round varies along a lexsorted table (few duplicates among the middle ranks), which left an
+    equal-rows split 5 % out of balance at 8 GPUs.  Bounds are multiples of the tile; every rank computes
+    the same bounds from the same (replicated) sorted table."""
+    P = int(sorted_rows.shape[0])
+    if world_size == 1 or P < tile * world_size * 4:
+        return all_shard_bounds(P, world_size)
+    heads = torch.ones(P, dtype=torch.bool, device=sorted_rows.device)
+    heads[1:] = (sorted_rows[1:] != sorted_rows[:-1]).any(dim=1)
+    ntiles = (P + tile - 1) // tile
+    padded = torch.zeros(ntiles * tile, dtype=torch.int32, device=sorted_rows.device)
+    padded[:P] = heads
+    D_tile = padded.view(ntiles, tile).sum(dim=1)
+    rounds = torch.clamp((D_tile + 31) // 32, min=1).to(torch.float64)
+    cum = torch.cumsum(1.0 + extra_round_cost * (rounds - 1.0), dim=0)
+    targets = cum[-1] * torch.arange(1, world_size, dtype=torch.float64, device=cum.device) / world_size
+    cuts = (torch.searchsorted(cum, targets) + 1).clamp(max=ntiles).cpu().numpy().astype(np.int64) * tile
+    edges = [0] + [int(min(c, P)) for c in cuts] + [P]
+    for i in range(1, len(edges)):
+        edges[i] = max(edges[i], edges[i - 1])
+    return [(edges[r], edges[r + 1]) for r in range(world_size)]
+
+
 def chains_for_rank(n_chains, world_size, rank, base_seed=0):
     """Chain indices and seeds (base_seed + i, main.py:1930-1938) this rank runs."""
     return [(i, base_seed + i) for i in range(n_chains) if i % world_size == rank]
 
 
-def allgather_loglik(local, P, group=None):
+def allgather_loglik(local, P, group=None, bounds=None):
     """local: float64[stop-start] on this rank -> float64[P] on every rank (shard order)."""
     ws, rank = world(group)
     if ws == 1:
         return local
-    bounds = all_shard_bounds(P, ws)
+    bounds = bounds if bounds is not None else all_shard_bounds(P, ws)
     width = max(b - a for a, b in bounds)
     padded = local.new_zeros(width)
     padded[:local.shape[0]] = local
@@ -127,13 +153,14 @@ class ShardedScorer:
     CUDA tensor).  `score` runs mitre_score_all on the slice; `gather` / `draw` are the two exchange
     modes."""
 
-    def __init__(self, local_rows, P, N, group=None):
+    def __init__(self, local_rows, P, N, group=None, bounds=None):
         from . import device as D
         self.D = D
         self.group = group
         self.P, self.N = int(P), int(N)
         self.ws, self.rank = world(group)
-        self.start, self.stop = shard_bounds(self.P, self.ws, self.rank)
+        self.bounds = bounds if bounds is not None else all_shard_bounds(self.P, self.ws)
+        self.start, self.stop = self.bounds[self.rank]
         if local_rows.shape[0] != self.stop - self.start:
             raise ValueError("local slice has %d rows, expected %d" % (local_rows.shape[0],
                                                                         self.stop - self.start))
@@ -156,7 +183,7 @@ class ShardedScorer:
                                 buffers=self.buffers, out=out)
 
     def gather(self, local_out):
-        return allgather_loglik(local_out, self.P, self.group)
+        return allgather_loglik(local_out, self.P, self.group, self.bounds)
 
     def draw(self, local_out, local_prior, u, stabilise=True):
         """Two-stage draw of a global index from w = local_out (+ local_prior)."""
@@ -425,10 +452,11 @@ class ShardedPopulation:
         describe(k)         (variable, window, type, direction, threshold) of global sorted index k
     """
 
-    def __init__(self, data, tmin, N_intervals, tmax=None, group=None):
+    def __init__(self, data, tmin, N_intervals, tmax=None, group=None, balance=True):
         from . import device as D
         from . import rules as R
         self.group = group
+        self.balance = balance
         self.ws, self.rank = world(group)
         self.N = data.n_subjects
         self.V = data.n_variables
@@ -490,7 +518,10 @@ class ShardedPopulation:
         else:
             perm, sorted_rows = torch.empty(0, dtype=torch.int64, device=dev), rows_enum
         del rows_enum
-        self.start, self.stop = shard_bounds(self.P, self.ws, self.rank)
+        # slices of the sorted order: equal work for the scoring kernel (balanced_bounds), or equal rows
+        self.bounds = (balanced_bounds(sorted_rows, self.ws) if self.balance and self.P
+                       else all_shard_bounds(self.P, self.ws))
+        self.start, self.stop = self.bounds[self.rank]
         self.local_rows = sorted_rows[self.start:self.stop].clone()
         self.local_perm = perm[self.start:self.stop].clone()
         del perm, sorted_rows
@@ -498,11 +529,10 @@ class ShardedPopulation:
         pop._rows_padded = None
 
     def scorer(self):
-        return ShardedScorer(self.local_rows, self.P, self.N, self.group)
+        return ShardedScorer(self.local_rows, self.P, self.N, self.group, bounds=self.bounds)
 
     def owner_of_index(self, k):
-        for r in range(self.ws):
-            a, b = shard_bounds(self.P, self.ws, r)
+        for r, (a, b) in enumerate(self.bounds):
             if a <= k < b:
                 return r
         raise IndexError(k)

@@ -275,6 +275,7 @@ class DiscreteRulePopulation:
         for k in list(state):
             if k.startswith('_d_') or k in ('_values', '_thresholds', '_K', '_row_offsets', '_rows',
                                             '_perm', '_sorted_rows', '_row_group', '_rows_padded', '_fused', '_fused_args', '_active_rows',
+                                            '_slope_flags', '_slope_flagged',
                                             '_d_windows'):
                 state[k] = None
         state['_host_cache'] = {}
@@ -357,6 +358,7 @@ class DiscreteRulePopulation:
             self._group_tables_cache = cached
         _, self._group_window, self._group_variable, self._group_type = cached
         self._host_cache = {}
+        self._slope_flags = self._slope_flagged = None
         if W == 0:
             self._values = torch.empty((0, self.data.n_subjects), dtype=torch.float64, device=D.dev())
             self._d_windows = None
@@ -380,14 +382,34 @@ class DiscreteRulePopulation:
                 tw.append(w); tt.append(1)
             d_tw = torch.as_tensor(np.array(tw, dtype=np.int32), device=D.dev())
             d_tt = torch.as_tensor(np.array(tt, dtype=np.int8), device=D.dev())
-            self._fused_args = (ds['series_t'], N, V, lists, d_gb, d_ok, d_tw, d_tt, self._G)
-            self._values, thr, K, rows_padded = D.detectors_fused(*self._fused_args)
+            d_gt = torch.as_tensor(np.ascontiguousarray(self._group_type).view(np.uint8), device=D.dev())
+            self._fused_args = (ds['series_t'], N, V, lists, d_gb, d_ok, d_tw, d_tt, self._G, d_gt)
+            self._values, thr, K, rows_padded, self._slope_flags, self._slope_flagged = \
+                D.detectors_fused(*self._fused_args)
             self._fused = (thr, K, rows_padded)
         else:
             lo, cnt = D.window_ranges(ds['times'], ds['t_offsets'], self._d_windows)
             self._values = D.detector_values(ds['series'], ds['times'], ds['t_offsets'],
                                              self._d_windows, lo, cnt, d_gb, d_ok, self._G, ds['max_T'])
+            d_gt = torch.as_tensor(np.ascontiguousarray(self._group_type).view(np.uint8), device=D.dev())
+            self._slope_flags, self._slope_flagged = D.slope_guard(self._values, d_gt)
         self.primitive_values = _PrimitiveValues(self)
+
+    @property
+    def slope_groups_flagged(self):
+        """Number of slope groups whose truth rows are not guaranteed to be the reference's: two sorted
+        neighbours closer than 1e-10 of the group's largest |slope|, or a constant non-zero in-window series
+        (rules.py:110-114 reaches the slope through LAPACK gelsd; see include/mitre_b200.h, mitre_slope_guard)."""
+        f = getattr(self, '_slope_flagged', None)
+        return 0 if f is None else int(f.item())
+
+    def flagged_groups(self):
+        """[(window index, variable)] of the flagged slope groups."""
+        f = getattr(self, '_slope_flags', None)
+        if f is None:
+            return []
+        idx = np.nonzero(f.cpu().numpy())[0]
+        return [(int(self._group_window[g]), int(self._group_variable[g])) for g in idx]
 
     # -- step 3 (rules.py:465-511) ------------------------------------------------------------------------
     def update_base_rules(self):

@@ -271,3 +271,76 @@ def test_near_ties_below_key_resolution_take_the_exact_path(fused):
     assert np.array_equal(pop._K_host[is_mean], ref["K"][is_mean]), (pop._K_host[is_mean][:4], ref["K"][is_mean][:4])
     assert np.array_equal(pop.packed_truth.cpu().numpy().view(np.uint64), DO.pack_rows(ref["truth"][o]))
     assert np.array_equal(pop._perm_host(), o)
+
+
+# ---- slope guard band: groups whose rows are not guaranteed to be the reference's are FLAGGED ----------
+
+def _group_rows(v):
+    """The (above, below) truth rows of one group from its N values, as the reference builds them
+    (rules.py:490-497, 536-539): sorted midpoints, unique, v > theta / v <= theta."""
+    sv = np.sort(v)
+    thr = np.unique(0.5 * (sv[:-1] + sv[1:]))
+    return tuple((tuple(v > t), tuple(v <= t)) for t in thr)
+
+
+def _criterion(values, group_type):
+    """numpy restatement of the flag criterion (include/mitre_b200.h, mitre_slope_guard)."""
+    flags = np.zeros(values.shape[0], dtype=bool)
+    for g in np.nonzero(group_type == 0)[0]:
+        v = values[g]
+        sv = np.sort(v)
+        scale = max(abs(sv[0]), abs(sv[-1]))
+        d = np.diff(sv)
+        near = np.any((d != 0) & (d <= 1e-10 * scale))
+        const = np.any((v == 0) & (values[g + 1] != 0))
+        flags[g] = near or const
+    return flags
+
+
+@pytest.mark.parametrize("fused", [True, "direct", False])
+def test_slope_guard_flags_the_constant_series_divergence(fused):
+    """det_constslope (reference fixture): every group whose rows differ from the reference's is flagged,
+    the flags are exactly the documented criterion, and nothing outside slope groups is flagged."""
+    cfg = MG.DIVERGENT_CASES["det_constslope"]
+    gold = np.load(os.path.join(GOLD, "det_constslope.npz"))
+    d = synthetic.make_series(**cfg["series"])
+    data, pop = build_gpu_population(d, cfg["pop"], fused)
+    vals = pop._values.cpu().numpy()
+    gtype = gold["groups"][:, 2]
+    differ = np.array([_group_rows(vals[g]) != _group_rows(gold["values"][g]) for g in range(vals.shape[0])])
+    flags = pop._slope_flags.cpu().numpy().astype(bool)
+    assert differ.any(), "the fixture is meant to diverge"
+    assert not differ[gtype == 1].any(), "average groups are bit-exact"
+    assert np.all(flags[differ]), "a group whose rows differ from the reference must be flagged"
+    assert np.array_equal(flags, _criterion(vals, gtype))
+    assert pop.slope_groups_flagged == int(flags.sum()) > 0
+    assert len(pop.flagged_groups()) == int(flags.sum())
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_slope_guard_flags_near_ties_and_nothing_else(fused):
+    """Two subjects whose slopes agree to 1e-13: their order is not certain (closed form here, LAPACK gelsd
+    in the reference), so the group is flagged; every unflagged group carries the oracle's rows."""
+    rng = np.random.RandomState(11)
+    N, V = 12, 6
+    X, T = [], []
+    for s in range(N):
+        t = np.array([1.0 + 0.01 * s, 2.0, 3.5 + 0.02 * s])
+        x = rng.rand(V, 3)
+        X.append(x)
+        T.append(t)
+    # variable 2: subjects 3 and 7 get the same straight line up to 1e-13 (slope 0.25)
+    for s, eps in ((3, 0.0), (7, 1e-13)):
+        X[s][2, :] = 0.1 + 0.25 * (1.0 + eps) * (T[s] - T[s][0])
+    y = np.arange(N) % 2 == 0
+    d = dict(X=X, T=T, y=y, variable_weights=np.ones(V), experiment_start=0.0, experiment_end=5.0)
+    ref = DO.build_population(X, T, 0.0, 5.0, 1, 1.0, None)
+    data, pop = build_gpu_population(d, dict(tmin=1.0, N_intervals=1, tmax=None), fused)
+    vals = pop._values.cpu().numpy()
+    flags = pop._slope_flags.cpu().numpy().astype(bool)
+    gtype = ref["group_type"]
+    g_near = int(np.nonzero((pop._group_variable == 2) & (pop._group_type == 0))[0][0])
+    assert flags[g_near] and flags.sum() == 1
+    assert np.array_equal(flags, _criterion(vals, gtype))
+    for g in np.nonzero(~flags)[0]:
+        assert _group_rows(vals[g]) == _group_rows(ref["values"][g]), g

@@ -3,7 +3,7 @@
 MAXN=${1:-8}
 STEPS=${2:-20}
 mkdir -p gpurun_out
-for n in 1 2 4 8; do
+for n in ${NLIST:-1 2 4 8}; do
   [ $n -gt $MAXN ] && break
   if [ $n -eq 1 ]; then
     python bench.py --gpus 1 --steps $STEPS --warmup 5 --no-cpu-baseline > gpurun_out/scale_$n.json 2> gpurun_out/scale_$n.err
