@@ -637,6 +637,7 @@ def run_b200(args):
                                   "lexsort": build_marks["lexsort"]},
                 "build_wall_s": build_marks["wall_s"]}
             line["e2e_full_vector"] = e2e_full_vector(args, torch, D, pop, state, N, P)
+            line["e2e_dropin"] = e2e_dropin(args, torch, D, pop, state, N, P)
             if not args.no_cpu_baseline:
                 line["cpu_baseline"] = cpu_baseline(args, pop, state, N, P, torch, D)
         print_line = line
@@ -651,6 +652,34 @@ def run_b200(args):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def e2e_dropin(args, torch, D, pop, state, N, P):
+    """The ZERO-EDIT drop-in: mitre_b200.efficient_likelihoods.likelihoods_of_all_options with the reference's
+    exact arguments (efficient_likelihoods.pyx:15-21) -- a float64[P', N] truth matrix in pageable host memory
+    in, float64[P'] out -- on the first 8 Mi candidates of the benchmarked table (2.3 GB of float64 rows)."""
+    from mitre_b200 import efficient_likelihoods as EL
+    n = int(min(P, 8 << 20))
+    rows = D.unpack_rows(pop.packed_truth[:n], N).cpu().numpy()
+    opts = (rows * state["mask"]).astype(np.float64)                  # logit_rules.py:214-217
+    del rows
+    z = state["kappa"] / state["omega"]
+    EL.likelihoods_of_all_options(state["X"], state["omega"], z, opts[:4096], SIGMA2)
+    best, out = None, None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        out = EL.likelihoods_of_all_options(state["X"], state["omega"], z, opts, SIGMA2)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    dm = torch.as_tensor(D.pack_mask(state["mask"]), device=pop.packed_truth.device)
+    want, _ = D.score_all(pop.packed_truth[:n].contiguous(), N, state["X"], state["omega"], state["kappa"], SIGMA2,
+                          mask=dm)
+    w = want.cpu().numpy()
+    rel = float(np.max(np.abs(w - out) / np.abs(w)))      # not bit-equal: the entry receives z = kappa / omega
+    return {"what": "efficient_likelihoods.likelihoods_of_all_options(X, omega, z, float64[P', N], sigma2) -> "
+                    "float64[P'], host arrays in and out (rows packed to bits on the host, 8 B/candidate over PCIe)",
+            "candidates": n, "value": n / best, "unit": UNIT, "ms": 1e3 * best,
+            "host_bytes_read_per_candidate": 8 * N, "max_rel_diff_vs_device_path": rel}
 
 
 def e2e_full_vector(args, torch, D, pop, state, N, P):

@@ -1,5 +1,6 @@
 // lib.cu -- library plumbing: version / errors / device info, row packing kernels, and the
 // host-pointer compatibility entry with the reference's exact argument list.
+#include <emmintrin.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -163,91 +164,129 @@ extern "C" int mitre_unpack_rows_u8(void *stream, const uint64_t *packed, int64_
 }
 
 // ---- host-pointer compatibility entry -------------------------------------------------------------
-// Same arguments as efficient_likelihoods.likelihoods_of_all_options (pyx:15-21).  The float64
-// truth matrix is staged through two pinned buffers so that the H2D copy of chunk c+1 overlaps
-// packing + scoring of chunk c.
-// ---- drop-in host entry ------------------------------------------------------------------------
-// Staging resources live for the life of the process: allocating two 64 MiB pinned buffers and the
-// device buffers on every call cost more than the transfer itself (165 ms per call for a 560 MB
-// truth matrix before; cudaMallocHost alone is tens of milliseconds).
+// Same arguments as efficient_likelihoods.likelihoods_of_all_options (pyx:15-21): the caller hands over
+// the float64[P, N] truth matrix the reference builds on every sweep (logit_rules.py:214-217), 8 N bytes
+// per candidate, in pageable host memory.  Sending that over PCIe (15 GB/s from pageable memory) made
+// this entry no faster than the reference itself; the rows are therefore packed to bits ON THE HOST
+// (SSE2 compares, a few threads over row blocks, bound by reading the matrix from host DRAM) and only
+// 8 W64 bytes per candidate cross the bus.  Two pinned staging sets alternate: packing of chunk c + 1
+// overlaps the copies and the kernel of chunk c.  Staging resources live for the life of the process.
 namespace {
 
 struct HostStage {
     std::mutex lock;
     int device = -1;
-    int64_t chunk_elems = 0;      // float64 elements per staging buffer
-    int64_t chunk_rows = 0, words = 0;
-    size_t ws_bytes = 0;
+    int64_t chunk_rows = 0;
+    int W64 = 0;
+    size_t ws_bytes = 0, small_elems = 0;
     cudaStream_t st[2] = {nullptr, nullptr};
-    double *d_truth[2] = {nullptr, nullptr}, *d_out[2] = {nullptr, nullptr}, *h_stage[2] = {nullptr, nullptr};
-    uint64_t *d_packed[2] = {nullptr, nullptr};
+    cudaEvent_t inputs_ready = nullptr;
+    uint64_t *h_packed[2] = {nullptr, nullptr}, *d_packed[2] = {nullptr, nullptr};
+    double *h_out[2] = {nullptr, nullptr}, *d_out[2] = {nullptr, nullptr};
     void *d_ws[2] = {nullptr, nullptr};
-    double *d_small = nullptr;    // X, omega, kappa
-    size_t small_elems = 0;
-    int32_t *d_status = nullptr;
+    double *h_small = nullptr, *d_small = nullptr;    // X, omega, kappa
+    int32_t *d_status = nullptr, *h_status = nullptr;
 
     void release()
     {
         for (int b = 0; b < 2; ++b) {
             if (st[b]) cudaStreamDestroy(st[b]);
-            cudaFree(d_truth[b]); cudaFree(d_packed[b]); cudaFree(d_out[b]); cudaFree(d_ws[b]);
-            if (h_stage[b]) cudaFreeHost(h_stage[b]);
-            st[b] = nullptr; d_truth[b] = d_out[b] = h_stage[b] = nullptr; d_packed[b] = nullptr; d_ws[b] = nullptr;
+            cudaFree(d_packed[b]); cudaFree(d_out[b]); cudaFree(d_ws[b]);
+            if (h_packed[b]) cudaFreeHost(h_packed[b]);
+            if (h_out[b]) cudaFreeHost(h_out[b]);
+            st[b] = nullptr; d_packed[b] = h_packed[b] = nullptr; d_out[b] = h_out[b] = nullptr; d_ws[b] = nullptr;
         }
+        if (inputs_ready) cudaEventDestroy(inputs_ready);
+        inputs_ready = nullptr;
         cudaFree(d_small); cudaFree(d_status);
-        d_small = nullptr; d_status = nullptr;
-        chunk_elems = chunk_rows = words = 0; ws_bytes = 0; small_elems = 0; device = -1;
+        if (h_small) cudaFreeHost(h_small);
+        if (h_status) cudaFreeHost(h_status);
+        d_small = h_small = nullptr; d_status = h_status = nullptr;
+        chunk_rows = 0; W64 = 0; ws_bytes = 0; small_elems = 0; device = -1;
     }
 
-    // (re)allocate so that `rows` rows of N float64, W64 packed words, `ws` workspace bytes and
-    // `small` doubles of sweep inputs fit
-    cudaError_t ensure(int64_t rows, int N, int W64, size_t ws, size_t small)
+    cudaError_t ensure(int64_t rows, int w64, size_t ws, size_t small)
     {
         int dev = 0;
         cudaError_t e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return e;
-        const int64_t elems = rows * N;
-        if (dev == device && elems <= chunk_elems && rows <= chunk_rows && (int64_t)rows * W64 <= words &&
-            ws <= ws_bytes && small <= small_elems)
+        if (dev == device && rows <= chunk_rows && w64 <= W64 && ws <= ws_bytes && small <= small_elems)
             return cudaSuccess;
         release();
         device = dev;
         for (int b = 0; b < 2; ++b) {
             if ((e = cudaStreamCreateWithFlags(&st[b], cudaStreamNonBlocking)) != cudaSuccess) return e;
-            if ((e = cudaMalloc(&d_truth[b], sizeof(double) * elems)) != cudaSuccess) return e;
-            if ((e = cudaMalloc(&d_packed[b], sizeof(uint64_t) * rows * W64)) != cudaSuccess) return e;
+            if ((e = cudaMalloc(&d_packed[b], sizeof(uint64_t) * rows * w64)) != cudaSuccess) return e;
             if ((e = cudaMalloc(&d_out[b], sizeof(double) * rows)) != cudaSuccess) return e;
             if ((e = cudaMalloc(&d_ws[b], ws)) != cudaSuccess) return e;
-            if ((e = cudaMallocHost(&h_stage[b], sizeof(double) * elems)) != cudaSuccess) return e;
+            if ((e = cudaMallocHost(&h_packed[b], sizeof(uint64_t) * rows * w64)) != cudaSuccess) return e;
+            if ((e = cudaMallocHost(&h_out[b], sizeof(double) * rows)) != cudaSuccess) return e;
         }
+        if ((e = cudaEventCreateWithFlags(&inputs_ready, cudaEventDisableTiming)) != cudaSuccess) return e;
         if ((e = cudaMalloc(&d_small, sizeof(double) * small)) != cudaSuccess) return e;
+        if ((e = cudaMallocHost(&h_small, sizeof(double) * small)) != cudaSuccess) return e;
         if ((e = cudaMalloc(&d_status, sizeof(int32_t))) != cudaSuccess) return e;
-        chunk_elems = elems; chunk_rows = rows; words = rows * W64; ws_bytes = ws; small_elems = small;
+        if ((e = cudaMallocHost(&h_status, sizeof(int32_t))) != cudaSuccess) return e;
+        chunk_rows = rows; W64 = w64; ws_bytes = ws; small_elems = small;
         return cudaSuccess;
     }
 };
 
 HostStage g_host_stage;
 
-// pageable -> pinned copy on several host threads (one thread moves ~8 GB/s; PCIe wants 50).
-// cudaMemcpyAsync straight from the pageable buffer was measured at 10.4 GB/s, this at ~15.
-void parallel_memcpy(void *dst, const void *src, size_t bytes)
+unsigned host_threads()
 {
     unsigned n = std::thread::hardware_concurrency();
-    if (n > 8) n = 8;         // 16 threads measured slower (13 vs 15 GB/s)
-    if (n < 2 || bytes < (8u << 20)) {
-        memcpy(dst, src, bytes);
+    if (n > 16) n = 16;
+    return n < 1 ? 1 : n;
+}
+
+template <class F>
+void parallel_rows(int64_t rows, int64_t min_rows_per_thread, F f)
+{
+    unsigned n = host_threads();
+    if ((int64_t)n * min_rows_per_thread > rows) n = (unsigned)(rows / min_rows_per_thread);
+    if (n < 2) {
+        f((int64_t)0, rows);
         return;
     }
-    const size_t piece = ((bytes / n) + 4095) & ~(size_t)4095;
+    const int64_t piece = (rows + n - 1) / n;
     std::vector<std::thread> workers;
     for (unsigned t = 0; t < n; ++t) {
-        const size_t off = (size_t)t * piece;
-        if (off >= bytes) break;
-        const size_t len = (off + piece <= bytes) ? piece : bytes - off;
-        workers.emplace_back([=] { memcpy((char *)dst + off, (const char *)src + off, len); });
+        const int64_t lo = (int64_t)t * piece, hi = (lo + piece < rows) ? lo + piece : rows;
+        if (lo >= hi) break;
+        workers.emplace_back([=] { f(lo, hi); });
     }
     for (auto &w : workers) w.join();
+}
+
+// float64[rows, N] (non-zero = True) -> packed uint64[rows, W64]; subject i at bit 63 - i % 64 of word i / 64
+void pack_rows_host(const double *truth, int64_t rows, int N, int W64, uint64_t *packed)
+{
+    parallel_rows(rows, 4096, [=](int64_t lo, int64_t hi) {
+        const __m128d zero = _mm_setzero_pd();
+        for (int64_t r = lo; r < hi; ++r) {
+            const double *x = truth + r * N;
+            uint64_t *out = packed + r * W64;
+            for (int w = 0; w < W64; ++w) {
+                const int i0 = w * 64, n = (N - i0 < 64) ? (N - i0) : 64;
+                uint64_t word = 0;
+                int i = 0;
+                for (; i + 2 <= n; i += 2) {
+                    const unsigned m = (unsigned)_mm_movemask_pd(_mm_cmpneq_pd(_mm_loadu_pd(x + i0 + i), zero));
+                    // bit 0 of m = element i, bit 1 = element i + 1; element i goes to bit 63 - i
+                    word |= ((uint64_t)(m & 1u) << (63 - i)) | ((uint64_t)(m >> 1) << (62 - i));
+                }
+                if (i < n && x[i0 + i] != 0.0) word |= 1ull << (63 - i);
+                out[w] = word;
+            }
+        }
+    });
+}
+
+void copy_rows_host(double *dst, const double *src, int64_t count)
+{
+    parallel_rows(count, 1 << 18, [=](int64_t lo, int64_t hi) { memcpy(dst + lo, src + lo, sizeof(double) * (hi - lo)); });
 }
 
 }  // namespace
@@ -261,15 +300,14 @@ extern "C" int mitre_score_all_host(const double *X_host, const double *omega_ho
     if (p > MITRE_MAX_P) return MITRE_ERR_UNSUPPORTED;
     const int W64 = words_for(N);
     const size_t ws_bytes = mitre_score_workspace_bytes(N, p);
-    // chunk: ~64 MiB of float64 rows
-    int64_t chunk = (64ll << 20) / ((int64_t)N * 8);
+    // chunk: 8 Mi rows (64 MiB of packed rows at N <= 64), fewer for wide rows
+    int64_t chunk = (64ll << 20) / ((int64_t)W64 * 8);
     if (chunk < 1024) chunk = 1024;
     if (chunk > P) chunk = P > 0 ? P : 1;
 
     std::lock_guard<std::mutex> guard(g_host_stage.lock);
     HostStage &hs = g_host_stage;
     int rc = MITRE_OK;
-    int32_t h_status = 0;
 #define TRY(expr)                                   \
     do {                                            \
         cudaError_t _e = (expr);                    \
@@ -281,42 +319,48 @@ extern "C" int mitre_score_all_host(const double *X_host, const double *omega_ho
         if (rc != MITRE_OK) { cudaDeviceSynchronize(); return rc; } \
     } while (0)
     const size_t small = (size_t)N * p + 2 * (size_t)N;
-    TRY(hs.ensure(chunk, N, W64, ws_bytes, small));
+    TRY(hs.ensure(chunk, W64, ws_bytes, small));
     double *d_X = hs.d_small, *d_omega = d_X + (size_t)N * p, *d_kappa = d_omega + N;
+    // sweep inputs and the cleared status word: stream-ordered on st[0] from pinned memory; st[1] waits for
+    // them through an event (the streams are non-blocking: nothing orders them against the default stream)
+    memcpy(hs.h_small, X_host, sizeof(double) * N * p);
+    memcpy(hs.h_small + (size_t)N * p, omega_host, sizeof(double) * N);
+    for (int i = 0; i < N; ++i) hs.h_small[(size_t)N * p + N + i] = response_host[i] * omega_host[i];  // z = kappa/omega
+    TRY(cudaMemcpyAsync(hs.d_small, hs.h_small, sizeof(double) * small, cudaMemcpyHostToDevice, hs.st[0]));
+    TRY(cudaMemsetAsync(hs.d_status, 0, sizeof(int32_t), hs.st[0]));
+    TRY(cudaEventRecord(hs.inputs_ready, hs.st[0]));
+    TRY(cudaStreamWaitEvent(hs.st[1], hs.inputs_ready, 0));
     {
-        std::vector<double> h_small(small);
-        memcpy(h_small.data(), X_host, sizeof(double) * N * p);
-        memcpy(h_small.data() + (size_t)N * p, omega_host, sizeof(double) * N);
-        for (int i = 0; i < N; ++i) h_small[(size_t)N * p + N + i] = response_host[i] * omega_host[i];  // z = kappa/omega
-        TRY(cudaMemcpy(hs.d_small, h_small.data(), sizeof(double) * small, cudaMemcpyHostToDevice));
-        TRY(cudaMemset(hs.d_status, 0, sizeof(int32_t)));
-    }
-    {
+        int64_t start_of[2] = {0, 0}, rows_of[2] = {0, 0};     // chunk whose result sits in h_out[b]
         int64_t done = 0;
         int b = 0;
-        // out copies land directly in the caller's (pageable) buffer after each chunk's sync
         while (done < P) {
             const int64_t n = (P - done < chunk) ? (P - done) : chunk;
-            TRY(cudaStreamSynchronize(hs.st[b]));  // previous use of this buffer pair finished
-            parallel_memcpy(hs.h_stage[b], truth_host + done * N, sizeof(double) * n * N);
-            TRY(cudaMemcpyAsync(hs.d_truth[b], hs.h_stage[b], sizeof(double) * n * N, cudaMemcpyHostToDevice,
+            TRY(cudaStreamSynchronize(hs.st[b]));              // the chunk that used this staging set is complete
+            if (rows_of[b]) copy_rows_host(out_host + start_of[b], hs.h_out[b], rows_of[b]);
+            pack_rows_host(truth_host + done * N, n, N, W64, hs.h_packed[b]);   // overlaps the other set's GPU work
+            TRY(cudaMemcpyAsync(hs.d_packed[b], hs.h_packed[b], sizeof(uint64_t) * n * W64, cudaMemcpyHostToDevice,
                                 hs.st[b]));
-            TRYRC(mitre_pack_rows_f64(hs.st[b], hs.d_truth[b], n, N, hs.d_packed[b]));
             TRYRC(mitre_score_all(hs.st[b], hs.d_packed[b], n, W64, nullptr, d_X, d_omega, d_kappa, N, p, sigma2,
                                   hs.d_ws[b], ws_bytes, hs.d_out[b], hs.d_status));
-            TRY(cudaMemcpyAsync(out_host + done, hs.d_out[b], sizeof(double) * n, cudaMemcpyDeviceToHost, hs.st[b]));
+            TRY(cudaMemcpyAsync(hs.h_out[b], hs.d_out[b], sizeof(double) * n, cudaMemcpyDeviceToHost, hs.st[b]));
+            start_of[b] = done;
+            rows_of[b] = n;
             done += n;
             b ^= 1;
         }
-        TRY(cudaStreamSynchronize(hs.st[0]));
-        TRY(cudaStreamSynchronize(hs.st[1]));
+        for (int k = 0; k < 2; ++k, b ^= 1) {
+            TRY(cudaStreamSynchronize(hs.st[b]));
+            if (rows_of[b]) copy_rows_host(out_host + start_of[b], hs.h_out[b], rows_of[b]);
+            rows_of[b] = 0;
+        }
         if (P == 0) {
             TRYRC(mitre_score_all(hs.st[0], nullptr, 0, W64, nullptr, d_X, d_omega, d_kappa, N, p, sigma2, hs.d_ws[0],
                                   ws_bytes, nullptr, hs.d_status));
-            TRY(cudaStreamSynchronize(hs.st[0]));
         }
-        TRY(cudaMemcpy(&h_status, hs.d_status, sizeof(int32_t), cudaMemcpyDeviceToHost));
-        if (h_status & (MITRE_STATUS_BASE_NOT_PD | MITRE_STATUS_BAD_SCHUR)) rc = MITRE_ERR_NOT_PD;
+        TRY(cudaMemcpyAsync(hs.h_status, hs.d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, hs.st[0]));
+        TRY(cudaStreamSynchronize(hs.st[0]));
+        if (*hs.h_status & (MITRE_STATUS_BASE_NOT_PD | MITRE_STATUS_BAD_SCHUR)) rc = MITRE_ERR_NOT_PD;
     }
 #undef TRY
 #undef TRYRC

@@ -5,8 +5,8 @@
                                prior_coefficient_variance) -> float64[P]
 
 Same signature and return value as efficient_likelihoods.pyx:15-21,169; host ndarrays in, host
-ndarray out.  The work is done by mitre_score_all_host in libmitre_b200.so (pack + score on the
-GPU).  A failed Cholesky raises numpy.linalg.LinAlgError like np.linalg.cholesky does at
+ndarray out.  The work is done by mitre_score_all_host in libmitre_b200.so (rows packed to bits on
+the host, 8 bytes per candidate over PCIe, scored on the GPU).  A failed Cholesky raises numpy.linalg.LinAlgError like np.linalg.cholesky does at
 pyx:42.  The model-level path (mitre_b200.logit_rules) never builds the float64[P, N] array this
 signature requires; it scores the device-resident packed table directly.
 """
@@ -33,7 +33,7 @@ def likelihoods_of_all_options(X, omega, response, list_of_truth_vectors,
     P = tv.shape[0]
     if tv.shape[1] != N or omega.shape[0] != N or response.shape[0] != N:
         raise ValueError('inconsistent shapes')
-    out = np.zeros(P, dtype=np.float64)
+    out = np.empty(P, dtype=np.float64)
     rc = lib().mitre_score_all_host(_dp(X), _dp(omega), _dp(response), _dp(tv),
                                     float(prior_coefficient_variance), N, p, P, _dp(out))
     if rc == MITRE_ERR_NOT_PD:

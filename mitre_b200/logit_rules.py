@@ -697,10 +697,12 @@ class LogisticRuleSampler(RuleListSampler):
         if 'draw' not in st:
             st['draw'] = D.DrawBuffers(max(len(self.model.rule_population), 1))
         token = self._with_sparse(d_b, deltas) if deltas else None
-        u = np.random.rand()
-        idx = D.draw_index(d_a, d_b, u, stabilise=False, buffers=st['draw'])
-        k = int(D.read_with_status(idx, status)[0]) if status is not None else int(idx.item())
-        self._restore(d_b, token)
+        try:
+            u = np.random.rand()
+            idx = D.draw_index(d_a, d_b, u, stabilise=False, buffers=st['draw'])
+            k = int(D.read_with_status(idx, status)[0]) if status is not None else int(idx.item())
+        finally:
+            self._restore(d_b, token)     # also when the status word raises LinAlgError
         return min(k, d_a.shape[0] - 1)
 
     def _device_gibbs_draw(self, rule_list, i, j, base_counts):
@@ -708,10 +710,21 @@ class LogisticRuleSampler(RuleListSampler):
         (logit_rules.py:861-862) assembled and drawn on the device."""
         from . import device as D
         d_prior = self.model.flat_prior_device(self.current_state)
-        out, status = self.model.likelihoods_of_all_options_device(rule_list, self.current_state.omega, i, j)
         deltas = {k: -1.0 * gammaln(n + 1 + 1) + np.log(1.0 + n) for k, n in base_counts.items()
                   if k is not None and k >= 0}
-        return self._device_draw(out, d_prior, deltas, status=status)     # index and status in one read
+        # the sparse terms go into the prior BEFORE the sweep: the scoring launch then leaves the per-tile
+        # (max, sum-exp) pairs of exactly the weights the draw needs, and the draw makes no pass over them
+        token = self._with_sparse(d_prior, deltas) if deltas else None
+        try:
+            out, status, _stats = self.model.likelihoods_with_stats_device(
+                rule_list, self.current_state.omega, i, j, d_prior)
+            u = np.random.rand()
+            st = self.model._dev()
+            idx = D.draw_index(out, d_prior, u, stabilise=False, buffers=st['draw'], reuse_tiles=True)
+            k = int(D.read_with_status(idx, status)[0])                   # index and status in one read
+        finally:
+            self._restore(d_prior, token)
+        return min(k, out.shape[0] - 1)
 
     def add_remove(self):
         if np.random.rand() < 0.5:

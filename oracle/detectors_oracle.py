@@ -202,10 +202,10 @@ def pack_rows(truth):
     rules.py:450).  Test helper for comparing with the device layout (include/mitre_b200.h)."""
     P, N = truth.shape
     W = (N + 63) // 64
-    out = np.zeros((P, W), dtype=np.uint64)
-    for i in range(N):
-        out[:, i // 64] |= truth[:, i].astype(np.uint64) << np.uint64(63 - (i % 64))
-    return out
+    padded = np.zeros((P, W * 64), dtype=bool)
+    padded[:, :N] = truth
+    # big-endian bits within bytes, big-endian bytes within words: subject 0 is the word's top bit
+    return np.packbits(padded, axis=1).view('>u8').astype(np.uint64).reshape(P, W)
 
 
 def unpack_rows(packed, N):

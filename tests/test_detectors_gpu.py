@@ -344,3 +344,57 @@ def test_slope_guard_flags_near_ties_and_nothing_else(fused):
     assert np.array_equal(flags, _criterion(vals, gtype))
     for g in np.nonzero(~flags)[0]:
         assert _group_rows(vals[g]) == _group_rows(ref["values"][g]), g
+
+
+def test_s3_shape_population_vs_oracle():
+    """BASELINE configs[2] shape (N = 2000 subjects, T = 50 samples, 12 intervals, t <= 180): the N > 64
+    path end to end -- TMA-staged values kernel, block-wide threshold sort, rank-plane row kernel, 250-pass
+    multi-word lexsort -- against the oracle for 4 variables and the 5-interval windows.  The permutation is
+    checked without running np.lexsort over 2000 keys: the device order must (a) carry exactly the
+    oracle's rows, (b) be lexicographically non-decreasing with subject 0 most significant and (c) keep
+    enumeration order among equal rows; a stable sort is unique, so that IS np.lexsort's permutation."""
+    shape = dict(synthetic.SHAPES["S3"], V=4)
+    d = synthetic.make_series(seed=5, allow_constant=False, **shape)   # whole-table comparison: no constant series
+    N = len(d["X"])
+    assert N == 2000 and all(len(t) == 50 for t in d["T"])
+    cfg = dict(tmin=140.0, N_intervals=12, tmax=180.0)
+    data, pop = build_gpu_population(d, cfg, False)
+    windows, ok_slope = DO.enumerate_windows(d["T"], d["experiment_start"], d["experiment_end"], 12, 140.0, 180.0)
+    assert len(windows) == 8 and all(ok_slope)
+    assert np.array_equal(np.array(pop.windows), np.array(windows))
+    groups = DO.calculate_values(d["X"], d["T"], windows, ok_slope)
+    gold_values = np.vstack([g[3] for g in groups])
+    gtype = np.array([g[2] for g in groups])
+    vals = pop._values.cpu().numpy()
+    assert np.array_equal(vals[gtype == 1], gold_values[gtype == 1]), "window means must be bit-exact"
+    scale = np.abs(gold_values[gtype == 0]).max(axis=1, keepdims=True)
+    assert np.max(np.abs(vals[gtype == 0] - gold_values[gtype == 0]) / scale) < 1e-9
+    prim = DO.enumerate_primitives(groups, N)
+    flags = pop._slope_flags.cpu().numpy().astype(bool)
+    assert np.array_equal(flags, _criterion(vals, gtype))
+    assert not flags.any(), "this seed has no near-tie: the whole table must be the oracle's"
+    # thresholds and K per group (slope thresholds to 1e-9: different slope arithmetic, same order)
+    assert np.array_equal(pop._K_host, prim["K"])
+    thr = pop._thresholds.cpu().numpy()
+    off = 0
+    for g, k in enumerate(prim["K"]):
+        want = prim["thresholds"][off:off + k]
+        if gtype[g] == 1:
+            assert np.array_equal(thr[g, :k], want)
+        else:
+            assert np.max(np.abs(thr[g, :k] - want)) <= 1e-9 * np.abs(want).max()
+        off += k
+    rows_enum = DO.pack_rows(prim["truth"])
+    P = rows_enum.shape[0]
+    assert len(pop) == P
+    perm = pop._perm_host()
+    got = pop.packed_truth.cpu().numpy().view(np.uint64)
+    assert np.array_equal(np.sort(perm), np.arange(P))
+    assert np.array_equal(got, rows_enum[perm]), "sorted table must carry the oracle's rows, bit for bit"
+    a, b = got[:-1], got[1:]
+    diff = a != b
+    differs = diff.any(axis=1)
+    first = diff.argmax(axis=1)
+    i = np.nonzero(differs)[0]
+    assert np.all(b[i, first[i]] > a[i, first[i]]), "rows must be lexicographically non-decreasing"
+    assert np.all(perm[1:][~differs] > perm[:-1][~differs]), "equal rows must keep enumeration order"
