@@ -200,7 +200,9 @@ class LogisticRuleModel(object):
                            mask=dmask, buffers=st['buffers'])
 
     def likelihoods_of_all_options(self, rl, current_omega, i, j, N_workers=None):
-        """logit_rules.py:186-229: host ndarray[P] out (a view of a reused pinned buffer)."""
+        """logit_rules.py:186-229: host ndarray[P] out.  NOTE: the array is a VIEW of a reused pinned
+        staging buffer -- the next call overwrites it (the reference returns a fresh array; copying
+        2.35 GB per sweep at S5 would cost more than the sweep).  Callers that keep it must .copy()."""
         import torch
         from . import device as D
         out, status = self.likelihoods_of_all_options_device(rl, current_omega, i, j)
@@ -303,7 +305,7 @@ class LogisticRuleModel(object):
         primitives (identical up to summation order)."""
         pop = self.rule_population
         key = (state.phylogeny_mean, state.phylogeny_std, state.window_concentration,
-               state.window_typical_fraction, id(pop._filter_map), pop.n_primitives)
+               state.window_typical_fraction, pop._filter_generation, pop.n_primitives, pop._build_generation)
         cache = self.__dict__.setdefault('_prior_table_cache', [])
         for k, v in cache:
             if k == key:
@@ -334,7 +336,7 @@ class LogisticRuleModel(object):
     def _prior_count_matrix(self):
         """float64[W, V]: active primitives per (window, variable), both detector types together."""
         pop = self.rule_population
-        key = (id(pop._filter_map), pop.n_primitives, id(pop._K_host))
+        key = (pop._filter_generation, pop.n_primitives, pop._build_generation)
         cached = self.__dict__.get('_prior_count_cache')
         if cached is not None and cached[0] == key:
             return cached[1]
@@ -349,7 +351,7 @@ class LogisticRuleModel(object):
         from . import device as D
         pop = self.rule_population
         key = (state.phylogeny_mean, state.phylogeny_std, state.window_concentration,
-               state.window_typical_fraction, id(pop._filter_map), pop.n_primitives)
+               state.window_typical_fraction, pop._filter_generation, pop.n_primitives, pop._build_generation)
         cached = self.__dict__.get('_prior_device_cache')
         if cached is not None and cached[0] == key:
             return cached[1]
@@ -383,7 +385,7 @@ class LogisticRuleModel(object):
         over the same P-vector."""
         pop = self.rule_population
         key = (state.phylogeny_mean, state.phylogeny_std, state.window_concentration,
-               state.window_typical_fraction, id(pop._filter_map), pop.n_primitives)
+               state.window_typical_fraction, pop._filter_generation, pop.n_primitives, pop._build_generation)
         cache = self.__dict__.setdefault('_flat_prior_cache', [])
         for k, v in cache:
             if k == key:

@@ -72,6 +72,11 @@ class PyPolyaGamma:
         pa = _pnorm(-w * (t * z + 1.0))
         xb = x0 - z + (math.log(pb) if pb > 0.0 else -math.inf)
         xa = x0 + z + (math.log(pa) if pa > 0.0 else -math.inf)
+        # exp(xb) overflows a double from |psi| ~ 98 on (xb ~ 0.32 z^2 - z); BayesLogit / pypolyagamma
+        # get inf there and a ratio of 0, so do we
+        m = max(xb, xa)
+        if m > 700.0:
+            return 0.0
         qdivp = 4.0 / math.pi * (math.exp(xb) + math.exp(xa))
         return 1.0 / (1.0 + qdivp)
 

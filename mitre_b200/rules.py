@@ -261,11 +261,9 @@ class DiscreteRulePopulation:
         self.tmin = tmin
         self.tmax = np.inf if tmax is None else tmax
         self.N_intervals = N_intervals
-        if max_thresholds is not None:
-            raise NotImplementedError(
-                'max_thresholds (the UPGMA threshold cap, rules.py:547-574) is not implemented '
-                'on the device path')
-        self.max_thresholds = np.inf
+        # rules.py:287-290: None = the full grid (every midpoint); a number caps the thresholds per
+        # (window, variable, type) group at that many by UPGMA clustering of the sorted values
+        self.max_thresholds = np.inf if max_thresholds is None else max_thresholds
         self.mine_rules()
         self.applied_filters = []
 
@@ -370,7 +368,8 @@ class DiscreteRulePopulation:
         N = self.data.n_subjects
         self._fused = None
         self._fused_args = None
-        if (self.use_fused and 2 <= N <= 63 and
+        capped = N > self.max_thresholds + 1        # rules.py:535: groups with more values than the cap cluster
+        if (self.use_fused and 2 <= N <= 63 and not capped and
                 ds['series_t'].shape[0] * ds['series_t'].shape[1] < 2 ** 31 - 1):
             # values + thresholds + K + padded truth rows without a host round trip (fused_detectors.cuh)
             lists = D.window_lists(ds['times'], ds['t_offsets'], self._d_windows,
@@ -416,6 +415,7 @@ class DiscreteRulePopulation:
         from . import device as D
         import torch
         N = self.data.n_subjects
+        self._build_generation = getattr(self, '_build_generation', 0) + 1    # cache key of K / row offsets
         if self._G == 0:
             self._P = 0
             self._K_host = np.zeros(0, dtype=np.int32)
@@ -433,7 +433,10 @@ class DiscreteRulePopulation:
             self._rows = None
         else:
             self._rows_padded = None
-            self._thresholds, self._K = D.detector_thresholds(self._values)
+            if N > self.max_thresholds + 1:
+                self._thresholds, self._K = self._capped_thresholds()
+            else:
+                self._thresholds, self._K = D.detector_thresholds(self._values)
             self._row_offsets = D.detector_row_offsets(self._K)
             self._row_offsets_host = self._row_offsets.cpu().numpy()
             self._K_host = self._K.cpu().numpy()
@@ -445,6 +448,20 @@ class DiscreteRulePopulation:
                 self._rows = torch.empty((0, D.words_for(N)), dtype=torch.int64, device=D.dev())
         self.truth_table = _TruthTable(self)
         self._host_cache = {}
+
+    def _capped_thresholds(self):
+        """thresholds_from_values with max_thresholds set (rules.py:533-576): UPGMA (average-linkage)
+        clustering of a group's sorted values, cut at max_thresholds + 1 clusters, thresholds midway
+        between neighbouring clusters.  This is the reference's own host computation -- the same
+        scipy.cluster.hierarchy calls on the same pairwise-distance vector -- applied to the values the
+        device computed: the clustering walks a dendrogram whose merge order hangs on floating-point
+        ties that only scipy's own Lance-Williams updates reproduce, and with the cap in force the table
+        is small (at most 2 * max_thresholds rows per group), so the host pass is not the cost.  Values,
+        truth rows, the lexsort and everything downstream stay on the device."""
+        import torch
+        from . import device as D
+        thresholds, K = capped_thresholds_host(self._values.cpu().numpy(), self.max_thresholds)
+        return torch.as_tensor(thresholds, device=D.dev()), torch.as_tensor(K, device=D.dev())
 
     # -- step 4 (rules.py:439-462) ------------------------------------------------------------------------
     def sort_base_rules(self):
@@ -559,6 +576,7 @@ class DiscreteRulePopulation:
     # -- filters (rules.py:602-629) -----------------------------------------------------------------------
     def reset_filter(self):
         self._filter_map = None          # positions (base order) of the active primitives
+        self._filter_generation = getattr(self, '_filter_generation', 0) + 1   # cache key (id() can be reused)
         self._active_rows = self._sorted_rows
         self.flat_rules = _FlatRules(self)
         self.n_primitives = self._P
@@ -576,6 +594,7 @@ class DiscreteRulePopulation:
         if keep.shape[0] != current.shape[0]:
             raise ValueError('filter index must match the active population')
         self._filter_map = current[keep]
+        self._filter_generation = getattr(self, '_filter_generation', 0) + 1
         inv = -np.ones(self._P, dtype=np.int64)
         inv[self._filter_map] = np.arange(len(self._filter_map))
         idx = torch.as_tensor(self._filter_map, device=self._sorted_rows.device)
@@ -595,7 +614,7 @@ class DiscreteRulePopulation:
         from . import device as D
         import torch
         c = self._host_cache
-        key = ('row_group_dev', id(self._filter_map))
+        key = ('row_group_dev', self._filter_generation)
         if key not in c:
             if self._P == 0:
                 base = torch.empty(0, dtype=torch.int32, device=D.dev())
@@ -620,7 +639,7 @@ class DiscreteRulePopulation:
     def group_counts(self):
         """int64[G]: number of active primitives in every group (2 K_g unless filtered)."""
         c = self._host_cache
-        key = ('group_counts', id(self._filter_map))
+        key = ('group_counts', self._filter_generation)
         if key not in c:
             if self._filter_map is None:
                 c[key] = 2 * self._K_host.astype(np.int64)
@@ -675,6 +694,26 @@ class DiscreteRulePopulation:
 
     def __len__(self):
         return self.n_primitives
+
+
+def capped_thresholds_host(values, max_thresholds):
+    """rules.py:533-576 for every row of values float64[G, N] (N > max_thresholds + 1): returns
+    (thresholds float64[G, N-1] zero-padded, K int32[G])."""
+    from scipy.cluster import hierarchy
+    G, N = values.shape
+    n_clusters = int(min(max_thresholds + 1, N))
+    iu, ju = np.triu_indices(N, k=1)               # pair order of rules.py:548-551
+    thresholds = np.zeros((G, max(N - 1, 0)), dtype=np.float64)
+    K = np.zeros(G, dtype=np.int32)
+    for g in range(G):
+        v = np.sort(values[g])
+        linkage = hierarchy.linkage(v[ju] - v[iu], method='average')
+        clusters = hierarchy.fcluster(linkage, n_clusters, criterion='maxclust')
+        boundaries = clusters[:-1] != clusters[1:]
+        t = np.unique(0.5 * (v[:-1][boundaries] + v[1:][boundaries]))
+        K[g] = len(t)
+        thresholds[g, :len(t)] = t
+    return thresholds, K
 
 
 def _unpack_words(words, N):

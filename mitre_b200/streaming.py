@@ -250,7 +250,9 @@ class StreamingSweep:
         pairs = torch.zeros((n_tiles, 2), dtype=torch.float64, device=D.dev())
         pairs[:, 0] = -np.inf
         counts = torch.zeros(n_tiles, dtype=torch.int64, device=D.dev())
-        status_all = None
+        # one status word for the whole sweep (the per-tile buffers may be reallocated on the way), raised
+        # on EVERY rank AFTER the collectives: a rank that raised before them would leave the others blocked
+        status_all = torch.zeros(1, dtype=torch.int32, device=D.dev())
         for t in range(self.rank, n_tiles, self.ws):          # tiles are dealt round-robin to the ranks
             tile = self.build_tile(t)
             counts[t] = tile['P']
@@ -258,16 +260,17 @@ class StreamingSweep:
                 continue
             out, status, stats = self._weights_tile(tile, X, omega, kappa, sigma2, mask, prior_tables, deltas)
             pairs[t] = stats
-            status_all = status
+            status_all |= status
+            status.zero_()
             del tile, out
-        if status_all is not None:
-            D.raise_on_status(status_all)
         if self.ws > 1:
             # the sweep's only exchange: 16 bytes per tile (every rank ends up with every tile's pair)
             gathered = torch.empty((self.ws, n_tiles, 2), dtype=torch.float64, device=D.dev())
             dist.all_gather_into_tensor(gathered, pairs, group=self.group)
             pairs = combine_tile_pairs(gathered)
             dist.all_reduce(counts, group=self.group)
+            dist.all_reduce(status_all, op=dist.ReduceOp.MAX, group=self.group)
+        D.raise_on_status(status_all)
         self.tile_stats = pairs.cpu().numpy()
         self.tile_counts = counts.cpu().numpy()
         _, _, log_total = owner_of_marker(self.tile_stats, 0.5)

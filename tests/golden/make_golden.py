@@ -57,6 +57,16 @@ DIVERGENT_CASES = {
                            pop=dict(tmin=1.0, N_intervals=2, tmax=None)),
 }
 
+# max_thresholds (rules.py:533-576): the UPGMA threshold cap, the reference's own worked example uses 10
+# (logit_rule_test.py:18).  Separate from DETECTOR_CASES because only the default and the phase-by-phase
+# variants of the device path apply (the fused kernels emit the full grid).
+CAPPED_CASES = {
+    "det_maxthr10": dict(series=dict(N=35, V=5, T=(6, 14), span=(0.0, 100.0), seed=31, zero_fraction=0.2),
+                         pop=dict(tmin=1.0, N_intervals=4, tmax=None, max_thresholds=10)),
+    "det_maxthr3_n100": dict(series=dict(N=100, V=3, T=(4, 8), span=(0.0, 30.0), seed=32),
+                             pop=dict(tmin=1.0, N_intervals=2, tmax=None, max_thresholds=3)),
+}
+
 TYPE_INDEX = {"slope": 0, "average": 1}
 DIR_INDEX = {"above": 0, "below": 1}
 
@@ -67,7 +77,8 @@ def make_detector_case(rules, name, cfg):
     data = rules.Dataset(d["X"], d["T"], d["y"], ["v%d" % i for i in range(V)],
                          d["variable_weights"], d["experiment_start"], d["experiment_end"])
     pop = rules.DiscreteRulePopulation(None, cfg["pop"]["tmin"], cfg["pop"]["N_intervals"],
-                                       tmax=cfg["pop"]["tmax"], data=data)
+                                       tmax=cfg["pop"]["tmax"], data=data,
+                                       max_thresholds=cfg["pop"].get("max_thresholds"))
     windows = np.array(pop.windows, dtype=np.float64).reshape(-1, 2)
     wl = {tuple(w): i for i, w in enumerate(pop.windows)}
     # values in enumeration order (window-major, variable, slope/average)
@@ -176,8 +187,12 @@ DENSE_CASES = [(31, 35, 1), (32, 35, 4), (33, 40, 11), (34, 70, 6), (35, 200, 8)
 def main():
     rules = ref_shim.load_rules()
     ref = build_ref.load()
-    for name, cfg in list(DETECTOR_CASES.items()) + list(DIVERGENT_CASES.items()):
-        make_detector_case(rules, name, cfg)
+    only = sys.argv[1:]
+    for name, cfg in list(DETECTOR_CASES.items()) + list(DIVERGENT_CASES.items()) + list(CAPPED_CASES.items()):
+        if not only or name in only:
+            make_detector_case(rules, name, cfg)
+    if only:
+        return
     for name, cfg in SCORING_CASES.items():
         make_scoring_case(ref, name, cfg)
     mc = reference_mc_logpdf_np()

@@ -398,3 +398,48 @@ def test_s3_shape_population_vs_oracle():
     i = np.nonzero(differs)[0]
     assert np.all(b[i, first[i]] > a[i, first[i]]), "rows must be lexicographically non-decreasing"
     assert np.all(perm[1:][~differs] > perm[:-1][~differs]), "equal rows must keep enumeration order"
+
+
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("name", sorted(MG.CAPPED_CASES))
+def test_max_thresholds_population_vs_reference_golden(name, fused):
+    """max_thresholds (the UPGMA threshold cap of the [model] section, rules.py:533-576; the reference's
+    own worked example uses 10, logit_rule_test.py:18): windows, values, capped thresholds, truth rows,
+    lexsort order and rule descriptors against fixtures generated by the reference's rules.py."""
+    cfg = MG.CAPPED_CASES[name]
+    gold = np.load(os.path.join(GOLD, name + ".npz"))
+    d = synthetic.make_series(**cfg["series"])
+    from mitre_b200 import rules as R
+    V = d["X"][0].shape[0]
+    data = R.Dataset(d["X"], d["T"], d["y"], ["v%d" % i for i in range(V)], d["variable_weights"],
+                     d["experiment_start"], d["experiment_end"])
+    old = R.DiscreteRulePopulation.use_fused
+    R.DiscreteRulePopulation.use_fused = fused
+    try:
+        pop = R.DiscreteRulePopulation(None, cfg["pop"]["tmin"], cfg["pop"]["N_intervals"], tmax=cfg["pop"]["tmax"],
+                                       data=data, max_thresholds=cfg["pop"]["max_thresholds"])
+    finally:
+        R.DiscreteRulePopulation.use_fused = old
+    N = int(gold["n_subjects"])
+    assert int(pop._K_host.max()) <= cfg["pop"]["max_thresholds"]
+    check_population(pop, gold["windows"], gold["ok_slope"], gold["groups"], gold["values"], gold["order"],
+                     gold["sorted_truth_packed"],
+                     (gold["rule_variable"], gold["rule_window"], gold["rule_type"], gold["rule_direction"],
+                      gold["rule_threshold"]), N)
+    assert np.array_equal(pop.flat_truth, DO.unpack_rows(gold["sorted_truth_packed"], N))
+
+
+def test_model_builds_with_max_thresholds():
+    """LogisticRuleModel(..., max_thresholds=10) as in the reference's worked example (logit_rule_test.py:18)."""
+    from mitre_b200 import logit_rules as LR, rules as R
+    cfg = MG.CAPPED_CASES["det_maxthr10"]
+    d = synthetic.make_series(**cfg["series"])
+    V = d["X"][0].shape[0]
+    data = R.Dataset(d["X"], d["T"], d["y"], ["v%d" % i for i in range(V)], d["variable_weights"],
+                     d["experiment_start"], d["experiment_end"])
+    model = LR.LogisticRuleModel(data, tmin=1.0, tmax=None, N_intervals=4, max_thresholds=10)
+    pop = model.rule_population
+    assert 0 < len(pop) <= pop._G * 2 * 10
+    out = model.likelihoods_of_all_options(R.RuleList([[R.PrimitiveRule(*pop.flat_rules[0])]]),
+                                           np.full(35, 0.25), 0, 0)
+    assert out.shape == (len(pop),) and np.isfinite(out).all()

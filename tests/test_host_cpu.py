@@ -109,3 +109,31 @@ def test_fastdist_is_bit_identical_to_scipy():
     assert F.expon_logpdf(-1.0, 2.0) == scipy.stats.expon.logpdf(-1.0, scale=2.0) == -np.inf
     assert F.beta_logpdf(1.5, 2.0, 2.0) == scipy.stats.beta.logpdf(1.5, 2.0, 2.0) == -np.inf
     assert F.logsumexp(np.array([-np.inf, -np.inf])) == scipy.special.logsumexp(np.array([-np.inf, -np.inf]))
+
+
+def test_capped_thresholds_equal_the_reference_restatement():
+    """max_thresholds (rules.py:533-576): the host clustering used by the device population against the
+    oracle's restatement of thresholds_from_values, group by group, including ties and tiny groups."""
+    from mitre_b200 import rules as R
+    from oracle import detectors_oracle as DO
+    rng = np.random.RandomState(3)
+    for N, cap in [(35, 10), (12, 3), (100, 7), (9, 1), (20, 18)]:
+        values = rng.normal(size=(40, N))
+        values[3] = 0.0                                   # all tied: one cluster, no threshold
+        values[4, : N // 2] = 0.0                         # a run of ties
+        values[5] = np.round(values[5], 1)                # many ties
+        thr, K = R.capped_thresholds_host(values, cap)
+        for g in range(values.shape[0]):
+            want = DO.thresholds_from_values(values[g], cap)
+            assert K[g] == len(want) <= cap
+            assert np.array_equal(thr[g, :K[g]], want)
+
+
+def test_polyagamma_large_argument_does_not_overflow():
+    """PG(1, z) for |z| >= ~98 used to raise OverflowError in math.exp."""
+    from mitre_b200 import polyagamma
+    pg = polyagamma.PyPolyaGamma(0)
+    for z in (100.0, -500.0, 2000.0):
+        x = pg.pgdraw(1, z)
+        assert np.isfinite(x) and x > 0
+        assert abs(x - 0.5 / abs(z)) < 0.5 / abs(z)      # PG(1, z) concentrates at tanh(z/2) / (2 z)
