@@ -277,6 +277,38 @@ int mitre_detectors_fused(void *stream, const double *series_t, int64_t vstride,
                           const int8_t *task_type, int n_tasks_wt, int n_windows, int64_t G,
                           double *values, double *thresholds, int32_t *K, uint64_t *rows_padded,
                           const uint8_t *group_type, uint8_t *group_flags, int64_t *flagged);
+/* ---- walk-forward detector values (default device path, N <= 63) + stand-alone sort/emit ------------------
+ *
+ * mitre_detector_values_walk computes the same values float64[G, N] as mitre_detector_values / the values
+ * half of mitre_detectors_fused, an order of magnitude cheaper: windows are pairs (t_i, t_j) of one grid
+ * (rules.py:391-402) enumerated start-major, so the admitted windows sharing a start ("start group":
+ * windows sg_first[k] .. sg_first[k+1]-1, int32[n_sg + 1]) are prefixes of one another, and a thread per
+ * (variable, subject) walks the samples once per start group, emitting the mean (numpy's pairwise order is
+ * prefix-stable: bit-identical to np.mean) and the slope (running sums of x - x_first against t - t_i) at
+ * every window's sample count.  series float64[V, series_stride] variable-major (Dataset.device_series
+ * 'series'), times float64[S], wlo / wcnt int32[W, N] (mitre_window_ranges or mitre_window_lists), winv_sxx
+ * float64[W, N] (mitre_window_lists), wtbar float64[W, N] (mitre_window_tbar: mean of t - t0 over the
+ * window's samples), group_base / slope_ok as for mitre_detector_values.  group_flags (optional, uint8[G],
+ * caller-zeroed): constant non-zero series are flagged (slope guard band, below).  A block takes
+ * sg_per_block consecutive start groups of a tile of variables and keeps the (window, subject) tables of all
+ * their windows in shared memory: max_block_windows = the largest window count of such a run; the caller
+ * picks sg_per_block so that mitre_values_walk_smem_bytes(N, S, max_block_windows) fits the device's opt-in
+ * shared memory (else MITRE_ERR_UNSUPPORTED: use mitre_detectors_fused).
+ * mitre_detector_sort_emit is the second half of mitre_detectors_fused on its own: values -> thresholds, K,
+ * padded truth rows (+ near-tie flags into group_flags, which it does NOT clear, and the count). */
+int mitre_window_tbar(void *stream, const double *times, int N, const double *windows, int W,
+                      const int32_t *wlo, const int32_t *wcnt, double *tbar);
+size_t mitre_values_walk_smem_bytes(int N, int S, int max_block_windows);
+int mitre_detector_values_walk(void *stream, const double *series, int64_t series_stride,
+                               const double *times, const int32_t *t_offsets, int S, int N, int V,
+                               const double *windows, int W, const int32_t *wlo, const int32_t *wcnt,
+                               const double *winv_sxx, const double *wtbar, const int64_t *group_base,
+                               const uint8_t *slope_ok, const int32_t *sg_first, int n_sg,
+                               int sg_per_block, int max_block_windows, double *values, uint8_t *group_flags);
+int mitre_detector_sort_emit(void *stream, const double *values, int64_t G, int N, double *thresholds,
+                             int32_t *K, uint64_t *rows_padded, const uint8_t *group_type,
+                             uint8_t *group_flags, int64_t *flagged);
+
 /* Slope guard band.  'slope' detector values come from a closed form here and from LAPACK gelsd in the
  * reference (rules.py:110-114); the truth rows of a group depend only on the order and tie structure of
  * its N values, so they are the reference's unless (a) two neighbours of the sorted values are unequal but

@@ -72,6 +72,12 @@ SIGNATURES = {
                            [c_void_p] * 7),
     "mitre_detectors_fused": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int] + [c_void_p] * 7 +
                               [c_i64] + [c_void_p] * 4 + [c_int, c_int, c_i64] + [c_void_p] * 7),
+    "mitre_window_tbar": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "mitre_values_walk_smem_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "mitre_detector_values_walk": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_int, c_int, c_int,
+                                           c_void_p, c_int] + [c_void_p] * 7 + [c_int, c_int, c_int, c_void_p,
+                                                                                 c_void_p]),
+    "mitre_detector_sort_emit": (c_int, [c_void_p, c_void_p, c_i64, c_int] + [c_void_p] * 6),
     "mitre_slope_guard": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p, c_void_p]),
     "mitre_set_detector_split": (c_int, [c_int]),
     "mitre_selftest_divide": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p]),

@@ -146,6 +146,33 @@ static int detectors_fused_launch(void *stream, const double *series_t, int64_t 
                                   const int8_t *task_type, int n_tasks_wt, int n_windows, int64_t G,
                                   double *values, double *thresholds, int32_t *K, uint64_t *rows_padded);
 
+// sorting-network size -> translation unit
+static int nb_dispatch(cudaStream_t st, const double *series_t, int64_t vstride, int N, int V, const int32_t *wlo,
+                       const int32_t *wcnt, const int32_t *wstart, const double *winv_n, const double *winv_sxx,
+                       const int32_t *widx, const double *wdt, int64_t ld, const int64_t *group_base,
+                       const uint8_t *slope_ok, const int32_t *task_window, const int8_t *task_type, int n_tasks_wt,
+                       int64_t G, double *values, double *thresholds, int32_t *K, uint64_t *rows_padded)
+{
+    if (N <= 4) return launch_fused_nb4(st, series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
+    if (N <= 8) return launch_fused_nb8(st, series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
+    if (N <= 12) return launch_fused_nb12(st, series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
+    if (N <= 16) return launch_fused_nb16(st, series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
+    if (N <= 20) return launch_fused_nb20(st, series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
+    if (N <= 24) return launch_fused_nb24(st, series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
+    if (N <= 28) return launch_fused_nb28(st, series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
+    if (N <= 32) return launch_fused_nb32(st, series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
+    if (N <= 36) return launch_fused_nb36(st, series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
+    if (N <= 40) return launch_fused_nb40(st, series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
+    if (N <= 44) return launch_fused_nb44(st, series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
+    if (N <= 48) return launch_fused_nb48(st, series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
+    if (N <= 52) return launch_fused_nb52(st, series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
+    if (N <= 56) return launch_fused_nb56(st, series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
+    if (N <= 60) return launch_fused_nb60(st, series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
+    if (N <= 64) return launch_fused_nb64(st, series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
+    return MITRE_ERR_UNSUPPORTED;
+}
+
+
 extern "C" int mitre_detectors_fused(void *stream, const double *series_t, int64_t vstride, int N, int V,
                                      const int32_t *wlo, const int32_t *wcnt, const int32_t *wstart,
                                      const double *winv_n, const double *winv_sxx, const int32_t *widx,
@@ -246,23 +273,84 @@ static int detectors_fused_launch(void *stream, const double *series_t, int64_t 
         }
         MITRE_LAUNCH_CHECK();
     }
-    if (N <= 4) return launch_fused_nb4(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
-    if (N <= 8) return launch_fused_nb8(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
-    if (N <= 12) return launch_fused_nb12(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
-    if (N <= 16) return launch_fused_nb16(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
-    if (N <= 20) return launch_fused_nb20(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
-    if (N <= 24) return launch_fused_nb24(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
-    if (N <= 28) return launch_fused_nb28(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
-    if (N <= 32) return launch_fused_nb32(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
-    if (N <= 36) return launch_fused_nb36(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
-    if (N <= 40) return launch_fused_nb40(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
-    if (N <= 44) return launch_fused_nb44(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
-    if (N <= 48) return launch_fused_nb48(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
-    if (N <= 52) return launch_fused_nb52(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
-    if (N <= 56) return launch_fused_nb56(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
-    if (N <= 60) return launch_fused_nb60(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
-    if (N <= 64) return launch_fused_nb64(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld, group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
-    return MITRE_ERR_UNSUPPORTED;
+    return nb_dispatch(as_stream(stream), series_t, vstride, N, V, wlo, wcnt, wstart, winv_n, winv_sxx, widx, wdt, ld,
+                       group_base, slope_ok, task_window, task_type, n_tasks_wt, G, values, thresholds, K, rows_padded);
+}
+
+// ---- walk-forward values + stand-alone sort/emit (the default device path from round 2) --------------------
+extern "C" int mitre_window_tbar(void *stream, const double *times, int N, const double *windows, int W,
+                                 const int32_t *wlo, const int32_t *wcnt, double *tbar)
+{
+    if (N <= 0 || W < 0 || !times) return MITRE_ERR_INVALID;
+    if (W == 0) return MITRE_OK;
+    if (!windows || !wlo || !wcnt || !tbar) return MITRE_ERR_INVALID;
+    window_tbar_kernel<<<(W * N + 127) / 128, 128, 0, as_stream(stream)>>>(times, N, windows, W, wlo, wcnt, tbar);
+    MITRE_LAUNCH_CHECK();
+    return MITRE_OK;
+}
+
+// The block's start groups are chosen so that the (window, subject) tables of ALL its windows fit in shared
+// memory next to the series tile: sg_first is a host-visible copy is not available here, so the launcher
+// takes the window count of the fullest chunk from the caller (max_block_windows) for a given split.
+extern "C" size_t mitre_values_walk_smem_bytes(int N, int S, int max_block_windows)
+{
+    if (N <= 0 || S <= 0 || max_block_windows <= 0) return 0;
+    return sizeof(double) * walk_smem_doubles(N, S, max_block_windows);
+}
+
+extern "C" int mitre_detector_values_walk(void *stream, const double *series, int64_t series_stride,
+                                          const double *times, const int32_t *t_offsets, int S, int N, int V,
+                                          const double *windows, int W, const int32_t *wlo, const int32_t *wcnt,
+                                          const double *winv_sxx, const double *wtbar, const int64_t *group_base,
+                                          const uint8_t *slope_ok, const int32_t *sg_first, int n_sg,
+                                          int sg_per_block, int max_block_windows, double *values,
+                                          uint8_t *group_flags)
+{
+    if (N < 1 || N > kWalkMaxThreads || V <= 0 || S <= 0 || W < 0 || n_sg < 0 || series_stride < S ||
+        sg_per_block < 1 || max_block_windows < 1)
+        return MITRE_ERR_INVALID;
+    if (W == 0 || n_sg == 0) return MITRE_OK;
+    if (!series || !times || !t_offsets || !windows || !wlo || !wcnt || !winv_sxx || !wtbar || !group_base ||
+        !slope_ok || !sg_first || !values)
+        return MITRE_ERR_INVALID;
+    const size_t smem = mitre_values_walk_smem_bytes(N, S, max_block_windows);
+    if (smem > smem_optin()) return MITRE_ERR_UNSUPPORTED;
+    MITRE_CUDA_TRY(cudaFuncSetAttribute(values_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int VB = walk_vars_per_block(N);
+    const int tiles = (V + VB - 1) / VB;
+    const int chunks = (n_sg + sg_per_block - 1) / sg_per_block;
+    const int threads = ((VB * N + 31) / 32) * 32;
+    values_walk_kernel<<<dim3((unsigned)tiles, (unsigned)chunks), threads, smem, as_stream(stream)>>>(
+        series, series_stride, times, t_offsets, S, N, V, windows, wlo, wcnt, winv_sxx, wtbar, group_base, slope_ok,
+        sg_first, n_sg, sg_per_block, max_block_windows, values, group_flags);
+    MITRE_LAUNCH_CHECK();
+    return MITRE_OK;
+}
+
+extern "C" int mitre_detector_sort_emit(void *stream, const double *values, int64_t G, int N, double *thresholds,
+                                        int32_t *K, uint64_t *rows_padded, const uint8_t *group_type,
+                                        uint8_t *group_flags, int64_t *flagged)
+{
+    if (N < 2 || N > 63) return MITRE_ERR_UNSUPPORTED;
+    if (G < 0) return MITRE_ERR_INVALID;
+    if (G == 0) return MITRE_OK;
+    if (!values || !thresholds || !K || !rows_padded) return MITRE_ERR_INVALID;
+    if ((group_flags || flagged) && !group_type) return MITRE_ERR_INVALID;
+    if (flagged && !group_flags) return MITRE_ERR_INVALID;
+    // group_flags is NOT cleared here: the values kernel may already have set constant-series flags
+    if (flagged) MITRE_CUDA_TRY(cudaMemsetAsync(flagged, 0, sizeof(int64_t), as_stream(stream)));
+    const int saved = g_detector_split;
+    g_detector_split = 1;
+    g_slope_guard = (group_type && group_flags) ? SlopeGuardArgs{group_type, group_flags, nullptr}
+                                                 : SlopeGuardArgs{nullptr, nullptr, nullptr};
+    const int rc = nb_dispatch(as_stream(stream), nullptr, 0, N, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                               nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, G, const_cast<double *>(values),
+                               thresholds, K, rows_padded);
+    g_slope_guard = SlopeGuardArgs{nullptr, nullptr, nullptr};
+    g_detector_split = saved;
+    if (rc != MITRE_OK) return rc;
+    if (flagged) return launch_count_flags(as_stream(stream), group_flags, G, reinterpret_cast<unsigned long long *>(flagged));
+    return MITRE_OK;
 }
 
 extern "C" int mitre_densify_perm(void *stream, const int64_t *perm_padded, int64_t P, int N,

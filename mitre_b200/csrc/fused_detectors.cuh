@@ -304,6 +304,19 @@ __device__ __forceinline__ double div_small_int(double a, double n, double y)
     return __ddiv_rn(a, n);
 }
 
+// The same quotient with the out-of-range case behind a real branch to a cold call: the if-converted form
+// above makes every caller pay for the full IEEE divide sequence.
+static __device__ __noinline__ double div_cold(double a, double n) { return __ddiv_rn(a, n); }
+__device__ __forceinline__ double div_small_int_hot(double a, double n, double y)
+{
+    const double aa = fabs(a);
+    if (aa == 0.0) return a;                                   // +-0 / n
+    if (!(aa > 1e-280 && aa < 1e280)) return div_cold(a, n);
+    const double q = __dmul_rn(a, y);
+    const double r = __fma_rn(-q, n, a);
+    return __fma_rn(r, y, q);
+}
+
 // numpy pairwise sum of this lane's column x[0..n) staged as x[j * 32] (n <= kFusedCap <= 128)
 __device__ __forceinline__ double pw_sum_staged(const double *x, int n)
 {
@@ -832,6 +845,164 @@ values_resident_kernel(const double *__restrict__ series_t, int64_t vstride, int
             for (int i = tid; i < n_out; i += blockDim.x) out[i] = st[i];
         }
     }
+}
+
+// =================================================================================================
+// Walk-forward values kernel (default from round 2).
+//
+// Windows are all pairs (t_i, t_j) of one grid of time points (rules.py:391-402), enumerated start-major,
+// so the admitted windows that share a start t_i are consecutive ("start group") and differ only in how
+// far they reach: the samples of window (i, j + 1) are those of (i, j) plus the ones between t_j and
+// t_{j+1}.  The kernels above re-read and re-sum every window from scratch (~200 warp-instructions per
+// window x subject x 32 variables); here a thread owns one (variable, subject) pair and WALKS the
+// subject's samples once per start group, keeping running sums and emitting both detector values every
+// time the sample count reaches a window's count:
+//   'average'  numpy's pairwise summation order is prefix-stable -- for n < 8 a sequential sum; from 8
+//              on eight strided accumulators r[k] that absorb each completed block of 8, the combine
+//              ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the tail added one element at a time
+//              (pw_leaf_col above) -- so the mean of every window of the walk is bit-identical to
+//              np.mean of its own masked copy (windows beyond 128 samples take pairwise_sum_col);
+//   'slope'    with d_j = x_j - x_first and tau_j = t_j - t_i:  slope = (sum tau_j d_j - taubar sum d_j) / Sxx,
+//              taubar and 1/Sxx per (window, subject) from window tables.  Differencing against the first
+//              sample keeps a constant series at slope exactly 0.
+// Thread layout: tid = v_local * N + s, so the N subjects of a variable are consecutive lanes and every
+// emission is a coalesced store of values[g][0..N) -- no staging tile, no barrier after the tile load.
+// The tile's series (kWalk variables x S samples, variable-major) sits in shared memory; sample counts
+// differ between the lanes of a warp, so the inner while loop is divergent (each lane advances to its
+// own count) while the emissions are converged.
+// =================================================================================================
+constexpr int kWalkMaxThreads = 640;
+
+__host__ __device__ inline int walk_vars_per_block(int N)
+{
+    int v = kWalkMaxThreads / N;
+    return v > 16 ? 16 : (v < 1 ? 1 : v);
+}
+
+// shared memory of values_walk_kernel, in doubles: series tile, sample times, 1/n table, then for ALL the
+// windows of the block's start groups the (window, subject) tables (taubar, 1/Sxx, counts as int32) and the
+// per-window group offsets / type counts -- loaded once, so that the walk itself has no barrier
+__host__ __device__ inline size_t walk_smem_doubles(int N, int S, int max_block_windows)
+{
+    const size_t VB = walk_vars_per_block(N);
+    const size_t m = (size_t)max_block_windows * N;
+    return VB * (S | 1) + S + 129 + 2 * m + (m + 1) / 2 + (size_t)max_block_windows + ((size_t)max_block_windows + 1) / 2;
+}
+
+static __global__ void __launch_bounds__(kWalkMaxThreads)
+values_walk_kernel(const double *__restrict__ series, int64_t series_stride, const double *__restrict__ times,
+                   const int32_t *__restrict__ t_offsets, int S, int N, int V,
+                   const double *__restrict__ windows, const int32_t *__restrict__ wlo,
+                   const int32_t *__restrict__ wcnt, const double *__restrict__ winv_sxx,
+                   const double *__restrict__ wtbar, const int64_t *__restrict__ group_base,
+                   const uint8_t *__restrict__ slope_ok, const int32_t *__restrict__ sg_first, int n_sg,
+                   int sg_per_block, int max_block_windows, double *__restrict__ values,
+                   uint8_t *__restrict__ group_flags)
+{
+    extern __shared__ __align__(16) double wsm[];
+    const int VB = walk_vars_per_block(N);
+    const int Sp = S | 1;                               // odd row length: different variables, different banks
+    const int M = max_block_windows * N;
+    double *ser = wsm;                                  // [VB][Sp]
+    double *st = ser + (size_t)VB * Sp;                 // [S] sample times
+    double *rcp = st + S;                               // [129] 1/n
+    double *m_tb = rcp + 129;                           // [block windows][N] taubar
+    double *m_is = m_tb + M;                            // [block windows][N] 1/Sxx
+    int32_t *m_cnt = reinterpret_cast<int32_t *>(m_is + M);                           // [block windows][N]
+    long long *m_gb = reinterpret_cast<long long *>(m_cnt + ((M + 1) & ~1));          // [block windows] group_base * N
+    int32_t *m_nt = reinterpret_cast<int32_t *>(m_gb + max_block_windows);            // [block windows]
+    const int v0 = blockIdx.x * VB;
+    const int nv = min(VB, V - v0);
+    const int sg_begin = blockIdx.y * sg_per_block, sg_end = min(n_sg, sg_begin + sg_per_block);
+    if (sg_begin >= sg_end) return;
+    const int wb0 = sg_first[sg_begin], nbw = sg_first[sg_end] - wb0;      // the block's windows
+    for (int i = threadIdx.x; i < nv * S; i += blockDim.x) {
+        const int vl = i / S, j = i - vl * S;
+        ser[vl * Sp + j] = series[(int64_t)(v0 + vl) * series_stride + j];
+    }
+    for (int i = threadIdx.x; i < S; i += blockDim.x) st[i] = times[i];
+    for (int i = threadIdx.x; i <= 128; i += blockDim.x) rcp[i] = i ? __ddiv_rn(1.0, (double)i) : 0.0;
+    for (int i = threadIdx.x; i < nbw * N; i += blockDim.x) {
+        m_cnt[i] = wcnt[wb0 * N + i];
+        m_tb[i] = wtbar[wb0 * N + i];
+        m_is[i] = winv_sxx[wb0 * N + i];
+    }
+    for (int i = threadIdx.x; i < nbw; i += blockDim.x) {
+        m_gb[i] = group_base[wb0 + i] * N;               // element offset of the window's first group
+        m_nt[i] = 1 + slope_ok[wb0 + i];
+    }
+    __syncthreads();
+    const int vl = threadIdx.x / N, s = threadIdx.x - vl * N;
+    if (vl >= nv) return;
+    const double *x = ser + vl * Sp;
+    const int64_t vNs = (int64_t)(v0 + vl) * N + s;      // (variable, subject) offset inside a window's groups
+    for (int sg = sg_begin; sg < sg_end; ++sg) {
+        const int w_begin = sg_first[sg], nw = sg_first[sg + 1] - w_begin;
+        const int mb = (w_begin - wb0) * N + s;         // this thread's column in the block's tables
+        const double t0 = windows[2 * w_begin];
+        const int a = wlo[w_begin * N + s];            // first sample at or after t0: the same for the whole group
+        const double x0 = x[a];
+        int n = 0;
+        double res = -0.0, Sd = 0.0, Std = 0.0;
+        double r0 = 0, r1 = 0, r2 = 0, r3 = 0, r4 = 0, r5 = 0, r6 = 0, r7 = 0;
+        for (int wi = 0; wi < nw; ++wi) {
+            const int target = m_cnt[mb + wi * N];
+            while (n < target) {
+                const double xv = x[a + n];
+                const double d = __dadd_rn(xv, -x0);
+                Sd = __dadd_rn(Sd, d);
+                Std = __fma_rn(__dadd_rn(st[a + n], -t0), d, Std);
+                ++n;
+                if (n < 8 || (n & 7)) {
+                    res = __dadd_rn(res, xv);          // sequential head (n < 8) or the tail after the last block
+                } else {
+                    const double *b = x + a + n - 8;    // a block of 8 is complete
+                    if (n == 8) {
+                        r0 = b[0]; r1 = b[1]; r2 = b[2]; r3 = b[3]; r4 = b[4]; r5 = b[5]; r6 = b[6]; r7 = b[7];
+                    } else {
+                        r0 = __dadd_rn(r0, b[0]); r1 = __dadd_rn(r1, b[1]); r2 = __dadd_rn(r2, b[2]);
+                        r3 = __dadd_rn(r3, b[3]); r4 = __dadd_rn(r4, b[4]); r5 = __dadd_rn(r5, b[5]);
+                        r6 = __dadd_rn(r6, b[6]); r7 = __dadd_rn(r7, b[7]);
+                    }
+                    res = __dadd_rn(__dadd_rn(__dadd_rn(r0, r1), __dadd_rn(r2, r3)),
+                                    __dadd_rn(__dadd_rn(r4, r5), __dadd_rn(r6, r7)));
+                }
+            }
+            const int wl = w_begin - wb0 + wi;
+            const int nt = m_nt[wl];
+            // element offset of this thread's slope value (nt == 2) / mean (nt == 1): no 64-bit multiplies here
+            double *out = values + (m_gb[wl] + (nt == 2 ? 2 * vNs - s : vNs));
+            double mean;
+            if (n <= 128) mean = div_small_int_hot(res, (double)n, rcp[n]);
+            else mean = __ddiv_rn(pairwise_sum_col(SmemVec{x + a}, n), (double)n);   // numpy splits above 128
+            if (nt == 2) {
+                const double slope =
+                    __dmul_rn(__dadd_rn(Std, -__dmul_rn(m_tb[mb + wi * N], Sd)), m_is[mb + wi * N]);
+                out[0] = slope;
+                out[N] = mean;
+                // slope guard band: slope exactly 0 with a non-zero mean = constant non-zero series
+                if (group_flags && slope == 0.0 && mean != 0.0)
+                    group_flags[group_base[w_begin + wi] + (int64_t)(v0 + vl) * 2] = 1;
+            } else {
+                out[0] = mean;
+            }
+        }
+    }
+}
+
+// taubar[w][s] = mean over the window's samples of (t - t0_w): the variable-independent half of the slope
+static __global__ void __launch_bounds__(128)
+window_tbar_kernel(const double *__restrict__ times, int N, const double *__restrict__ windows, int W,
+                   const int32_t *__restrict__ wlo, const int32_t *__restrict__ wcnt, double *__restrict__ tbar)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= W * N) return;
+    const int w = i / N;
+    const double t0 = windows[2 * w];
+    const int lo = wlo[i], c = wcnt[i];
+    double acc = 0.0;
+    for (int j = 0; j < c; ++j) acc = __dadd_rn(acc, __dadd_rn(times[lo + j], -t0));
+    tbar[i] = c > 0 ? __ddiv_rn(acc, (double)c) : 0.0;
 }
 #endif  // MITRE_FUSED_MAIN
 

@@ -341,6 +341,65 @@ def detectors_fused(series_t, N, V, lists, group_base, slope_ok, task_window, ta
     return values, thresholds, K, rows
 
 
+def window_tbar(times, windows, lo, cnt):
+    """float64[W, N]: mean over each (window, subject)'s samples of t - t0 (mitre_window_tbar)."""
+    W, N = lo.shape
+    tbar = torch.empty((W, N), dtype=F64, device=dev())
+    check(lib().mitre_window_tbar(_stream(), _p(times), N, _p(windows), W, _p(lo), _p(cnt), _p(tbar)),
+          "mitre_window_tbar")
+    return tbar
+
+
+def values_walk_plan(N, S, V, sg_first):
+    """How the walk-forward values kernel splits the start groups over blockIdx.y: (sg_per_block,
+    max_block_windows) such that the per-block window tables fit in shared memory and the grid fills whole
+    waves, or None when not even one start group fits (then: mitre_detectors_fused).
+    sg_first: host int array [n_sg + 1]."""
+    info = device_info()
+    n_sg = len(sg_first) - 1
+    vb = max(1, min(16, 640 // int(N)))
+    tiles = (int(V) + vb - 1) // vb
+    best = None
+    for chunks in range(1, n_sg + 1):
+        per = (n_sg + chunks - 1) // chunks
+        widest = max(int(sg_first[min(k + per, n_sg)] - sg_first[k]) for k in range(0, n_sg, per))
+        smem = lib().mitre_values_walk_smem_bytes(int(N), int(S), widest)
+        if not 0 < smem <= info['smem_optin']:
+            continue
+        blocks = tiles * ((n_sg + per - 1) // per)
+        waves = -(-blocks // info['sm_count'])
+        fill = blocks / float(waves * info['sm_count']) - 0.01 * chunks
+        if best is None or fill > best[0]:
+            best = (fill, per, widest)
+        if chunks >= 8 and best is not None:
+            break
+    return None if best is None else (best[1], best[2])
+
+
+def detectors_walk(series, times, t_offsets, S, N, V, windows, lists, tbar, group_base, slope_ok, sg_first, G,
+                   group_type, plan):
+    """The default device path for N <= 63: mitre_detector_values_walk (one thread per (variable, subject),
+    samples walked once per start group) + mitre_detector_sort_emit.  Same returns as detectors_fused with
+    group_type: (values, thresholds, K, rows_padded, group_flags, flagged).  plan = values_walk_plan(...)."""
+    L = 2 * (N - 1)
+    values = torch.empty((G, N), dtype=F64, device=dev())
+    thresholds = torch.empty((G, N - 1), dtype=F64, device=dev())
+    K = torch.empty(G, dtype=I32, device=dev())
+    rows = torch.empty((G, L), dtype=I64, device=dev())
+    flags = torch.zeros(G, dtype=U8, device=dev())
+    flagged = torch.zeros(1, dtype=I64, device=dev())
+    W = windows.shape[0]
+    check(lib().mitre_detector_values_walk(_stream(), _p(series), series.shape[1], _p(times), _p(t_offsets), int(S),
+                                           int(N), int(V), _p(windows), W, _p(lists['lo']), _p(lists['cnt']),
+                                           _p(lists['inv_sxx']), _p(tbar), _p(group_base), _p(slope_ok),
+                                           _p(sg_first), sg_first.shape[0] - 1, int(plan[0]), int(plan[1]),
+                                           _p(values), _p(flags)),
+          "mitre_detector_values_walk")
+    check(lib().mitre_detector_sort_emit(_stream(), _p(values), G, int(N), _p(thresholds), _p(K), _p(rows),
+                                         _p(group_type), _p(flags), _p(flagged)), "mitre_detector_sort_emit")
+    return values, thresholds, K, rows, flags, flagged
+
+
 def slope_guard(values, group_type):
     """Slope guard band over values f64[G, N] (any N): (group_flags uint8[G], flagged int64[1])."""
     G, N = values.shape

@@ -253,7 +253,8 @@ class _PrimitiveValues:
 class DiscreteRulePopulation:
     """rules.py:245-810, mined on the GPU."""
 
-    use_fused = True    # N <= 63: mitre_detectors_fused (values + sort/emit kernels); False forces the phase-by-phase path
+    use_fused = True    # N <= 63: values + sort/emit kernels without a host round trip; False forces the phase-by-phase path
+    use_walk = True     # ... with the walk-forward values kernel (mitre_detector_values_walk); False: mitre_detectors_fused
 
     def __init__(self, model, tmin, N_intervals, tmax=None, data=None, max_thresholds=None):
         self.model = model
@@ -273,7 +274,7 @@ class DiscreteRulePopulation:
         for k in list(state):
             if k.startswith('_d_') or k in ('_values', '_thresholds', '_K', '_row_offsets', '_rows',
                                             '_perm', '_sorted_rows', '_row_group', '_rows_padded', '_fused', '_fused_args', '_active_rows',
-                                            '_slope_flags', '_slope_flagged',
+                                            '_slope_flags', '_slope_flagged', '_walk_args',
                                             '_d_windows'):
                 state[k] = None
         state['_host_cache'] = {}
@@ -368,6 +369,7 @@ class DiscreteRulePopulation:
         N = self.data.n_subjects
         self._fused = None
         self._fused_args = None
+        self._walk_args = None
         capped = N > self.max_thresholds + 1        # rules.py:535: groups with more values than the cap cluster
         if (self.use_fused and 2 <= N <= 63 and not capped and
                 ds['series_t'].shape[0] * ds['series_t'].shape[1] < 2 ** 31 - 1):
@@ -383,8 +385,19 @@ class DiscreteRulePopulation:
             d_tt = torch.as_tensor(np.array(tt, dtype=np.int8), device=D.dev())
             d_gt = torch.as_tensor(np.ascontiguousarray(self._group_type).view(np.uint8), device=D.dev())
             self._fused_args = (ds['series_t'], N, V, lists, d_gb, d_ok, d_tw, d_tt, self._G, d_gt)
-            self._values, thr, K, rows_padded, self._slope_flags, self._slope_flagged = \
-                D.detectors_fused(*self._fused_args)
+            self._walk_args = None
+            # start groups: runs of consecutive windows with the same start (rules.py:397-402 is start-major)
+            t0s = np.array([w[0] for w in self.windows], dtype=np.float64)
+            first = np.concatenate([[0], np.nonzero(t0s[1:] != t0s[:-1])[0] + 1, [W]]).astype(np.int32)
+            plan = D.values_walk_plan(N, ds['S'], V, first) if self.use_walk else None
+            if plan is not None:
+                tbar = D.window_tbar(ds['times'], self._d_windows, lists['lo'], lists['cnt'])
+                self._walk_args = (ds['series'], ds['times'], ds['t_offsets'], ds['S'], N, V, self._d_windows, lists,
+                                   tbar, d_gb, d_ok, torch.as_tensor(first, device=D.dev()), self._G, d_gt, plan)
+                out = D.detectors_walk(*self._walk_args)
+            else:
+                out = D.detectors_fused(*self._fused_args)
+            self._values, thr, K, rows_padded, self._slope_flags, self._slope_flagged = out
             self._fused = (thr, K, rows_padded)
         else:
             lo, cnt = D.window_ranges(ds['times'], ds['t_offsets'], self._d_windows)

@@ -36,6 +36,26 @@ def main():
         same = all(torch.equal(a, b) for a, b in zip(ref, out))
         print("%-36s %.3f ms  identical=%s" % (name, ms, same))
     lib().mitre_set_detector_split(1)
+    if pop._walk_args is not None:
+        wa = pop._walk_args
+        out = D.detectors_walk(*wa)
+        ms = min(bench.cuda_time_ms(torch, lambda: D.detectors_walk(*wa), 10) for _ in range(3))
+        same = all(torch.equal(a, b) for a, b in zip(ref[1:4], out[1:4]))
+        means_same = torch.equal(ref[0][1::2], out[0][1::2]) if bool(wa[10].all()) else None
+        print("%-36s %.3f ms  thresholds/K/rows identical=%s  means identical=%s" % ("walk values + staged sort/emit", ms,
+                                                                                    same, means_same))
+        tbar_ms = bench.cuda_time_ms(torch, lambda: D.window_tbar(wa[1], wa[6], wa[7]['lo'], wa[7]['cnt']), 10)
+        import ctypes
+        from mitre_b200.device import _p, _stream
+        vals = out[0]
+        flags = torch.zeros(wa[12], dtype=torch.uint8, device=vals.device)
+        def values_only():
+            lib().mitre_detector_values_walk(_stream(), _p(wa[0]), wa[0].shape[1], _p(wa[1]), _p(wa[2]), int(wa[3]),
+                                             int(wa[4]), int(wa[5]), _p(wa[6]), wa[6].shape[0], _p(wa[7]['lo']),
+                                             _p(wa[7]['cnt']), _p(wa[7]['inv_sxx']), _p(wa[8]), _p(wa[9]), _p(wa[10]),
+                                             _p(wa[11]), wa[11].shape[0] - 1, int(wa[14][0]), int(wa[14][1]), _p(vals), _p(flags))
+        print("  values_walk_kernel alone            %.3f ms  (window_tbar %.3f ms)" % (
+            min(bench.cuda_time_ms(torch, values_only, 10) for _ in range(3)), tbar_ms))
     N = fa[1]
     padded = ref[3]
     D.lexsort_rows(padded.view(-1, 1), N + 1)
