@@ -156,7 +156,7 @@ score_stats_final_kernel(const double *__restrict__ part, int nparts, double *__
 
 // ---------------------------------------------------------------------------------------------
 // Base system for one design matrix.  Called by every thread of a CTA; smem scratch:
-//   sA[p*p] (in: nothing, out: L lower-triangular), sb[p] (out: yb = L^-1 b), sred[blockDim]
+//   sA[p*p] (in: nothing, out: L strictly-lower-triangular, diagonal = 1 / L_jj), sb[p] (out: yb = L^-1 b), sred[blockDim]
 // Returns the base log-likelihood log N(kappa/omega; 0, Omega^-1 + s2 X X') in every thread;
 // *ok = 0 if A is not positive definite.
 // ---------------------------------------------------------------------------------------------
@@ -189,36 +189,53 @@ __device__ double base_system(const double *__restrict__ X, int ldx, const doubl
         if (tid < s) sred[tid] += sred[tid + s];
         __syncthreads();
     }
-    if (tid == 0) {
-        // unblocked Cholesky, in place (lower), then yb = L^-1 b
+    if (tid < 32) {
+        // Cholesky of the p x p system by one warp, lane = row: per column the pivot lane forms d_j, every
+        // lane below it its entry -- a dependency depth of ~p^2 multiply-adds instead of the p^3/3 + divides
+        // + square roots of a single thread (that serial stretch was most of the prepare launch).  The
+        // reciprocal square root of the pivot replaces every later division: L_ij = s * rs_j,
+        // L_jj = d_j * rs_j, yb_i = s * rs_i, log L_jj = log(d_j) / 2; the diagonal itself is stored as its
+        // reciprocal (sA[j][j] = 1 / L_jj), which is what subject_vector multiplies by.
+        const int lane = tid;
         int ok = 1;
-        for (int j = 0; j < p && ok; ++j) {
-            double d = sA[j * p + j];
-            for (int k = 0; k < j; ++k) d -= sA[j * p + k] * sA[j * p + k];
-            if (!(d > 0.0)) { ok = 0; break; }
-            d = sqrt(d);
-            sA[j * p + j] = d;
-            for (int i = j + 1; i < p; ++i) {
-                double s = sA[i * p + j];
-                for (int k = 0; k < j; ++k) s -= sA[i * p + k] * sA[j * p + k];
-                sA[i * p + j] = s / d;
+        double half_logd = 0.0;                      // lane j: log(L_jj)
+        for (int j = 0; j < p; ++j) {
+            double d = 0.0;
+            if (lane == j) {
+                d = sA[j * p + j];
+                for (int k = 0; k < j; ++k) d -= sA[j * p + k] * sA[j * p + k];
             }
-        }
-        double logdetL = 0.0, yy = 0.0;
-        if (ok) {
-            for (int i = 0; i < p; ++i) {
-                double s = sb[i];
-                for (int k = 0; k < i; ++k) s -= sA[i * p + k] * sb[k];
-                s /= sA[i * p + i];
-                sb[i] = s;
-                yy += s * s;
-                logdetL += log(sA[i * p + i]);
+            d = __shfl_sync(0xffffffffu, d, j);
+            if (!(d > 0.0)) { ok = 0; break; }        // warp-uniform
+            const double rs = rsqrt(d);
+            if (lane == j) {
+                half_logd = 0.5 * log(d);
+                sA[j * p + j] = rs;
+            } else if (lane > j && lane < p) {
+                double v = sA[lane * p + j];
+                for (int k = 0; k < j; ++k) v -= sA[lane * p + k] * sA[j * p + k];
+                sA[lane * p + j] = v * rs;
             }
+            __syncwarp();
         }
-        *s_ok = ok;
-        // sred[0] = sum kappa^2/omega - sum log omega
-        const double quad_plus_logdet = sred[0] - yy + p * log(sigma2) + 2.0 * logdetL;
-        sred[0] = -0.5 * quad_plus_logdet - 0.5 * N * log(2.0 * M_PI);
+        double logdetL = 0.0;
+        for (int j = 0; j < p; ++j) logdetL += __shfl_sync(0xffffffffu, half_logd, j);   // fixed order
+        if (lane == 0) {
+            double yy = 0.0;
+            if (ok) {
+                for (int i = 0; i < p; ++i) {
+                    double v = sb[i];
+                    for (int k = 0; k < i; ++k) v -= sA[i * p + k] * sb[k];
+                    v *= sA[i * p + i];
+                    sb[i] = v;
+                    yy += v * v;
+                }
+            }
+            *s_ok = ok;
+            // sred[0] = sum kappa^2/omega - sum log omega
+            const double quad_plus_logdet = sred[0] - yy + p * log(sigma2) + 2.0 * logdetL;
+            sred[0] = -0.5 * quad_plus_logdet - 0.5 * N * log(2.0 * M_PI);
+        }
     }
     __syncthreads();
     return sred[0];
@@ -241,7 +258,7 @@ __device__ __forceinline__ void subject_vector(const double *__restrict__ X, con
     for (int j = 0; j < p; ++j) {
         double s = om * X[(size_t)i * p + j];
         for (int k = 0; k < j; ++k) s -= sA[j * p + k] * w[k];
-        s /= sA[j * p + j];
+        s *= sA[j * p + j];                           // the diagonal holds 1 / L_jj
         w[j] = s;
         dot += s * sb[j];
     }
@@ -311,22 +328,32 @@ score_prepare16_kernel(const double *__restrict__ X, const double *__restrict__ 
         }
         for (int i = threadIdx.x; i < N * EP; i += blockDim.x) ws[kHdr + i] = sq[i];
     }
+    // tables: one thread per subset pattern forms all EP components of the entry (ascending subject order, like
+    // score_build_tables16_kernel, so both layouts hold bit-identical sums); a thread per (pattern, component)
+    // spent most of its instructions on index arithmetic and re-testing the pattern bits
     const int nt = n_tables16(N);
     size_t base = 0;
     for (int t = 0; t < nt; ++t) {
         const int bits = table16_bits(N, t), start = table16_start(N, t);
-        const size_t count = ((size_t)1 << bits) * stride;
-        for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < count;
-             idx += (size_t)gridDim.x * blockDim.x) {
-            const int e = (int)(idx % stride);
-            const unsigned pat = (unsigned)(idx / stride);
-            double acc = 0.0;
-            if (e < EP)
-                for (int j = 0; j < bits; ++j)
-                    if ((pat >> (bits - 1 - j)) & 1) acc += sq[(start + j) * EP + e];
-            tables[base + idx] = acc;
+        const unsigned npat = 1u << bits;
+        for (unsigned pat = blockIdx.x * blockDim.x + threadIdx.x; pat < npat; pat += gridDim.x * blockDim.x) {
+            double acc[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = 0.0;
+            for (int j = 0; j < bits; ++j) {
+                if ((pat >> (bits - 1 - j)) & 1) {
+                    const double *qj = sq + (start + j) * EP;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        if (e < EP) acc[e] += qj[e];
+                }
+            }
+            double *dst = tables + base + (size_t)pat * stride;
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if (e < stride) dst[e] = acc[e];
         }
-        base += count;
+        base += (size_t)npat * stride;
     }
 }
 
