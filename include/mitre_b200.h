@@ -308,6 +308,21 @@ int mitre_detector_values_walk(void *stream, const double *series, int64_t serie
 int mitre_detector_sort_emit(void *stream, const double *values, int64_t G, int N, double *thresholds,
                              int32_t *K, uint64_t *rows_padded, const uint8_t *group_type,
                              uint8_t *group_flags, int64_t *flagged);
+/* Both halves pipelined: the start groups are cut into n_stages runs (stage_sg_host int32[n_stages + 1]: start
+ * group bounds; stage_group_host int64[n_stages + 1]: the matching group bounds, group_base of each run's first
+ * window and G at the end; both HOST arrays).  Run c's values are computed on one internal stream while run
+ * c - 1 is sorted and emitted on another, ordered by events; the call returns with the caller's stream waiting
+ * on both.  Neither kernel fills an SM alone (issue-bound at low occupancy vs store-bound), so they overlap,
+ * and a run's values are re-read from L2 instead of HBM.  Outputs and flags as for the two calls above
+ * (group_flags is cleared here). */
+int mitre_detectors_walk(void *stream, const double *series, int64_t series_stride, const double *times,
+                         const int32_t *t_offsets, int S, int N, int V, const double *windows, int W,
+                         const int32_t *wlo, const int32_t *wcnt, const double *winv_sxx, const double *wtbar,
+                         const int64_t *group_base, const uint8_t *slope_ok, const int32_t *sg_first, int n_sg,
+                         int sg_per_block, int max_block_windows, const int32_t *stage_sg_host,
+                         const int64_t *stage_group_host, int n_stages, int64_t G, double *values,
+                         double *thresholds, int32_t *K, uint64_t *rows_padded, const uint8_t *group_type,
+                         uint8_t *group_flags, int64_t *flagged);
 
 /* Slope guard band.  'slope' detector values come from a closed form here and from LAPACK gelsd in the
  * reference (rules.py:110-114); the truth rows of a group depend only on the order and tie structure of

@@ -77,6 +77,9 @@ SIGNATURES = {
     "mitre_detector_values_walk": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_int, c_int, c_int,
                                            c_void_p, c_int] + [c_void_p] * 7 + [c_int, c_int, c_int, c_void_p,
                                                                                  c_void_p]),
+    "mitre_detectors_walk": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                                     c_int] + [c_void_p] * 7 + [c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                                                                 c_i64] + [c_void_p] * 7),
     "mitre_detector_sort_emit": (c_int, [c_void_p, c_void_p, c_i64, c_int] + [c_void_p] * 6),
     "mitre_slope_guard": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p, c_void_p]),
     "mitre_set_detector_split": (c_int, [c_int]),

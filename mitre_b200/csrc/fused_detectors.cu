@@ -1,6 +1,8 @@
 // fused_detectors.cu -- C ABI entry points of the fused detector path (kernel: fused_detectors.cuh,
 // instantiated per sorting-network size in fused_inst.cu).
 #define MITRE_FUSED_MAIN 1
+#include <vector>
+
 #include "fused_detectors.cuh"
 
 namespace mitre {
@@ -322,8 +324,109 @@ extern "C" int mitre_detector_values_walk(void *stream, const double *series, in
     const int threads = ((VB * N + 31) / 32) * 32;
     values_walk_kernel<<<dim3((unsigned)tiles, (unsigned)chunks), threads, smem, as_stream(stream)>>>(
         series, series_stride, times, t_offsets, S, N, V, windows, wlo, wcnt, winv_sxx, wtbar, group_base, slope_ok,
-        sg_first, n_sg, sg_per_block, max_block_windows, values, group_flags);
+        sg_first, 0, n_sg, sg_per_block, max_block_windows, values, group_flags);
     MITRE_LAUNCH_CHECK();
+    return MITRE_OK;
+}
+
+// ---- the two halves pipelined over runs of start groups ---------------------------------------------------
+// The values kernel is bound by instruction issue and dependent fp64 chains at ~28 % occupancy, the sort/emit
+// kernel by HBM stores and its own issue rate at ~18 %: alone, each leaves most of an SM idle.  Here the
+// start groups are cut into `n_stages` runs; run c's values are computed on one internal stream while run
+// c - 1's values are sorted and emitted on another (event-ordered), so the two kernels share the SMs, and a
+// run's values (tens of MB) are still in the 126 MB L2 when the sort/emit kernel reads them back.
+namespace {
+struct WalkPipe {
+    cudaStream_t st[2] = {nullptr, nullptr};
+    cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> done;
+    int device = -1;
+    cudaError_t ensure(int n)
+    {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev != device) {
+            for (int i = 0; i < 2; ++i) {
+                if ((e = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking)) != cudaSuccess) return e;
+                if ((e = cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+            }
+            if ((e = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming)) != cudaSuccess) return e;
+            done.clear();
+            device = dev;
+        }
+        while ((int)done.size() < n) {
+            cudaEvent_t ev;
+            if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+            done.push_back(ev);
+        }
+        return cudaSuccess;
+    }
+};
+WalkPipe g_walk_pipe;
+}  // namespace
+
+extern "C" int mitre_detectors_walk(void *stream, const double *series, int64_t series_stride, const double *times,
+                                    const int32_t *t_offsets, int S, int N, int V, const double *windows, int W,
+                                    const int32_t *wlo, const int32_t *wcnt, const double *winv_sxx,
+                                    const double *wtbar, const int64_t *group_base, const uint8_t *slope_ok,
+                                    const int32_t *sg_first, int n_sg, int sg_per_block, int max_block_windows,
+                                    const int32_t *stage_sg_host, const int64_t *stage_group_host, int n_stages,
+                                    int64_t G, double *values, double *thresholds, int32_t *K, uint64_t *rows_padded,
+                                    const uint8_t *group_type, uint8_t *group_flags, int64_t *flagged)
+{
+    if (N < 2 || N > 63) return MITRE_ERR_UNSUPPORTED;
+    if (V <= 0 || S <= 0 || W <= 0 || n_sg <= 0 || series_stride < S || sg_per_block < 1 || max_block_windows < 1 ||
+        n_stages < 1 || G <= 0)
+        return MITRE_ERR_INVALID;
+    if (!series || !times || !t_offsets || !windows || !wlo || !wcnt || !winv_sxx || !wtbar || !group_base ||
+        !slope_ok || !sg_first || !stage_sg_host || !stage_group_host || !values || !thresholds || !K || !rows_padded)
+        return MITRE_ERR_INVALID;
+    if ((group_flags || flagged) && !group_type) return MITRE_ERR_INVALID;
+    if (flagged && !group_flags) return MITRE_ERR_INVALID;
+    const size_t smem = mitre_values_walk_smem_bytes(N, S, max_block_windows);
+    if (smem > smem_optin()) return MITRE_ERR_UNSUPPORTED;
+    MITRE_CUDA_TRY(cudaFuncSetAttribute(values_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaStream_t user = as_stream(stream);
+    WalkPipe &wp = g_walk_pipe;
+    MITRE_CUDA_TRY(wp.ensure(n_stages));
+    if (group_flags) MITRE_CUDA_TRY(cudaMemsetAsync(group_flags, 0, (size_t)G, user));
+    if (flagged) MITRE_CUDA_TRY(cudaMemsetAsync(flagged, 0, sizeof(int64_t), user));
+    MITRE_CUDA_TRY(cudaEventRecord(wp.fork, user));
+    MITRE_CUDA_TRY(cudaStreamWaitEvent(wp.st[0], wp.fork, 0));
+    MITRE_CUDA_TRY(cudaStreamWaitEvent(wp.st[1], wp.fork, 0));
+    const int VB = walk_vars_per_block(N);
+    const int tiles = (V + VB - 1) / VB;
+    const int threads = ((VB * N + 31) / 32) * 32;
+    const int M = N - 1;
+    const int saved = g_detector_split;
+    int rc = MITRE_OK;
+    for (int c = 0; c < n_stages && rc == MITRE_OK; ++c) {
+        const int sg0 = stage_sg_host[c], sg1 = stage_sg_host[c + 1];
+        const int64_t g0 = stage_group_host[c], g1 = stage_group_host[c + 1];
+        if (sg1 <= sg0 || g1 <= g0) continue;
+        const int chunks = (sg1 - sg0 + sg_per_block - 1) / sg_per_block;
+        values_walk_kernel<<<dim3((unsigned)tiles, (unsigned)chunks), threads, smem, wp.st[0]>>>(
+            series, series_stride, times, t_offsets, S, N, V, windows, wlo, wcnt, winv_sxx, wtbar, group_base,
+            slope_ok, sg_first, sg0, sg1, sg_per_block, max_block_windows, values, group_flags);
+        MITRE_LAUNCH_CHECK();
+        MITRE_CUDA_TRY(cudaEventRecord(wp.done[c], wp.st[0]));
+        MITRE_CUDA_TRY(cudaStreamWaitEvent(wp.st[1], wp.done[c], 0));
+        g_detector_split = 1;
+        g_slope_guard = (group_type && group_flags) ? SlopeGuardArgs{group_type + g0, group_flags + g0, nullptr}
+                                                     : SlopeGuardArgs{nullptr, nullptr, nullptr};
+        rc = nb_dispatch(wp.st[1], nullptr, 0, N, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0,
+                         nullptr, nullptr, nullptr, nullptr, 0, g1 - g0, values + g0 * N, thresholds + g0 * M, K + g0,
+                         rows_padded + g0 * 2 * M);
+        g_slope_guard = SlopeGuardArgs{nullptr, nullptr, nullptr};
+        g_detector_split = saved;
+    }
+    MITRE_CUDA_TRY(cudaEventRecord(wp.join[0], wp.st[0]));
+    MITRE_CUDA_TRY(cudaEventRecord(wp.join[1], wp.st[1]));
+    MITRE_CUDA_TRY(cudaStreamWaitEvent(user, wp.join[0], 0));
+    MITRE_CUDA_TRY(cudaStreamWaitEvent(user, wp.join[1], 0));
+    if (rc != MITRE_OK) return rc;
+    if (flagged) return launch_count_flags(user, group_flags, G, reinterpret_cast<unsigned long long *>(flagged));
     return MITRE_OK;
 }
 

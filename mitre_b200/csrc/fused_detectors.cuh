@@ -895,8 +895,8 @@ values_walk_kernel(const double *__restrict__ series, int64_t series_stride, con
                    const double *__restrict__ windows, const int32_t *__restrict__ wlo,
                    const int32_t *__restrict__ wcnt, const double *__restrict__ winv_sxx,
                    const double *__restrict__ wtbar, const int64_t *__restrict__ group_base,
-                   const uint8_t *__restrict__ slope_ok, const int32_t *__restrict__ sg_first, int n_sg,
-                   int sg_per_block, int max_block_windows, double *__restrict__ values,
+                   const uint8_t *__restrict__ slope_ok, const int32_t *__restrict__ sg_first, int sg_base,
+                   int n_sg, int sg_per_block, int max_block_windows, double *__restrict__ values,
                    uint8_t *__restrict__ group_flags)
 {
     extern __shared__ __align__(16) double wsm[];
@@ -913,7 +913,8 @@ values_walk_kernel(const double *__restrict__ series, int64_t series_stride, con
     int32_t *m_nt = reinterpret_cast<int32_t *>(m_gb + max_block_windows);            // [block windows]
     const int v0 = blockIdx.x * VB;
     const int nv = min(VB, V - v0);
-    const int sg_begin = blockIdx.y * sg_per_block, sg_end = min(n_sg, sg_begin + sg_per_block);
+    // this launch covers start groups [sg_base, n_sg), sg_per_block of them per blockIdx.y
+    const int sg_begin = sg_base + blockIdx.y * sg_per_block, sg_end = min(n_sg, sg_begin + sg_per_block);
     if (sg_begin >= sg_end) return;
     const int wb0 = sg_first[sg_begin], nbw = sg_first[sg_end] - wb0;      // the block's windows
     for (int i = threadIdx.x; i < nv * S; i += blockDim.x) {

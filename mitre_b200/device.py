@@ -376,11 +376,29 @@ def values_walk_plan(N, S, V, sg_first):
     return None if best is None else (best[1], best[2])
 
 
+def walk_stages(sg_first, group_base_host, G, n_stages):
+    """Cut the start groups into ~n_stages runs of about equal group counts for the pipelined detector call:
+    (stage_sg int32[k + 1], stage_group int64[k + 1]) host arrays."""
+    n_sg = len(sg_first) - 1
+    gb = [int(group_base_host[int(sg_first[k])]) for k in range(n_sg)] + [int(G)]
+    sg_bounds, k = [0], 0
+    for c in range(1, n_stages):
+        target = G * c / float(n_stages)
+        while k < n_sg and gb[k] < target:
+            k += 1
+        if sg_bounds[-1] < k < n_sg:
+            sg_bounds.append(k)
+    sg_bounds.append(n_sg)
+    return (np.array(sg_bounds, dtype=np.int32), np.array([gb[k] for k in sg_bounds], dtype=np.int64))
+
+
 def detectors_walk(series, times, t_offsets, S, N, V, windows, lists, tbar, group_base, slope_ok, sg_first, G,
-                   group_type, plan):
+                   group_type, plan, stages=None):
     """The default device path for N <= 63: mitre_detector_values_walk (one thread per (variable, subject),
-    samples walked once per start group) + mitre_detector_sort_emit.  Same returns as detectors_fused with
-    group_type: (values, thresholds, K, rows_padded, group_flags, flagged).  plan = values_walk_plan(...)."""
+    samples walked once per start group) + mitre_detector_sort_emit; with stages = walk_stages(...) the two
+    kernels are pipelined over runs of start groups on two internal streams (mitre_detectors_walk).  Same
+    returns as detectors_fused with group_type: (values, thresholds, K, rows_padded, group_flags, flagged).
+    plan = values_walk_plan(...)."""
     L = 2 * (N - 1)
     values = torch.empty((G, N), dtype=F64, device=dev())
     thresholds = torch.empty((G, N - 1), dtype=F64, device=dev())
@@ -389,6 +407,16 @@ def detectors_walk(series, times, t_offsets, S, N, V, windows, lists, tbar, grou
     flags = torch.zeros(G, dtype=U8, device=dev())
     flagged = torch.zeros(1, dtype=I64, device=dev())
     W = windows.shape[0]
+    if stages is not None and len(stages[0]) > 2:
+        st_sg, st_g = stages
+        check(lib().mitre_detectors_walk(_stream(), _p(series), series.shape[1], _p(times), _p(t_offsets), int(S),
+                                         int(N), int(V), _p(windows), W, _p(lists['lo']), _p(lists['cnt']),
+                                         _p(lists['inv_sxx']), _p(tbar), _p(group_base), _p(slope_ok), _p(sg_first),
+                                         sg_first.shape[0] - 1, int(plan[0]), int(plan[1]),
+                                         st_sg.ctypes.data_as(ctypes.c_void_p), st_g.ctypes.data_as(ctypes.c_void_p),
+                                         len(st_sg) - 1, int(G), _p(values), _p(thresholds), _p(K), _p(rows),
+                                         _p(group_type), _p(flags), _p(flagged)), "mitre_detectors_walk")
+        return values, thresholds, K, rows, flags, flagged
     check(lib().mitre_detector_values_walk(_stream(), _p(series), series.shape[1], _p(times), _p(t_offsets), int(S),
                                            int(N), int(V), _p(windows), W, _p(lists['lo']), _p(lists['cnt']),
                                            _p(lists['inv_sxx']), _p(tbar), _p(group_base), _p(slope_ok),

@@ -255,6 +255,8 @@ class DiscreteRulePopulation:
 
     use_fused = True    # N <= 63: values + sort/emit kernels without a host round trip; False forces the phase-by-phase path
     use_walk = True     # ... with the walk-forward values kernel (mitre_detector_values_walk); False: mitre_detectors_fused
+    walk_stages = 1     # > 1: values / sort-emit kernels pipelined over that many runs of start groups on two streams
+                        # (mitre_detectors_walk; measured SLOWER on B200 -- the kernels do not co-reside -- so off)
 
     def __init__(self, model, tmin, N_intervals, tmax=None, data=None, max_thresholds=None):
         self.model = model
@@ -392,8 +394,12 @@ class DiscreteRulePopulation:
             plan = D.values_walk_plan(N, ds['S'], V, first) if self.use_walk else None
             if plan is not None:
                 tbar = D.window_tbar(ds['times'], self._d_windows, lists['lo'], lists['cnt'])
+                stages = (D.walk_stages(first, group_base, self._G, self.walk_stages)
+                          if self.walk_stages > 1 else None)
                 self._walk_args = (ds['series'], ds['times'], ds['t_offsets'], ds['S'], N, V, self._d_windows, lists,
-                                   tbar, d_gb, d_ok, torch.as_tensor(first, device=D.dev()), self._G, d_gt, plan)
+                                   tbar, d_gb, d_ok, torch.as_tensor(first, device=D.dev()), self._G, d_gt, plan,
+                                   stages)
+                self._walk_first = first
                 out = D.detectors_walk(*self._walk_args)
             else:
                 out = D.detectors_fused(*self._fused_args)

@@ -447,3 +447,25 @@ def test_model_builds_with_max_thresholds():
     out = model.likelihoods_of_all_options(R.RuleList([[R.PrimitiveRule(*pop.flat_rules[0])]]),
                                            np.full(35, 0.25), 0, 0)
     assert out.shape == (len(pop),) and np.isfinite(out).all()
+
+
+def test_pipelined_detector_call_equals_back_to_back():
+    """mitre_detectors_walk (values and sort/emit kernels pipelined over runs of start groups on two internal
+    streams) must produce exactly what the two calls made back to back produce."""
+    import torch
+    from mitre_b200 import rules as R
+    d = synthetic.make_series(N=35, V=70, T=(8, 25), span=(0.0, 375.0), seed=21)
+    cfg = dict(tmin=1.0, N_intervals=12, tmax=None)
+    data, pop = build_gpu_population(d, cfg, True)
+    assert pop._walk_args is not None
+    ref = [t.clone() for t in (pop._values, pop._thresholds, pop._K, pop._slope_flags)]
+    old = R.DiscreteRulePopulation.walk_stages
+    R.DiscreteRulePopulation.walk_stages = 5
+    try:
+        data2, pop2 = build_gpu_population(d, cfg, True)
+    finally:
+        R.DiscreteRulePopulation.walk_stages = old
+    assert pop2._walk_args[15] is not None and len(pop2._walk_args[15][0]) > 2
+    for a, b in zip(ref, (pop2._values, pop2._thresholds, pop2._K, pop2._slope_flags)):
+        assert torch.equal(a, b)
+    assert torch.equal(pop.packed_truth, pop2.packed_truth) and torch.equal(pop._perm, pop2._perm)

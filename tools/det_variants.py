@@ -44,6 +44,14 @@ def main():
         means_same = torch.equal(ref[0][1::2], out[0][1::2]) if bool(wa[10].all()) else None
         print("%-36s %.3f ms  thresholds/K/rows identical=%s  means identical=%s" % ("walk values + staged sort/emit", ms,
                                                                                     same, means_same))
+        for ns in (1, 2, 4, 8, 12, 24):
+            stages = D.walk_stages(pop._walk_first, pop._group_base, pop._G, ns) if ns > 1 else None
+            args = wa[:15] + (stages,)
+            o2 = D.detectors_walk(*args)
+            ms = min(bench.cuda_time_ms(torch, lambda: D.detectors_walk(*args), 10) for _ in range(3))
+            same = all(torch.equal(a, b) for a, b in zip(out, o2))
+            print("    pipelined over %2d runs of start groups: %.3f ms  identical=%s" % (
+                1 if stages is None else len(stages[0]) - 1, ms, same))
         tbar_ms = bench.cuda_time_ms(torch, lambda: D.window_tbar(wa[1], wa[6], wa[7]['lo'], wa[7]['cnt']), 10)
         import ctypes
         from mitre_b200.device import _p, _stream
