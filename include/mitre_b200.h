@@ -91,6 +91,8 @@ size_t mitre_score_workspace_bytes(int N, int p);
 int mitre_set_large_table_min_rows(int64_t rows);
 int mitre_set_split_tables(int enable);
 int mitre_set_wide_tables(int enable);   /* N > 64: 1 (default) byte tables in L2, 0 one fetch per set bit */
+int mitre_set_dedupe_table_bits(int bits); /* ... its subset-sum tables cover `bits` subjects each (11..16; default 11:
+                                            the last table is 2048 entries and stays in L1) */
 int mitre_set_dedupe(int mode);          /* large tables, N <= 64: 1 (default) score each run of equal rows once;
                                             2 the same with four lanes per 64-byte table entry; 0 off */
 int mitre_score_all(void *stream, const uint64_t *packed_truth, int64_t P, int W64,

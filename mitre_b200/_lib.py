@@ -38,6 +38,7 @@ SIGNATURES = {
     "mitre_set_groups_warp": (c_int, [c_int]),
     "mitre_set_wide_tables": (c_int, [c_int]),
     "mitre_set_dedupe": (c_int, [c_int]),
+    "mitre_set_dedupe_table_bits": (c_int, [c_int]),
     "mitre_score_all": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_int, c_int, c_double, c_void_p, c_size_t, c_void_p,
                                 c_void_p]),

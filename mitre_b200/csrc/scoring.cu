@@ -37,6 +37,24 @@ __host__ __device__ inline int ep_for(int p) { return (p + 2 + 1) & ~1; }  // ev
 // (table 0 takes the N mod 16 remainder), because neighbouring rows of a lexsorted table differ in
 // their trailing subjects: all of a warp's divergent lookups then fall into the last table and the
 // leading tables are warp-uniform loads.
+// The same split with B subjects per table (the duplicate-aware kernel uses B = 11: the last table is then
+// 2048 entries = 96 KB at p = 4 and stays in L1, where a 16-subject table (3 MB) is an L2 round trip per row).
+__host__ __device__ inline int n_tables(int N, int B) { return (N + B - 1) / B; }
+__host__ __device__ inline int table_bits(int N, int B, int t)
+{
+    return t == 0 ? N - B * (n_tables(N, B) - 1) : B;
+}
+__host__ __device__ inline int table_start(int N, int B, int t)
+{
+    return t == 0 ? 0 : table_bits(N, B, 0) + B * (t - 1);
+}
+__host__ __device__ inline size_t tables_doubles(int N, int B, int stride)
+{
+    size_t n = 0;
+    for (int t = 0; t < n_tables(N, B); ++t) n += ((size_t)1 << table_bits(N, B, t)) * stride;
+    return n;
+}
+constexpr int kMaxTables = 6;          // N <= 64, B >= 11
 __host__ __device__ inline int n_tables16(int N) { return (N + 15) >> 4; }
 __host__ __device__ inline int table16_bits(int N, int t)
 {
@@ -299,7 +317,7 @@ score_setup_kernel(const double *__restrict__ X, const double *__restrict__ omeg
 __global__ void __launch_bounds__(256)
 score_prepare16_kernel(const double *__restrict__ X, const double *__restrict__ omega,
                        const double *__restrict__ kappa, const uint64_t *__restrict__ mask, int N, int p,
-                       double sigma2, double *__restrict__ ws, int32_t *status, int stride,
+                       double sigma2, double *__restrict__ ws, int32_t *status, int stride, int B,
                        double *__restrict__ tables)
 {
     __shared__ double sA[MITRE_MAX_P * MITRE_MAX_P];
@@ -331,10 +349,10 @@ score_prepare16_kernel(const double *__restrict__ X, const double *__restrict__ 
     // tables: one thread per subset pattern forms all EP components of the entry (ascending subject order, like
     // score_build_tables16_kernel, so both layouts hold bit-identical sums); a thread per (pattern, component)
     // spent most of its instructions on index arithmetic and re-testing the pattern bits
-    const int nt = n_tables16(N);
+    const int nt = n_tables(N, B);
     size_t base = 0;
     for (int t = 0; t < nt; ++t) {
-        const int bits = table16_bits(N, t), start = table16_start(N, t);
+        const int bits = table_bits(N, B, t), start = table_start(N, B, t);
         const unsigned npat = 1u << bits;
         for (unsigned pat = blockIdx.x * blockDim.x + threadIdx.x; pat < npat; pat += gridDim.x * blockDim.x) {
             double acc[8];
@@ -1396,7 +1414,9 @@ score_w1g4_kernel(const uint64_t *__restrict__ rows, int64_t P, const double *__
 // consumes (draw.cu) and merged into the CTA's partial.  Deterministic for a given grid.
 // ---------------------------------------------------------------------------------------------
 static int g_dedupe = 1;
+static int g_dedupe_bits = 11;      // subjects per subset-sum table of the duplicate-aware kernel (11..16)
 constexpr int kCoopStride = 8;      // doubles per table entry (64 bytes)
+constexpr int kPrefetchTiles = 3;   // L2 prefetch distance of the row stream, in tiles per warp
 
 // 4x4 transpose of double2 elements inside each group of four lanes: a[r] of lane j <-> a[j] of lane r
 __device__ __forceinline__ double2 shfl_xor_d2(double2 v, int m)
@@ -1420,7 +1440,7 @@ __device__ __forceinline__ void transpose4(double2 (&a)[4], int j)
 template <int EP, bool STATS, bool COOP>
 __global__ void __launch_bounds__(256, STATS ? 3 : 4)
 score_w1d_kernel(const uint64_t *__restrict__ rows, int64_t P, const double *__restrict__ ws, int N,
-                 const double *__restrict__ tables, double *__restrict__ out, int32_t *status,
+                 const double *__restrict__ tables, int B, double *__restrict__ out, int32_t *status,
                  const double *__restrict__ log_prior, double *__restrict__ stat_partials,
                  double *__restrict__ tile_pairs, unsigned int *ticket, double *__restrict__ stats)
 {
@@ -1431,25 +1451,25 @@ score_w1d_kernel(const uint64_t *__restrict__ rows, int64_t P, const double *__r
     build_math_tables(logtab, exptab);
     __syncthreads();
     const double inv_s2 = ws[1], C1 = ws[3];
-    const int nt = n_tables16(N);
-    const double2 *tb[4];
-    int shift[4];
-    unsigned msk[4];
+    const int nt = n_tables(N, B);
+    const double2 *tb[kMaxTables];
+    int shift[kMaxTables];
+    unsigned msk[kMaxTables];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int g = lane >> 2, j = lane & 3;      // group of four lanes, quarter of the entry
     {
         size_t base = 0;
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const int bits = t < nt ? table16_bits(N, t) : 0;
+        for (int t = 0; t < kMaxTables; ++t) {
+            const int bits = t < nt ? table_bits(N, B, t) : 0;
             tb[t] = reinterpret_cast<const double2 *>(tables + base) + (COOP ? j : 0);
-            shift[t] = 64 - (t < nt ? table16_start(N, t) : 0) - bits;
+            shift[t] = 64 - (t < nt ? table_start(N, B, t) : 0) - bits;
             msk[t] = (1u << bits) - 1u;
             base += ((size_t)1 << bits) * (COOP ? kCoopStride : EP);
         }
     }
     const int last_shift = shift[nt - 1];
-    const int lead_bits = 64 - last_shift - table16_bits(N, nt - 1);   // subjects covered by the leading tables
+    const int lead_bits = 64 - last_shift - table_bits(N, B, nt - 1);   // subjects covered by the leading tables
     unsigned long long *sb = sbuf[wid];
     const int64_t ntiles = draw_ntiles(P);
     const int64_t nwarps = (int64_t)gridDim.x * 8;
@@ -1476,6 +1496,16 @@ score_w1d_kernel(const uint64_t *__restrict__ rows, int64_t P, const double *__r
         const uint64_t r[4] = {rn[0], rn[1], rn[2], rn[3]};
         if (t + nwarps < ntiles) load_rows(t + nwarps, rn);     // next tile's rows in flight
         const int64_t k0 = t * kDrawTileRows + 4 * lane;
+        {
+            // ... and the tiles after it on their way from HBM to L2: with one tile of registers in flight per
+            // warp the row loads were the kernel's long-scoreboard stall (HBM latency under load exceeds a
+            // tile's processing time)
+            const int64_t kp = k0 + (int64_t)kPrefetchTiles * nwarps * kDrawTileRows;
+            if (kp + 3 < P) {
+                prefetch_l2(rows + kp);
+                if (STATS && log_prior) prefetch_l2(log_prior + kp);
+            }
+        }
         const bool full = k0 + 3 < P;
         const uint64_t prev = __shfl_up_sync(0xffffffffu, r[3], 1);
         const int h0 = (lane == 0) || (r[0] != prev);
@@ -1497,13 +1527,14 @@ score_w1d_kernel(const uint64_t *__restrict__ rows, int64_t P, const double *__r
         __syncwarp();
         if (!COOP) {
             // one lane per distinct row: the whole (packed, EP-double) entry of every table
+            // (two rows per lane per pass for tiles with D > 32 was measured slower: 1.62 vs 1.44 ms)
             for (int jj = lane; jj < D; jj += 32) {
                 const uint64_t rr = sb[jj];
                 double acc[EP];
 #pragma unroll
                 for (int e = 0; e < EP; ++e) acc[e] = 0.0;
 #pragma unroll
-                for (int tt = 0; tt < 4; ++tt)
+                for (int tt = 0; tt < kMaxTables; ++tt)
                     if (tt < nt)
                         lut_add_g<EP>(acc, reinterpret_cast<const double *>(tb[tt]) +
                                                (size_t)((unsigned)(rr >> shift[tt]) & msk[tt]) * EP);
@@ -1520,7 +1551,7 @@ score_w1d_kernel(const uint64_t *__restrict__ rows, int64_t P, const double *__r
             double2 lead = make_double2(0.0, 0.0);
             if (uniform) {
 #pragma unroll
-                for (int tt = 0; tt < 3; ++tt) {
+                for (int tt = 0; tt < kMaxTables - 1; ++tt) {
                     if (tt < nt - 1) {
                         const double2 v2 = __ldg(tb[tt] + (size_t)((unsigned)(first >> shift[tt]) & msk[tt]) * (kCoopStride / 2));
                         lead.x += v2.x;
@@ -1537,7 +1568,7 @@ score_w1d_kernel(const uint64_t *__restrict__ rows, int64_t P, const double *__r
                     const uint64_t rr = sb[idx < D ? idx : D - 1];
                     if (!uniform) {
 #pragma unroll
-                        for (int tt = 0; tt < 3; ++tt) {
+                        for (int tt = 0; tt < kMaxTables - 1; ++tt) {
                             if (tt < nt - 1) {
                                 const double2 v2 = __ldg(tb[tt] + (size_t)((unsigned)(rr >> shift[tt]) & msk[tt]) * (kCoopStride / 2));
                                 a[sr].x += v2.x;
@@ -1932,9 +1963,9 @@ static int launch_w1g(cudaStream_t st, const uint64_t *rows, int64_t P, double *
         const int64_t need = ceil_div64(draw_ntiles(P), 8);                                              \
         if (need < blocks) blocks = need;                                                                \
         if (blocks > kMaxStatCtas) blocks = kMaxStatCtas;                                                \
-        kern<<<(unsigned)blocks, 256, 0, st>>>(rows, P, ws, N, tables, out, status, log_prior, partials, \
-                                               tile_pairs, reinterpret_cast<unsigned int *>(ws + kTicketSlot), \
-                                               stats);                                                   \
+        kern<<<(unsigned)blocks, 256, 0, st>>>(rows, P, ws, N, tables, g_dedupe_bits, out, status, log_prior, \
+                                               partials, tile_pairs,                                      \
+                                               reinterpret_cast<unsigned int *>(ws + kTicketSlot), stats); \
         MITRE_LAUNCH_CHECK();                                                                            \
     }
         if (stats) {
@@ -2080,6 +2111,13 @@ namespace mitre {
 int launch_tile_pairs(cudaStream_t st, const double *a, const double *b, int64_t P, double *pairs);   // draw.cu
 }
 
+extern "C" int mitre_set_dedupe_table_bits(int bits)
+{
+    if (bits < 11 || bits > 16) return MITRE_ERR_INVALID;
+    g_dedupe_bits = bits;
+    return MITRE_OK;
+}
+
 extern "C" int mitre_set_dedupe(int mode)
 {
     if (mode < 0 || mode > 2) return MITRE_ERR_INVALID;
@@ -2111,8 +2149,11 @@ extern "C" int mitre_score_all_stats(void *stream, const uint64_t *packed_truth,
         dedupe_eligible(EPr, P, packed_truth, out, log_prior, tile_pairs)) {
         // base system + tables in one launch
         const int stride = g_dedupe == 2 ? kCoopStride : EPr;
-        score_prepare16_kernel<<<2 * sm_count(), 256, sizeof(double) * ((size_t)N * (EPr + p + 2)), st>>>(
-            X, omega, kappa, mask, N, p, sigma2, ws, status, stride, tables16_ptr(ws, N, EPr));
+        const size_t patterns = tables_doubles(N, g_dedupe_bits, 1);
+        int64_t pblocks = ceil_div64((int64_t)patterns, 256);
+        if (pblocks > 2 * sm_count()) pblocks = 2 * sm_count();
+        score_prepare16_kernel<<<(unsigned)pblocks, 256, sizeof(double) * ((size_t)N * (EPr + p + 2)), st>>>(
+            X, omega, kappa, mask, N, p, sigma2, ws, status, stride, g_dedupe_bits, tables16_ptr(ws, N, EPr));
     } else {
         score_setup_kernel<<<1, 256, 0, st>>>(X, omega, kappa, mask, N, p, sigma2, ws, status);
     }

@@ -59,7 +59,13 @@ def main():
         print("dedupe=%d  score_all        %.3f ms" % (dd, t(plain)))
         print("dedupe=%d  score_all_stats  %.3f ms" % (dd, t(stats)))
         print("dedupe=%d  stats, no prior  %.3f ms" % (dd, t(lambda: stats(pr=None))))
-    print("identical outputs: %s %s" % (torch.equal(res[0], res[1]), torch.equal(res[0], res[2])))
+    print("max rel diff dedupe vs plain kernels: %.2e %.2e" % (float(((res[0] - res[1]) / res[0]).abs().max()),
+                                                              float(((res[0] - res[2]) / res[0]).abs().max())))
+    lib().mitre_set_dedupe(1)
+    for bits in (11, 12, 13, 14, 16):
+        lib().mitre_set_dedupe_table_bits(bits)
+        print("dedupe=1 table bits %2d  score_all %.3f ms   score_all_stats %.3f ms" % (bits, t(plain), t(stats)))
+    lib().mitre_set_dedupe_table_bits(11)
     out, _, st = stats()
     k_tiles = int(D.draw_index(out, prior, 0.37, stabilise=True, buffers=draw, reuse_tiles=True).item())
     k_pass = int(D.draw_index(out, prior, 0.37, stabilise=True, buffers=draw, reuse_stats=True).item())
