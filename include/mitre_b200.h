@@ -343,6 +343,9 @@ int mitre_slope_guard(void *stream, const double *values, int64_t G, int N, cons
 int mitre_densify_perm(void *stream, const int64_t *perm_padded, int64_t P, int N,
                        const int64_t *row_offsets, int64_t *perm);
 int mitre_set_detector_split(int enable); /* tuning/test hook, see above */
+int mitre_set_sort_emit_rolled(int enable); /* sort/emit with rolled emission loops over shared-memory copies of the
+                                              sorted values (small code, ~70 registers) instead of the unrolled
+                                              register-resident variant */
 int mitre_selftest_divide(void *stream, const double *a, const int32_t *n, int64_t count,
                           double *fast, double *exact);
 

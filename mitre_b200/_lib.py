@@ -84,6 +84,7 @@ SIGNATURES = {
     "mitre_detector_sort_emit": (c_int, [c_void_p, c_void_p, c_i64, c_int] + [c_void_p] * 6),
     "mitre_slope_guard": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p, c_void_p]),
     "mitre_set_detector_split": (c_int, [c_int]),
+    "mitre_set_sort_emit_rolled": (c_int, [c_int]),
     "mitre_selftest_divide": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p]),
     "mitre_densify_perm": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p]),
     "mitre_row_groups": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_void_p]),

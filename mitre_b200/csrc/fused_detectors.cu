@@ -7,6 +7,7 @@
 
 namespace mitre {
 int g_detector_split = 1;
+int g_sort_emit_rolled = 0;
 SlopeGuardArgs g_slope_guard = {nullptr, nullptr, nullptr};
 int launch_slope_guard(cudaStream_t st, const double *values, int64_t G, int N, const uint8_t *group_type,
                        uint8_t *group_flags, unsigned long long *flagged);   // detectors.cu
@@ -467,6 +468,12 @@ extern "C" int mitre_densify_perm(void *stream, const int64_t *perm_padded, int6
     densify_perm_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(perm_padded, P, 2 * (N - 1), row_offsets,
                                                                          perm);
     MITRE_LAUNCH_CHECK();
+    return MITRE_OK;
+}
+
+extern "C" int mitre_set_sort_emit_rolled(int enable)
+{
+    g_sort_emit_rolled = enable ? 1 : 0;
     return MITRE_OK;
 }
 

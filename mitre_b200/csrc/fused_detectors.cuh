@@ -33,6 +33,7 @@
 namespace mitre {
 
 extern int g_detector_split;  // see mitre_set_detector_split
+extern int g_sort_emit_rolled; // 1: sort_emit_rolled_kernel instead of sort_emit_staged_kernel (mitre_set_sort_emit_rolled)
 
 // ---- slope guard band (SURVEY hard part 1) ------------------------------------------------------------
 // 'slope' values come from a closed form here and from an SVD least-squares solve in the reference
@@ -1210,6 +1211,195 @@ sort_emit_staged_kernel(const double *__restrict__ values, int64_t G, int N, dou
     if (tid == 0) bulk_wait0();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Rolled variant of the staged sort/emit kernel (mitre_set_detector_split(6)).  sort_emit_staged_kernel keeps
+// the sorted values and ids in registers through fully unrolled threshold / row loops: 150 registers (12 warps
+// per SM) and 4432 SASS instructions = 71 KB of code against a 32 KB instruction cache.  Here only the sorting
+// network itself (32-bit keys) is unrolled; the sorted values and ids go back to shared memory and every later
+// phase is a rolled loop over them:
+//   A [T][N]  values in (TMA)            -> thresholds out, [T][M] flat (bulk store)
+//   B [T][N]  sorted values              -> `above` rows, in place
+//   ID [NB][T] sorted subject ids (bytes)
+// rows: iteration k (descending) reads B[k-1], B[k], B[k+1] and then overwrites slot k+1 -- no longer needed --
+// with threshold k's row or, for a repeated midpoint, the marker kDupRow (bit 0 = subject 63, never set for
+// N <= 63); an ascending pass compacts the rows to slots 0 .. K-1 and pads with the ~0 sentinel.
+// ---------------------------------------------------------------------------------------------------------
+constexpr uint64_t kDupRow = 1ull;
+
+__host__ __device__ inline size_t sort_emit_rolled_bytes(int N, int NB)
+{
+    return (size_t)kStageThreads * (2 * (size_t)N * 8 + (size_t)NB);
+}
+
+template <int NB>
+__global__ void __launch_bounds__(kStageThreads, 8)
+sort_emit_rolled_kernel(const double *__restrict__ values, int64_t G, int N, double *__restrict__ thresholds,
+                        int32_t *__restrict__ K, uint64_t *__restrict__ rows, SlopeGuardArgs sg)
+{
+    extern __shared__ __align__(128) unsigned char stage_smem[];
+    __shared__ uint64_t bar;
+    constexpr int T = kStageThreads;
+    const int M = N - 1;
+    const int tid = threadIdx.x;
+    double *sA = reinterpret_cast<double *>(stage_smem);              // [T][N] values in; [T][M] thresholds out
+    double *sB = sA + (size_t)T * N;                                  // [T][N] sorted values, then rows
+    uint64_t *sBr = reinterpret_cast<uint64_t *>(sB);
+    uint8_t *sID = reinterpret_cast<uint8_t *>(sB + (size_t)T * N);   // [NB][T]
+    const uint64_t valid = ~0ull << (64 - N);
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+    const int64_t n_tiles = ceil_div64(G, T);
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t g0 = tile * T;
+        const int cnt = (int)((G - g0 < T) ? (G - g0) : T);
+        const bool full = cnt == T;
+        if (full) {
+            if (tid == 0) {
+                bulk_wait_read0();       // the previous tile's thresholds have left A
+                mbar_arrive_expect_tx(&bar, (uint32_t)(T * N * 8));
+                bulk_g2s(sA, values + g0 * N, (uint32_t)(T * N * 8), &bar);
+            }
+            mbar_wait(&bar, phase);
+            phase ^= 1;
+        } else {
+            if (tid == 0) bulk_wait_read0();
+            __syncthreads();
+            for (int i = tid; i < cnt * N; i += T) sA[i] = values[g0 * N + i];
+            __syncthreads();
+        }
+        double *a = sA + tid * N, *b = sB + tid * N;
+        uint64_t *br = sBr + tid * N;
+        {
+            // sort by 32-bit keys (registers), then sorted values and ids back to shared memory
+            uint32_t key[NB];
+#pragma unroll
+            for (int s = 0; s < NB; ++s) key[s] = (s < N) ? sort_key32(a[s], s) : (0xFFFFFFC0u | (uint32_t)s);
+            run_network_u32<NB>(key, std::make_index_sequence<NetHolder<NB>::net.count>{});
+#pragma unroll
+            for (int k = 0; k < NB; ++k) {
+                const int id = (int)(key[k] & 63u);
+                sID[k * T + tid] = (uint8_t)id;
+                if (k < N) b[k] = a[id];
+            }
+        }
+        // near-ties below the key's resolution: odd-even transposition on the exact values (rare)
+        {
+            bool bad = false;
+            for (int k = 0; k + 1 < N; ++k) bad |= b[k] > b[k + 1];
+            while (bad) {
+                bad = false;
+                for (int par = 0; par < 2; ++par)
+                    for (int k = par; k + 1 < N; k += 2) {
+                        const double x = b[k], y = b[k + 1];
+                        if (x > y) {
+                            bad = true;
+                            b[k] = y; b[k + 1] = x;
+                            const uint8_t i0 = sID[k * T + tid];
+                            sID[k * T + tid] = sID[(k + 1) * T + tid];
+                            sID[(k + 1) * T + tid] = i0;
+                        }
+                    }
+            }
+        }
+        if (sg.group_type && tid < cnt && sg.group_type[g0 + tid] == 0) {
+            // slope guard band, near-tie half (the constant-series half is the values kernel's)
+            const double tol = kSlopeGuard * fmax(fabs(b[0]), fabs(b[M]));
+            bool flag = false;
+            for (int k = 0; k < M; ++k) flag |= (b[k] != b[k + 1]) && (b[k + 1] - b[k] <= tol);
+            if (flag) sg.group_flags[g0 + tid] = 1;
+        }
+        __syncthreads();      // every thread has read its values from A: A becomes the thresholds tile
+        int kcount = 0;
+        {
+            double *tg = sA + tid * M;
+            double prev = 0.0, lo = b[0];
+            for (int k = 0; k < M; ++k) {
+                const double hi = b[k + 1];
+                const double m = __dmul_rn(0.5, __dadd_rn(lo, hi));
+                const bool u = (k == 0) || (m != prev);
+                tg[kcount] = m;   // a repeated midpoint is overwritten by its successor
+                kcount += u;
+                prev = m;
+                lo = hi;
+            }
+            for (int k2 = kcount; k2 < M; ++k2) tg[k2] = 0.0;
+            if (tid < cnt) K[g0 + tid] = kcount;
+        }
+        {
+            // rows, walking the sorted order downwards: acc = subjects at ranks > k; Tn = subjects after the
+            // run of values equal to v[k+1]
+            uint64_t acc = 1ull << (63 - sID[M * T + tid]), Tn = 0;
+            double vk1 = b[M], vk = b[M - 1];
+            double mk = __dmul_rn(0.5, __dadd_rn(vk, vk1));
+            for (int k = M - 1; k >= 0; --k) {
+                const double vkm = k > 0 ? b[k - 1] : 0.0;
+                const double mkm = __dmul_rn(0.5, __dadd_rn(vkm, vk));
+                const bool uniq = (k == 0) || (mk != mkm);
+                const uint64_t above = (mk == vk1) ? Tn : acc;
+                br[k + 1] = uniq ? above : kDupRow;
+                Tn = (vk == vk1) ? Tn : acc;
+                acc |= 1ull << (63 - sID[k * T + tid]);
+                vk1 = vk; vk = vkm; mk = mkm;
+            }
+            int pos = 0;
+            for (int j = 1; j <= M; ++j) {
+                const uint64_t r = br[j];
+                if (r != kDupRow) br[pos++] = r;
+            }
+            for (int k2 = pos; k2 < M; ++k2) br[k2] = ~0ull;
+        }
+        // ---- finished tiles -> global ----
+        if (full) fence_async_smem();
+        __syncthreads();
+        if (full) {
+            if (tid == 0) {
+                bulk_s2g(thresholds + g0 * M, sA, (uint32_t)(T * M * 8));
+                bulk_commit();
+            }
+        } else {
+            for (int i = tid; i < cnt * M; i += T) thresholds[g0 * M + i] = sA[i];
+        }
+        {
+            // rows tile has row stride N, the output is [groups][M] flat: (group, slot) advance without a division
+            ulonglong2 *out = reinterpret_cast<ulonglong2 *>(rows) + g0 * M;
+            const int n_out = cnt * M;
+            const int dg = T / M, dj = T - dg * M;
+            int g = tid / M, j = tid - g * M;
+            for (int i = tid; i < n_out; i += T) {
+                const uint64_t above = sBr[g * N + j];
+                out[i] = make_ulonglong2(above, above == ~0ull ? ~0ull : (~above & valid));
+                g += dg; j += dj;
+                if (j >= M) { j -= M; ++g; }
+            }
+        }
+        __syncthreads();   // B and ID are free for the next tile
+    }
+    if (tid == 0) bulk_wait0();
+}
+
+template <int NB>
+static int launch_sort_emit_rolled(cudaStream_t st, const double *values, int64_t G, int N, double *thresholds,
+                                   int32_t *K, uint64_t *rows)
+{
+    auto kern = sort_emit_rolled_kernel<NB>;
+    const size_t smem = sort_emit_rolled_bytes(N, NB);
+    MITRE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    MITRE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kStageThreads, smem));
+    if (per_sm < 1) return MITRE_ERR_UNSUPPORTED;
+    int64_t blocks = (int64_t)sm_count() * per_sm;
+    const int64_t need = ceil_div64(G, kStageThreads);
+    if (need < blocks) blocks = need;
+    if (blocks < 1) blocks = 1;
+    kern<<<(unsigned)blocks, kStageThreads, smem, st>>>(values, G, N, thresholds, K, rows, g_slope_guard);
+    MITRE_LAUNCH_CHECK();
+    return MITRE_OK;
+}
+
 template <int NB>
 static int launch_sort_emit_staged(cudaStream_t st, const double *values, int64_t G, int N, double *thresholds,
                                    int32_t *K, uint64_t *rows)
@@ -1260,6 +1450,7 @@ static int launch_split_impl(cudaStream_t st, const double *series_t, int64_t vs
     (void)series_t; (void)vstride; (void)V; (void)wlo; (void)wcnt; (void)wstart; (void)winv_n; (void)winv_sxx;
     (void)wdt; (void)ld; (void)group_base; (void)slope_ok; (void)task_window; (void)task_type; (void)n_wt;
     if (g_detector_split == 4) return launch_sort_emit<NB, 256, 1, false>(st, values, G, N, thresholds, K, rows);
+    if (g_sort_emit_rolled && N >= 2) return launch_sort_emit_rolled<NB>(st, values, G, N, thresholds, K, rows);
     return launch_sort_emit_staged<NB>(st, values, G, N, thresholds, K, rows);
 }
 

@@ -21,7 +21,8 @@ def build_gpu_population(d, pop_cfg, fused=True):
     from mitre_b200 import rules as R
     from mitre_b200._lib import lib
     lib().mitre_set_detector_split({"single": 0, "flat": 2, "tile": 3, "direct": 4}.get(fused, 1))
-    walk = fused is True          # True: the default (walk-forward values kernel); "resident" etc.: mitre_detectors_fused
+    lib().mitre_set_sort_emit_rolled(1 if fused == "rolled" else 0)
+    walk = fused is True or fused == "rolled"   # the default values kernel; "resident" etc.: mitre_detectors_fused
     fused = bool(fused)
     V = d["X"][0].shape[0]
     data = R.Dataset(d["X"], d["T"], d["y"], ["v%d" % i for i in range(V)], d["variable_weights"],
@@ -36,6 +37,7 @@ def build_gpu_population(d, pop_cfg, fused=True):
         R.DiscreteRulePopulation.use_fused = old
         R.DiscreteRulePopulation.use_walk = old_walk
         lib().mitre_set_detector_split(1)
+        lib().mitre_set_sort_emit_rolled(0)
     return data, pop
 
 
@@ -72,7 +74,7 @@ def check_population(pop, gold_windows, gold_ok, gold_groups, gold_values, gold_
         assert np.array_equal(pop.truth_table[t], DO.unpack_rows(gold_packed[i:i + 1], N)[0])
 
 
-@pytest.mark.parametrize("fused", [True, "resident", "tile", "flat", "direct", "single", False])
+@pytest.mark.parametrize("fused", [True, "rolled", "resident", "tile", "flat", "direct", "single", False])
 @pytest.mark.parametrize("name", sorted(MG.DETECTOR_CASES))
 def test_population_vs_reference_golden(name, fused):
     cfg = MG.DETECTOR_CASES[name]
@@ -89,7 +91,7 @@ def test_population_vs_reference_golden(name, fused):
     assert np.array_equal(pop.flat_truth, DO.unpack_rows(gold["sorted_truth_packed"], N))
 
 
-@pytest.mark.parametrize("fused", [True, "resident", "tile", "flat", "direct", "single", False])
+@pytest.mark.parametrize("fused", [True, "rolled", "resident", "tile", "flat", "direct", "single", False])
 @pytest.mark.parametrize("N,V,T,nint", [(2, 3, (2, 3), 1), (3, 2, (2, 4), 2), (8, 40, (3, 6), 3), (9, 33, (3, 6), 3),
                                         (16, 3, (2, 5), 2), (24, 2, (3, 5), 2), (33, 5, (3, 20), 6),
                                         (40, 70, (3, 7), 2), (41, 2, (3, 7), 2), (48, 3, (3, 7), 2),
@@ -240,7 +242,7 @@ def test_exact_division_selftest():
     assert np.array_equal(exact, a / n)
 
 
-@pytest.mark.parametrize("fused", [True, "resident", "tile", "flat", "direct", "single", False])
+@pytest.mark.parametrize("fused", [True, "rolled", "resident", "tile", "flat", "direct", "single", False])
 def test_near_ties_below_key_resolution_take_the_exact_path(fused):
     """Values that differ only in their lowest mantissa bits collide in the 32-bit sort key (float32
     image of the value with the subject id in the low 6 bits); the kernel must detect the mis-ordered
@@ -301,7 +303,7 @@ def _criterion(values, group_type):
     return flags
 
 
-@pytest.mark.parametrize("fused", [True, "resident", "direct", False])
+@pytest.mark.parametrize("fused", [True, "rolled", "resident", "direct", False])
 def test_slope_guard_flags_the_constant_series_divergence(fused):
     """det_constslope (reference fixture): every group whose rows differ from the reference's is flagged,
     the flags are exactly the documented criterion, and nothing outside slope groups is flagged."""
@@ -321,7 +323,7 @@ def test_slope_guard_flags_the_constant_series_divergence(fused):
     assert len(pop.flagged_groups()) == int(flags.sum())
 
 
-@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("fused", [True, "rolled", False])
 def test_slope_guard_flags_near_ties_and_nothing_else(fused):
     """Two subjects whose slopes agree to 1e-13: their order is not certain (closed form here, LAPACK gelsd
     in the reference), so the group is flagged; every unflagged group carries the oracle's rows."""

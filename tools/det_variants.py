@@ -44,7 +44,13 @@ def main():
         means_same = torch.equal(ref[0][1::2], out[0][1::2]) if bool(wa[10].all()) else None
         print("%-36s %.3f ms  thresholds/K/rows identical=%s  means identical=%s" % ("walk values + staged sort/emit", ms,
                                                                                     same, means_same))
-        for ns in (1, 2, 4, 8, 12, 24):
+        lib().mitre_set_sort_emit_rolled(1)
+        o3 = D.detectors_walk(*wa)
+        ms = min(bench.cuda_time_ms(torch, lambda: D.detectors_walk(*wa), 10) for _ in range(3))
+        print("%-36s %.3f ms  identical to the unrolled sort/emit=%s" % ("walk values + ROLLED sort/emit", ms,
+                                                                        all(torch.equal(a, b) for a, b in zip(out, o3))))
+        lib().mitre_set_sort_emit_rolled(0)
+        for ns in (1, 4):
             stages = D.walk_stages(pop._walk_first, pop._group_base, pop._G, ns) if ns > 1 else None
             args = wa[:15] + (stages,)
             o2 = D.detectors_walk(*args)
