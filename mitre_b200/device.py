@@ -568,6 +568,44 @@ def gibbs_read_back(om, beta_io, betas, status):
             packed[:n_iters * p].reshape(n_iters, p).copy())
 
 
+class GibbsWorkspace:
+    """Persistent staging for the sampler's omega / beta sweeps: ONE pinned -> device copy in (X, kappa,
+    beta, cleared status slot), one launch, ONE device -> pinned copy out (betas, omega, beta, status), one
+    synchronisation.  gibbs_omega_beta + gibbs_read_back made three pageable host->device copies, a fill
+    kernel and a concatenation per call -- a quarter of an S2 sampler step."""
+
+    def __init__(self, N, p, n_iters):
+        self.N, self.p, self.n = int(N), int(p), int(n_iters)
+        n_in = self.N * self.p + self.N + self.p + 1           # X, kappa, beta, status slot
+        n_out = self.n * self.p + self.N                         # betas, omega
+        self.h = torch.zeros(n_in + n_out, dtype=F64).pin_memory()
+        self.d = torch.zeros(n_in + n_out, dtype=F64, device=dev())
+        self.n_in = n_in
+
+    def run(self, X, kappa, prior_variance, beta, seed):
+        N, p, n, n_in = self.N, self.p, self.n, self.n_in
+        h = self.h.numpy()
+        h[:N * p] = np.asarray(X, dtype=np.float64).reshape(-1)
+        h[N * p:N * p + N] = kappa
+        h[N * p + N:N * p + N + p] = beta
+        h[n_in - 1] = 0.0
+        d = self.d
+        d[:n_in].copy_(self.h[:n_in], non_blocking=True)
+        dX, dk = d[:N * p], d[N * p:N * p + N]
+        beta_io = d[N * p + N:N * p + N + p]
+        status = d[n_in - 1:n_in].view(I32)[:1]
+        betas, om = d[n_in:n_in + n * p], d[n_in + n * p:]
+        check(lib().mitre_gibbs_omega_beta(_stream(), _p(dX), _p(dk), N, p, float(prior_variance), n, 0,
+                                           int(seed) & 0xFFFFFFFFFFFFFFFF, _p(beta_io), _p(om), _p(betas),
+                                           _p(status)), "mitre_gibbs_omega_beta")
+        self.h.copy_(d, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        flags = int(h[n_in - 1:n_in].view(np.int32)[0])
+        if flags:
+            raise np.linalg.LinAlgError("Matrix is not positive definite (status flags %d)" % flags)
+        return (h[n_in + n * p:].copy(), h[N * p + N:N * p + N + p].copy(), h[n_in:n_in + n * p].reshape(n, p).copy())
+
+
 def pg_draw(z, seed):
     z = _dev_f64(z)
     out = torch.empty_like(z)

@@ -487,6 +487,12 @@ class LogisticRuleSampler(RuleListSampler):
         self.window_concentration_proposal_std = (self.model.window_concentration_typical *
                                                   self.model.window_concentration_update_ratio)
 
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state.pop('_gibbs_ws', None)          # device / pinned staging: rebuilt on first use
+        state['_current_prior_value'] = None
+        return state
+
     def ensure_current_rl_sorted(self):
         rl = self.current_state.rl
         for i in range(len(rl)):
@@ -512,8 +518,13 @@ class LogisticRuleSampler(RuleListSampler):
             self.move_primitive()
         self.update_beta()
         self.update_empty_probability()
-        self.update_window_parameters()
-        prior = self.update_phylogeny_parameters()
+        self._in_step = True
+        try:
+            self.update_window_parameters()
+            prior = self.update_phylogeny_parameters()
+        finally:
+            self._in_step = False
+            self._current_prior_value = None
         self.states.append(self.current_state.copy())
         self.likelihoods.append(
             self.model.likelihood_y_given_X_beta(self.current_X, self.current_state.beta))
@@ -531,14 +542,22 @@ class LogisticRuleSampler(RuleListSampler):
     def parameter_mh_update(self, proposed_state):
         """logit_rules.py:615-649."""
         proposed_prior = self.model.prior(proposed_state)
-        current_prior = self.model.prior(self.current_state)
+        # the four hyperparameter updates of a step run back to back on a state that only they change, so the
+        # prior of the current state is the value the previous update ended with (the reference recomputes it:
+        # same function of the same state, same number); update_window_parameters starts the run
+        current_prior = self.__dict__.get('_current_prior_value')
+        if current_prior is None:
+            current_prior = self.model.prior(self.current_state)
         acceptance_probability = np.exp(proposed_prior - current_prior)
         if np.random.rand() < acceptance_probability:
             self.current_state = proposed_state
+            self._current_prior_value = proposed_prior
             return proposed_prior
+        self._current_prior_value = current_prior
         return current_prior
 
     def update_window_parameters(self):
+        self._current_prior_value = None      # the structure move / beta / empty-probability updates came before
         delta_f = self.window_fraction_proposal_std * np.random.randn()
         current_f = self.current_state.window_typical_fraction
         proposed_state = self.current_state.copy()
@@ -551,6 +570,8 @@ class LogisticRuleSampler(RuleListSampler):
         self.parameter_mh_update(proposed_state)
 
     def update_phylogeny_parameters(self):
+        if not self.__dict__.get('_in_step'):
+            self._current_prior_value = None  # called on its own: nothing is known about the current state
         delta_mean = self.phylogeny_mean_proposal_std * np.random.randn()
         current_mean = self.current_state.phylogeny_mean
         proposed_state = self.current_state.copy()
@@ -588,9 +609,12 @@ class LogisticRuleSampler(RuleListSampler):
         p = self.current_X.shape[1]
         beta0 = state.beta if len(state.beta) == p else np.zeros(p)
         seed = int(np.random.randint(0, 2 ** 62))
-        omega, beta, betas, status = D.gibbs_omega_beta(
-            self.current_X, self.model.data.y - 0.5, self.model.prior_coefficient_variance, beta0, n, seed)
-        state.omega, state.beta, betas_h = D.gibbs_read_back(omega, beta, betas, status)   # one D2H, one sync
+        ws = self.__dict__.setdefault('_gibbs_ws', {})
+        key = (self.current_X.shape[0], p, n)
+        if key not in ws:
+            ws[key] = D.GibbsWorkspace(*key)
+        state.omega, state.beta, betas_h = ws[key].run(self.current_X, self.model.data.y - 0.5,
+                                                       self.model.prior_coefficient_variance, beta0, seed)
         return [betas_h[i].copy() for i in range(n)]
 
     def update_omega(self):
