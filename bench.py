@@ -645,10 +645,13 @@ def run_b200(args):
                 line["cpu_baseline"] = cpu_baseline(args, pop, state, N, P, torch, D)
         print_line = line
     sw.close()
+    del sw, prior, local_rows, scorer_out
+    pop = None
+    torch.cuda.empty_cache()
+    chains_line = chains_throughput(torch, dist, world, args.seed)
     if rank == 0:
+        print_line["chains"] = chains_line
         if world == 1 and not args.no_cpu_baseline:
-            del pop, local_rows, sw, prior
-            torch.cuda.empty_cache()
             print_line["mcmc"] = mcmc_samples_per_sec(args)
         print(json.dumps(print_line))
     if world > 1:
@@ -745,6 +748,33 @@ def cpu_baseline(args, pop, state, N, P, torch, D):
             "kernel_only_value": done / (spent - marshal), "max_rel_diff_vs_gpu": check_rel}
 
 
+def chains_throughput(torch, dist, world, seed, chains_per_gpu=8, steps=100):
+    """BASELINE configs[3] (64 independent chains of the Bokulich-shape problem over 8 GPUs, the reference's
+    [replicates] mode, main.py:1913-1986): every rank builds the S2 model on its GPU and runs
+    `chains_per_gpu` seeded replicas one after another, no collective while sampling; aggregate samples/s
+    over the slowest rank."""
+    from mitre_b200 import chains
+    rank = int(os.environ.get("RANK", "0"))
+    data, model = chains.build_model("S2", seed=seed)
+    r0 = chains.initial_rule_list(model)
+    chains.run_chain(model, 1, 3, r0, device_gibbs=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    lengths = []
+    for c in range(chains_per_gpu):
+        sampler = chains.run_chain(model, seed + rank * chains_per_gpu + c, steps, r0, device_gibbs=True)
+        lengths.append(len(sampler.current_state.rl))
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    return {"what": "independent S2 chains (replicas, seeds base + i), device draw + device Gibbs, %d per GPU "
+                    "one after another, no collective while sampling" % chains_per_gpu,
+            "chains": world * chains_per_gpu, "steps_per_chain": steps, "candidates": len(model.rule_population),
+            "samples_per_sec": world * chains_per_gpu * steps / float(dt[0]), "wall_s": float(dt[0])}
+
+
 def mcmc_samples_per_sec(args):
     """BASELINE.json's second metric: MCMC samples/s of the Bokulich-shaped problem (S2: N=35,
     V=200, 12 intervals, t in [1,180]) with the B200 likelihood path vs the same host sampler
@@ -757,7 +787,7 @@ def mcmc_samples_per_sec(args):
     r0 = chains.initial_rule_list(model)
     chains.run_chain(model, 1, 3, r0)                      # warm-up
     torch.cuda.synchronize()
-    steps = 40
+    steps = 300                                            # cfg2: 300 MCMC samples
     t0 = time.perf_counter()
     chains.run_chain(model, 2, steps, r0)
     gpu = steps / (time.perf_counter() - t0)

@@ -48,6 +48,38 @@ def run_chain(model, seed, steps, r0=None, device_draw=True, device_gibbs=False)
     return sampler
 
 
+def scalar_traces(sampler):
+    """float64[steps, 6] per-step scalars of a chain: rules, detectors, log-likelihood, log-prior, phylogeny
+    mean, window concentration -- the kind of columns the reference writes to `_mcmc_traces.csv`
+    (posterior.py:81-137) and feeds to its R-hat tool."""
+    rows = []
+    for st, lik, pri in zip(sampler.states, sampler.likelihoods, sampler.priors):
+        rows.append([len(st.rl), sum(len(r) for r in st.rl.rules), lik, pri, st.phylogeny_mean,
+                     st.window_concentration])
+    return np.asarray(rows, dtype=np.float64)
+
+
+def split_r_hat(traces):
+    """Gelman's potential scale reduction over independent runs, each split in halves, as the reference's
+    `mitre_mcmc_diagnostics` computes it (mcmc_diagnostics.py:39-84: first half without its last sample,
+    second half from the midpoint; within-run variances over n - 1, n = the shortest half minus one as in
+    its `compute_R_hat(runs2, n - 1)` call).  traces: list of float[steps, k] -> float64[k]."""
+    halves = []
+    for t in traces:
+        t = np.asarray(t, dtype=np.float64)
+        mid = t.shape[0] // 2
+        halves += [t[:mid - 1], t[mid:]]
+    n = min(h.shape[0] for h in halves) - 1
+    x = np.stack([h[:n] for h in halves])                    # [m, n, k]
+    m = x.shape[0]
+    means = x.mean(axis=1)
+    within = ((x - means[:, None, :]) ** 2).sum(axis=1) / (n - 1)
+    B = n * ((means - means.mean(axis=0)) ** 2).sum(axis=0) / (m - 1)
+    W = within.mean(axis=0)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        return np.sqrt((W * (n - 1) / n + B / n) / W)
+
+
 def summarize(sampler, burnin_fraction=0.05):
     from .posterior import PosteriorSummary
     s = PosteriorSummary(sampler, burnin_fraction=burnin_fraction)

@@ -81,3 +81,24 @@ def test_chain_with_device_gibbs_runs_and_is_seed_deterministic():
     assert a.comments == b.comments
     assert np.all(np.isfinite(a.likelihoods)) and len(a.states) == 25
     assert np.all(a.current_state.omega > 0)
+
+
+def test_device_gibbs_chains_mix_with_host_gibbs_chains():
+    """Chain-level check of the device omega/beta sweeps (pypolyagamma is absent and unpinned, so the device
+    Philox / Devroye stream cannot be compared draw for draw): four chains with the host Polya-Gamma sampler
+    and four with the device kernel, same model, pooled into one split R-hat (the reference's own
+    convergence tool, mcmc_diagnostics.py:57-84).  If the device sweeps sampled a different conditional the
+    two families would not mix and R-hat of the pooled runs would sit well above that of either family."""
+    from mitre_b200 import chains
+    data, model = chains.build_model("S2", seed=11, variables=5)
+    r0 = chains.initial_rule_list(model)
+    steps = 240
+    host = [chains.scalar_traces(chains.run_chain(model, 100 + i, steps, r0, device_gibbs=False))[40:] for i in range(4)]
+    dev = [chains.scalar_traces(chains.run_chain(model, 200 + i, steps, r0, device_gibbs=True))[40:] for i in range(4)]
+    cols = [2, 3]                                        # log-likelihood, log-prior: continuous, every step
+    r_host = chains.split_r_hat([t[:, cols] for t in host])
+    r_dev = chains.split_r_hat([t[:, cols] for t in dev])
+    r_all = chains.split_r_hat([t[:, cols] for t in host + dev])
+    assert np.all(np.isfinite(r_all))
+    assert np.all(r_all < 1.3), (r_host, r_dev, r_all)
+    assert np.all(r_all < np.maximum(r_host, r_dev) + 0.15), (r_host, r_dev, r_all)

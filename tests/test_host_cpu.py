@@ -137,3 +137,44 @@ def test_polyagamma_large_argument_does_not_overflow():
         x = pg.pgdraw(1, z)
         assert np.isfinite(x) and x > 0
         assert abs(x - 0.5 / abs(z)) < 0.5 / abs(z)      # PG(1, z) concentrates at tanh(z/2) / (2 z)
+
+
+def test_split_r_hat_equals_the_reference_restatement():
+    """chains.split_r_hat against a line-by-line restatement of mcmc_diagnostics.py:39-84 (divide_runs +
+    compute_R_hat as generate_diagnostics calls them)."""
+    from mitre_b200 import chains
+    rng = np.random.RandomState(8)
+    runs = [np.cumsum(rng.normal(size=(401, 3)), axis=0) * 0.05 + rng.normal(size=(401, 3)) for _ in range(3)]
+
+    def divide_runs(runs):                                   # mcmc_diagnostics.py:39-55 (column 0 kept here)
+        out = []
+        for r in runs:
+            spl = int(np.floor(r.shape[0] / 2))
+            out.append(r[0:(spl - 1), :])
+            out.append(r[spl:r.shape[0], :])
+        return out
+
+    def compute_R_hat(runs2, n):                             # mcmc_diagnostics.py:57-84
+        m, nv = len(runs2), runs2[0].shape[1]
+        pj, sj = np.zeros((m, nv)), np.zeros((m, nv))
+        for j in range(m):
+            pj[j, :] = np.mean(runs2[j][0:n, :], axis=0)
+        for j in range(m):
+            sj[j, :] = np.sum(np.power(runs2[j][0:n, :] - pj[j, :], 2.0), axis=0) / (n - 1)
+        B = np.zeros(nv)
+        pp = np.mean(pj, axis=0)
+        for j in range(m):
+            B = B + np.power(pj[j] - pp, 2.0)
+        B = B * n / (m - 1)
+        W = np.mean(sj, axis=0)
+        return np.sqrt((W * (n - 1) / n + B / n) / W)
+
+    runs2 = divide_runs(runs)
+    n = min(r.shape[0] for r in runs2)
+    want = compute_R_hat(runs2, n - 1)
+    got = chains.split_r_hat(runs)
+    assert np.allclose(got, want, rtol=1e-12, atol=0)
+    same = [rng.normal(size=(300, 2)) for _ in range(4)]
+    assert np.all(chains.split_r_hat(same) < 1.05)
+    shifted = [rng.normal(size=(300, 2)) + 3.0 * i for i in range(4)]
+    assert np.all(chains.split_r_hat(shifted) > 2.0)
