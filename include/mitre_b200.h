@@ -227,6 +227,24 @@ size_t mitre_lexsort_workspace_bytes(int64_t P, int W64);
 int mitre_lexsort_rows(void *stream, const uint64_t *rows, int64_t P, int W64, int N,
                        int64_t *perm, uint64_t *sorted_rows, void *workspace,
                        size_t workspace_bytes);
+/* Tables whose row and enumeration index fit one 64-bit word (W64 == 1, N + bits(P) <= 64, P < 2^30: S2, S5)
+ * take a one-sweep LSD radix sort of (row | index) words -- ceil(N / 9) passes, each reading its input once
+ * (decoupled look-back between tiles), same permutation.  mitre_set_packed_sort(0) keeps the general path
+ * (returns the previous setting).
+ *   mitre_lexsort_padded  the same sort straight from the padded detector output rows_padded
+ *       uint64[P_slots] (mitre_detectors_fused: 2(N-1) slots per group, unused slots = ~0): sentinel slots are
+ *       dropped in the first pass, the last pass writes sorted_rows uint64[P_valid] (may be NULL) and
+ *       perm int64[P_valid] already mapped from slot indices to dense enumeration indices through
+ *       row_offsets int64[G+1] (what mitre_densify_perm does).  MITRE_ERR_UNSUPPORTED when the table is not
+ *       eligible: use mitre_lexsort_rows(..., N + 1, ...) + mitre_densify_perm then.
+ *   mitre_lexsort_check   synchronises the stream and reports whether a look-back wait of the last packed
+ *       sort in `workspace` expired (never observed; the waits are bounded so that a lost CTA cannot hang the
+ *       device): MITRE_OK or MITRE_ERR_UNSUPPORTED. */
+int mitre_lexsort_padded(void *stream, const uint64_t *rows_padded, int64_t P_slots, int N,
+                         int64_t P_valid, const int64_t *row_offsets, int64_t *perm,
+                         uint64_t *sorted_rows, void *workspace, size_t workspace_bytes);
+int mitre_lexsort_check(void *stream, void *workspace, int64_t P, int N);
+int mitre_set_packed_sort(int enable);
 
 /* ---- fused detector evaluation (N <= 63): values + thresholds + truth rows, no host round trip --
  *
@@ -343,6 +361,9 @@ int mitre_slope_guard(void *stream, const double *values, int64_t G, int N, cons
 int mitre_densify_perm(void *stream, const int64_t *perm_padded, int64_t P, int N,
                        const int64_t *row_offsets, int64_t *perm);
 int mitre_set_detector_split(int enable); /* tuning/test hook, see above */
+int mitre_set_walk_vpt(int vpt);          /* variables per thread of the walk-forward values kernel: 1 (default) or 2 (
+                                             shared control flow, two interleaved fp64 chains; measured slower: 1.12 vs 0.82 ms at S5); same values.
+                                             Returns the previous setting. */
 int mitre_set_sort_emit_rolled(int enable); /* sort/emit with rolled emission loops over shared-memory copies of the
                                               sorted values (small code, ~70 registers) instead of the unrolled
                                               register-resident variant */

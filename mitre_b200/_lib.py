@@ -69,6 +69,10 @@ SIGNATURES = {
     "mitre_lexsort_workspace_bytes": (c_size_t, [c_i64, c_int]),
     "mitre_lexsort_rows": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p, c_size_t]),
+    "mitre_lexsort_padded": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_i64, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_size_t]),
+    "mitre_lexsort_check": (c_int, [c_void_p, c_void_p, c_i64, c_int]),
+    "mitre_set_packed_sort": (c_int, [c_int]),
     "mitre_window_lists": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_i64, c_i64] +
                            [c_void_p] * 7),
     "mitre_detectors_fused": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int] + [c_void_p] * 7 +
@@ -84,6 +88,7 @@ SIGNATURES = {
     "mitre_detector_sort_emit": (c_int, [c_void_p, c_void_p, c_i64, c_int] + [c_void_p] * 6),
     "mitre_slope_guard": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p, c_void_p]),
     "mitre_set_detector_split": (c_int, [c_int]),
+    "mitre_set_walk_vpt": (c_int, [c_int]),
     "mitre_set_sort_emit_rolled": (c_int, [c_int]),
     "mitre_selftest_divide": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p]),
     "mitre_densify_perm": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p]),

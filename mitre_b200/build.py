@@ -73,7 +73,10 @@ def build(force=False, verbose=False):
     for f in stale:
         os.remove(os.path.join(OBJ, f))
     if force or jobs or _newer(LIB, objs):
-        subprocess.check_call([nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart"])
+        # link beside the target and rename: a snapshot of the tree never sees a half-written library
+        tmp = LIB + ".tmp%d" % os.getpid()
+        subprocess.check_call([nvcc] + ARCH + ["-shared", "-o", tmp] + objs + ["-lcudart"])
+        os.replace(tmp, LIB)
     return LIB
 
 

@@ -295,6 +295,39 @@ extern "C" int mitre_window_tbar(void *stream, const double *times, int N, const
 // The block's start groups are chosen so that the (window, subject) tables of ALL its windows fit in shared
 // memory next to the series tile: sg_first is a host-visible copy is not available here, so the launcher
 // takes the window count of the fullest chunk from the caller (max_block_windows) for a given split.
+static int g_walk_vpt = 1;   // variables per thread of values_walk_kernel
+
+extern "C" int mitre_set_walk_vpt(int vpt)
+{
+    const int old = g_walk_vpt;
+    g_walk_vpt = vpt == 1 ? 1 : 2;
+    return old;
+}
+
+static int launch_values_walk(cudaStream_t st, dim3 grid, size_t smem, const double *series, int64_t series_stride,
+                              const double *times, const int32_t *t_offsets, int S, int N, int V, const double *windows,
+                              const int32_t *wlo, const int32_t *wcnt, const double *winv_sxx, const double *wtbar,
+                              const int64_t *group_base, const uint8_t *slope_ok, const int32_t *sg_first, int sg_base,
+                              int n_sg, int sg_per_block, int max_block_windows, double *values, uint8_t *group_flags)
+{
+    const int VB = walk_vars_per_block(N);
+    const int vpt = (g_walk_vpt == 2 && VB >= 2) ? 2 : 1;
+    const int threads = ((((VB + vpt - 1) / vpt) * N + 31) / 32) * 32;
+    if (vpt == 2) {
+        MITRE_CUDA_TRY(cudaFuncSetAttribute(values_walk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        values_walk_kernel<2><<<grid, threads, smem, st>>>(series, series_stride, times, t_offsets, S, N, V, windows, wlo,
+                                                           wcnt, winv_sxx, wtbar, group_base, slope_ok, sg_first, sg_base,
+                                                           n_sg, sg_per_block, max_block_windows, values, group_flags);
+    } else {
+        MITRE_CUDA_TRY(cudaFuncSetAttribute(values_walk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        values_walk_kernel<1><<<grid, threads, smem, st>>>(series, series_stride, times, t_offsets, S, N, V, windows, wlo,
+                                                           wcnt, winv_sxx, wtbar, group_base, slope_ok, sg_first, sg_base,
+                                                           n_sg, sg_per_block, max_block_windows, values, group_flags);
+    }
+    MITRE_LAUNCH_CHECK();
+    return MITRE_OK;
+}
+
 extern "C" size_t mitre_values_walk_smem_bytes(int N, int S, int max_block_windows)
 {
     if (N <= 0 || S <= 0 || max_block_windows <= 0) return 0;
@@ -318,16 +351,12 @@ extern "C" int mitre_detector_values_walk(void *stream, const double *series, in
         return MITRE_ERR_INVALID;
     const size_t smem = mitre_values_walk_smem_bytes(N, S, max_block_windows);
     if (smem > smem_optin()) return MITRE_ERR_UNSUPPORTED;
-    MITRE_CUDA_TRY(cudaFuncSetAttribute(values_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int VB = walk_vars_per_block(N);
     const int tiles = (V + VB - 1) / VB;
     const int chunks = (n_sg + sg_per_block - 1) / sg_per_block;
-    const int threads = ((VB * N + 31) / 32) * 32;
-    values_walk_kernel<<<dim3((unsigned)tiles, (unsigned)chunks), threads, smem, as_stream(stream)>>>(
-        series, series_stride, times, t_offsets, S, N, V, windows, wlo, wcnt, winv_sxx, wtbar, group_base, slope_ok,
-        sg_first, 0, n_sg, sg_per_block, max_block_windows, values, group_flags);
-    MITRE_LAUNCH_CHECK();
-    return MITRE_OK;
+    return launch_values_walk(as_stream(stream), dim3((unsigned)tiles, (unsigned)chunks), smem, series, series_stride,
+                              times, t_offsets, S, N, V, windows, wlo, wcnt, winv_sxx, wtbar, group_base, slope_ok,
+                              sg_first, 0, n_sg, sg_per_block, max_block_windows, values, group_flags);
 }
 
 // ---- the two halves pipelined over runs of start groups ---------------------------------------------------
@@ -387,7 +416,6 @@ extern "C" int mitre_detectors_walk(void *stream, const double *series, int64_t 
     if (flagged && !group_flags) return MITRE_ERR_INVALID;
     const size_t smem = mitre_values_walk_smem_bytes(N, S, max_block_windows);
     if (smem > smem_optin()) return MITRE_ERR_UNSUPPORTED;
-    MITRE_CUDA_TRY(cudaFuncSetAttribute(values_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaStream_t user = as_stream(stream);
     WalkPipe &wp = g_walk_pipe;
     MITRE_CUDA_TRY(wp.ensure(n_stages));
@@ -398,7 +426,6 @@ extern "C" int mitre_detectors_walk(void *stream, const double *series, int64_t 
     MITRE_CUDA_TRY(cudaStreamWaitEvent(wp.st[1], wp.fork, 0));
     const int VB = walk_vars_per_block(N);
     const int tiles = (V + VB - 1) / VB;
-    const int threads = ((VB * N + 31) / 32) * 32;
     const int M = N - 1;
     const int saved = g_detector_split;
     int rc = MITRE_OK;
@@ -407,10 +434,10 @@ extern "C" int mitre_detectors_walk(void *stream, const double *series, int64_t 
         const int64_t g0 = stage_group_host[c], g1 = stage_group_host[c + 1];
         if (sg1 <= sg0 || g1 <= g0) continue;
         const int chunks = (sg1 - sg0 + sg_per_block - 1) / sg_per_block;
-        values_walk_kernel<<<dim3((unsigned)tiles, (unsigned)chunks), threads, smem, wp.st[0]>>>(
-            series, series_stride, times, t_offsets, S, N, V, windows, wlo, wcnt, winv_sxx, wtbar, group_base,
-            slope_ok, sg_first, sg0, sg1, sg_per_block, max_block_windows, values, group_flags);
-        MITRE_LAUNCH_CHECK();
+        rc = launch_values_walk(wp.st[0], dim3((unsigned)tiles, (unsigned)chunks), smem, series, series_stride, times,
+                                t_offsets, S, N, V, windows, wlo, wcnt, winv_sxx, wtbar, group_base, slope_ok,
+                                sg_first, sg0, sg1, sg_per_block, max_block_windows, values, group_flags);
+        if (rc != MITRE_OK) break;
         MITRE_CUDA_TRY(cudaEventRecord(wp.done[c], wp.st[0]));
         MITRE_CUDA_TRY(cudaStreamWaitEvent(wp.st[1], wp.done[c], 0));
         g_detector_split = 1;

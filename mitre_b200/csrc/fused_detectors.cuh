@@ -60,6 +60,17 @@ __device__ __forceinline__ bool near_tie(double a, double b, double scale)   // 
     return a != b && (b - a) <= kSlopeGuard * scale;
 }
 
+// shared-memory stores through a 32-bit shared address that the emission loops advance themselves (the
+// generic pointer + index form was re-derived from the window base on every iteration)
+__device__ __forceinline__ void sts_f64(uint32_t addr, double v)
+{
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void sts_u64(uint32_t addr, uint64_t v)
+{
+    asm volatile("st.shared.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+
 // ---- compile-time Batcher merge-exchange network for n inputs ------------------------------------
 template <int N>
 struct Network {
@@ -134,20 +145,28 @@ __device__ __forceinline__ void run_network_u32(uint32_t (&k)[N], std::index_seq
     (cmp_exchange_u32(k[NetHolder<N>::net.a[I]], k[NetHolder<N>::net.b[I]]), ...);
 }
 
+// The launchers instantiate NB = N rounded up to a multiple of 4, so NB - 4 < N <= NB: only the last three
+// elements / four thresholds of the unrolled loops need a run-time comparison with N; for every other index
+// the bound folds at compile time (a run-time test per index was a compare and a branch per iteration and
+// kept the midpoints from being shared between iterations).
+#define MITRE_LT_N(s) ((s) < NB - 3 || (s) < N)
+#define MITRE_LT_M(k) ((k) < NB - 4 || (k) < M)
+#define MITRE_EQ_M(k) ((k) >= NB - 4 && (k) == M)
+
 // Sorted (value, id) pairs of one group from its values row `vin` (shared memory, N doubles).
 template <int NB>
 __device__ __forceinline__ void sort_group_key32(const double *vin, int N, double (&val)[NB], int (&id)[NB])
 {
     uint32_t key[NB];
 #pragma unroll
-    for (int s = 0; s < NB; ++s) key[s] = (s < N) ? sort_key32(vin[s], s) : (0xFFFFFFC0u | (uint32_t)s);
+    for (int s = 0; s < NB; ++s) key[s] = MITRE_LT_N(s) ? sort_key32(vin[s], s) : (0xFFFFFFC0u | (uint32_t)s);
     run_network_u32<NB>(key, std::make_index_sequence<NetHolder<NB>::net.count>{});
     bool bad = false;
 #pragma unroll
     for (int k = 0; k < NB; ++k) {
         id[k] = (int)(key[k] & 63u);
-        val[k] = (k < N) ? vin[id[k]] : INFINITY;
-        if (k > 0 && k < N) bad |= val[k - 1] > val[k];
+        val[k] = MITRE_LT_N(k) ? vin[id[k]] : INFINITY;
+        if (k > 0 && MITRE_LT_N(k)) bad |= val[k - 1] > val[k];
     }
     while (bad) {   // rare: near-ties below the key's resolution
         bad = false;
@@ -155,7 +174,7 @@ __device__ __forceinline__ void sort_group_key32(const double *vin, int N, doubl
         for (int par = 0; par < 2; ++par) {
 #pragma unroll
             for (int k = par; k + 1 < NB; k += 2) {
-                if (k + 1 < N) {
+                if (MITRE_LT_N(k + 1)) {
                     bad |= val[k] > val[k + 1];
                     cmp_exchange(val[k], val[k + 1], id[k], id[k + 1]);
                 }
@@ -873,6 +892,7 @@ values_resident_kernel(const double *__restrict__ series_t, int64_t vstride, int
 // own count) while the emissions are converged.
 // =================================================================================================
 constexpr int kWalkMaxThreads = 640;
+constexpr int kWalk2MaxThreads = 384;   // two variables per thread: ceil(VB / 2) * N <= 320 + N / 2, rounded to warps
 
 __host__ __device__ inline int walk_vars_per_block(int N)
 {
@@ -890,7 +910,14 @@ __host__ __device__ inline size_t walk_smem_doubles(int N, int S, int max_block_
     return VB * (S | 1) + S + 129 + 2 * m + (m + 1) / 2 + (size_t)max_block_windows + ((size_t)max_block_windows + 1) / 2;
 }
 
-static __global__ void __launch_bounds__(kWalkMaxThreads)
+// VPT = variables per thread (1 or 2).  With two, a thread walks the SAME subject's samples for two
+// neighbouring variables at once: the sample counts, the window tables, the centred times and all of the
+// control flow of the walk and of the emission are shared, and the two variables' fp64 chains interleave
+// (the kernel is bound by instruction issue -- under a fifth of its instructions are fp64 arithmetic -- and
+// by the latency of those chains, not by memory).  Per-variable arithmetic is the same sequence of
+// operations in the same order for either VPT.
+template <int VPT>
+static __global__ void __launch_bounds__(VPT == 1 ? kWalkMaxThreads : kWalk2MaxThreads)
 values_walk_kernel(const double *__restrict__ series, int64_t series_stride, const double *__restrict__ times,
                    const int32_t *__restrict__ t_offsets, int S, int N, int V,
                    const double *__restrict__ windows, const int32_t *__restrict__ wlo,
@@ -934,59 +961,96 @@ values_walk_kernel(const double *__restrict__ series, int64_t series_stride, con
         m_nt[i] = 1 + slope_ok[wb0 + i];
     }
     __syncthreads();
-    const int vl = threadIdx.x / N, s = threadIdx.x - vl * N;
+    const int vt = threadIdx.x / N, s = threadIdx.x - vt * N;
+    const int vl = vt * VPT;                             // first of this thread's variables
     if (vl >= nv) return;
-    const double *x = ser + vl * Sp;
+    // an odd tile leaves the last thread one variable: its second slot re-walks the first and stores nothing
+    const bool has2 = VPT == 2 && vl + 1 < nv;
+    const double *x[VPT];
+#pragma unroll
+    for (int u = 0; u < VPT; ++u) x[u] = ser + (vl + ((u && has2) ? 1 : 0)) * Sp;
     const int64_t vNs = (int64_t)(v0 + vl) * N + s;      // (variable, subject) offset inside a window's groups
+    double *const out_two = values + (2 * vNs - s);      // windows with both types: slope row, then the mean row
+    double *const out_one = values + vNs;                // mean only
     for (int sg = sg_begin; sg < sg_end; ++sg) {
         const int w_begin = sg_first[sg], nw = sg_first[sg + 1] - w_begin;
         const int mb = (w_begin - wb0) * N + s;         // this thread's column in the block's tables
         const double t0 = windows[2 * w_begin];
         const int a = wlo[w_begin * N + s];            // first sample at or after t0: the same for the whole group
-        const double x0 = x[a];
+        const double *ta = st + a;
+        const double *xa[VPT];
+        double x0[VPT], res[VPT], Sd[VPT], Std[VPT], r[VPT][8];
+#pragma unroll
+        for (int u = 0; u < VPT; ++u) {
+            xa[u] = x[u] + a;
+            x0[u] = xa[u][0];
+            res[u] = -0.0;
+            Sd[u] = 0.0;
+            Std[u] = 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) r[u][q] = 0.0;
+        }
         int n = 0;
-        double res = -0.0, Sd = 0.0, Std = 0.0;
-        double r0 = 0, r1 = 0, r2 = 0, r3 = 0, r4 = 0, r5 = 0, r6 = 0, r7 = 0;
         for (int wi = 0; wi < nw; ++wi) {
             const int target = m_cnt[mb + wi * N];
             while (n < target) {
-                const double xv = x[a + n];
-                const double d = __dadd_rn(xv, -x0);
-                Sd = __dadd_rn(Sd, d);
-                Std = __fma_rn(__dadd_rn(st[a + n], -t0), d, Std);
+                const double tau = __dadd_rn(ta[n], -t0);
+                double xv[VPT];
+#pragma unroll
+                for (int u = 0; u < VPT; ++u) {
+                    xv[u] = xa[u][n];
+                    const double d = __dadd_rn(xv[u], -x0[u]);
+                    Sd[u] = __dadd_rn(Sd[u], d);
+                    Std[u] = __fma_rn(tau, d, Std[u]);
+                }
                 ++n;
                 if (n < 8 || (n & 7)) {
-                    res = __dadd_rn(res, xv);          // sequential head (n < 8) or the tail after the last block
+#pragma unroll
+                    for (int u = 0; u < VPT; ++u)
+                        res[u] = __dadd_rn(res[u], xv[u]);   // sequential head (n < 8) or the tail after the last block
                 } else {
-                    const double *b = x + a + n - 8;    // a block of 8 is complete
-                    if (n == 8) {
-                        r0 = b[0]; r1 = b[1]; r2 = b[2]; r3 = b[3]; r4 = b[4]; r5 = b[5]; r6 = b[6]; r7 = b[7];
-                    } else {
-                        r0 = __dadd_rn(r0, b[0]); r1 = __dadd_rn(r1, b[1]); r2 = __dadd_rn(r2, b[2]);
-                        r3 = __dadd_rn(r3, b[3]); r4 = __dadd_rn(r4, b[4]); r5 = __dadd_rn(r5, b[5]);
-                        r6 = __dadd_rn(r6, b[6]); r7 = __dadd_rn(r7, b[7]);
+#pragma unroll
+                    for (int u = 0; u < VPT; ++u) {
+                        const double *b = xa[u] + n - 8;     // a block of 8 is complete
+                        if (n == 8) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) r[u][q] = b[q];
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) r[u][q] = __dadd_rn(r[u][q], b[q]);
+                        }
+                        res[u] = __dadd_rn(__dadd_rn(__dadd_rn(r[u][0], r[u][1]), __dadd_rn(r[u][2], r[u][3])),
+                                           __dadd_rn(__dadd_rn(r[u][4], r[u][5]), __dadd_rn(r[u][6], r[u][7])));
                     }
-                    res = __dadd_rn(__dadd_rn(__dadd_rn(r0, r1), __dadd_rn(r2, r3)),
-                                    __dadd_rn(__dadd_rn(r4, r5), __dadd_rn(r6, r7)));
                 }
             }
             const int wl = w_begin - wb0 + wi;
-            const int nt = m_nt[wl];
-            // element offset of this thread's slope value (nt == 2) / mean (nt == 1): no 64-bit multiplies here
-            double *out = values + (m_gb[wl] + (nt == 2 ? 2 * vNs - s : vNs));
-            double mean;
-            if (n <= 128) mean = div_small_int_hot(res, (double)n, rcp[n]);
-            else mean = __ddiv_rn(pairwise_sum_col(SmemVec{x + a}, n), (double)n);   // numpy splits above 128
-            if (nt == 2) {
-                const double slope =
-                    __dmul_rn(__dadd_rn(Std, -__dmul_rn(m_tb[mb + wi * N], Sd)), m_is[mb + wi * N]);
-                out[0] = slope;
-                out[N] = mean;
-                // slope guard band: slope exactly 0 with a non-zero mean = constant non-zero series
-                if (group_flags && slope == 0.0 && mean != 0.0)
-                    group_flags[group_base[w_begin + wi] + (int64_t)(v0 + vl) * 2] = 1;
-            } else {
-                out[0] = mean;
+            const bool two = m_nt[wl] == 2;
+            double *out = (two ? out_two : out_one) + m_gb[wl];
+            const int vstep = two ? 2 * N : N;            // from one variable's rows to the next variable's
+            double tb = 0.0, is = 0.0;
+            if (two) {
+                tb = m_tb[mb + wi * N];
+                is = m_is[mb + wi * N];
+            }
+            const double nd = (double)n, y = rcp[n <= 128 ? n : 0];
+#pragma unroll
+            for (int u = 0; u < VPT; ++u) {
+                if (u && !has2) break;
+                double mean;
+                if (n <= 128) mean = div_small_int_hot(res[u], nd, y);
+                else mean = __ddiv_rn(pairwise_sum_col(SmemVec{xa[u]}, n), nd);   // numpy splits above 128
+                if (two) {
+                    const double slope = __dmul_rn(__dadd_rn(Std[u], -__dmul_rn(tb, Sd[u])), is);
+                    out[0] = slope;
+                    out[N] = mean;
+                    // slope guard band: slope exactly 0 with a non-zero mean = constant non-zero series
+                    if (group_flags && slope == 0.0 && mean != 0.0)
+                        group_flags[group_base[w_begin + wi] + (int64_t)(v0 + vl + u) * 2] = 1;
+                } else {
+                    out[0] = mean;
+                }
+                out += vstep;
             }
         }
     }
@@ -1135,13 +1199,13 @@ sort_emit_staged_kernel(const double *__restrict__ values, int64_t G, int N, dou
             // criterion is checked by the values kernel; group_flags was cleared before the launches.
             double last = val[0];
 #pragma unroll
-            for (int k = 1; k < NB; ++k)
+            for (int k = (NB > 4 ? NB - 4 : 1); k < NB; ++k)
                 if (k == M) last = val[k];
             const double tol = kSlopeGuard * fmax(fabs(val[0]), fabs(last));
             bool flag = false;
+            // past M the neighbours are (value, +inf) or (+inf, +inf): neither is a near-tie
 #pragma unroll
-            for (int k = 0; k < NB - 1; ++k)
-                if (k < M) flag |= (val[k] != val[k + 1]) && (val[k + 1] - val[k] <= tol);
+            for (int k = 0; k < NB - 1; ++k) flag |= (val[k] != val[k + 1]) && (val[k + 1] - val[k] <= tol);
             if (flag) sg.group_flags[g0 + tid] = 1;
         }
         if (tid == 0) bulk_wait_read0();   // the previous tile's thresholds have left their buffer
@@ -1149,38 +1213,47 @@ sort_emit_staged_kernel(const double *__restrict__ values, int64_t G, int N, dou
         if (!dry) {
         int kcount = 0;
         {
-            double *tg = sthr + tid * M;
+            uint32_t ta = smem_u32(sthr + tid * M);   // slot of the threshold being written (ascending)
             double prev = 0.0;
 #pragma unroll
             for (int k = 0; k < NB - 1; ++k) {
-                if (k < M) {
+                if (MITRE_LT_M(k)) {
                     const double m = __dmul_rn(0.5, __dadd_rn(val[k], val[k + 1]));
                     const bool u = (k == 0) || (m != prev);
-                    tg[kcount] = m;   // a repeated midpoint is overwritten by its successor
+                    // a repeated midpoint lands on its (equal) predecessor
+                    if (k > 0 && u) ta += 8;
+                    sts_f64(ta, m);
                     kcount += u;
                     prev = m;
                 }
             }
+            double *tg = sthr + tid * M;
             for (int k2 = kcount; k2 < M; ++k2) tg[k2] = 0.0;
             if (tid < cnt) K[g0 + tid] = kcount;
         }
         {
             uint64_t *rg = sabove + (size_t)tid * M;
             uint64_t acc = 0, Tn = 0;
-            int pos = kcount - 1;
+            uint32_t ra = smem_u32(rg + (kcount - 1));   // slot of the row being emitted (descending)
+            double m = 0.0;                              // midpoint k, carried down from iteration k + 1
 #pragma unroll
             for (int k = NB - 1; k >= 0; --k) {
-                if (k == M) {
+                if (MITRE_EQ_M(k)) {
                     acc = 1ull << (63 - id[k]);
                     Tn = 0;
-                } else if (k < M) {
-                    const double m = __dmul_rn(0.5, __dadd_rn(val[k], val[k + 1]));
+                    if (k > 0) m = __dmul_rn(0.5, __dadd_rn(val[k - 1], val[k]));
+                } else if (MITRE_LT_M(k)) {
+                    double m_below = 0.0;
                     bool uniq = true;
-                    if (k > 0) uniq = m != __dmul_rn(0.5, __dadd_rn(val[k - 1], val[k]));
-                    rg[pos] = (m == val[k + 1]) ? Tn : acc;   // same row for a repeated midpoint
-                    pos -= uniq;
+                    if (k > 0) {
+                        m_below = __dmul_rn(0.5, __dadd_rn(val[k - 1], val[k]));
+                        uniq = m != m_below;
+                    }
+                    sts_u64(ra, (m == val[k + 1]) ? Tn : acc);   // same row for a repeated midpoint
+                    if (uniq) ra -= 8;
                     Tn = (val[k] == val[k + 1]) ? Tn : acc;
                     acc |= 1ull << (63 - id[k]);
+                    m = m_below;
                 }
             }
             for (int k2 = kcount; k2 < M; ++k2) rg[k2] = ~0ull;   // sentinel: no subject set is all ones

@@ -202,14 +202,54 @@ static size_t sort_ws_layout(int64_t P, int W64, void *base, SortWs *ws)
     return off;
 }
 
+// sort_packed.cu: one-sweep sort of (row | index) words for tables with N + bits(P) <= 64
+size_t lexsort_packed_workspace_bytes(int64_t P);
+bool lexsort_packed_eligible(int64_t P, int N);
+int lexsort_packed(cudaStream_t st, const uint64_t *rows, int64_t P, int N, int padded, int64_t P_valid,
+                   const int64_t *row_offsets, int L, int64_t *perm, uint64_t *sorted_rows, void *workspace,
+                   size_t workspace_bytes);
+int lexsort_packed_failed(cudaStream_t st, void *workspace, int64_t P);
+
+static int g_packed_sort = 1;
+
 }  // namespace mitre
 
 using namespace mitre;
 
+extern "C" int mitre_set_packed_sort(int enable)
+{
+    const int old = g_packed_sort;
+    g_packed_sort = enable ? 1 : 0;
+    return old;
+}
+
 extern "C" size_t mitre_lexsort_workspace_bytes(int64_t P, int W64)
 {
     if (P < 0 || W64 <= 0) return 0;
-    return sort_ws_layout(P, W64, nullptr, nullptr);
+    size_t general = sort_ws_layout(P, W64, nullptr, nullptr);
+    if (W64 == 1) {
+        const size_t packed = lexsort_packed_workspace_bytes(P);
+        if (packed > general) general = packed;
+    }
+    return general;
+}
+
+extern "C" int mitre_lexsort_padded(void *stream, const uint64_t *rows_padded, int64_t P_slots, int N,
+                                    int64_t P_valid, const int64_t *row_offsets, int64_t *perm,
+                                    uint64_t *sorted_rows, void *workspace, size_t workspace_bytes)
+{
+    if (P_slots < 0 || N < 2 || P_valid < 0 || P_valid > P_slots) return MITRE_ERR_INVALID;
+    if (P_slots == 0 || P_valid == 0) return MITRE_OK;
+    if (!rows_padded || !perm || !row_offsets || !workspace) return MITRE_ERR_INVALID;
+    if (!g_packed_sort || !lexsort_packed_eligible(P_slots, N)) return MITRE_ERR_UNSUPPORTED;
+    return lexsort_packed(as_stream(stream), rows_padded, P_slots, N, 1, P_valid, row_offsets, 2 * (N - 1), perm,
+                          sorted_rows, workspace, workspace_bytes);
+}
+
+extern "C" int mitre_lexsort_check(void *stream, void *workspace, int64_t P, int N)
+{
+    if (!workspace || P <= 0 || !g_packed_sort || !lexsort_packed_eligible(P, N)) return MITRE_OK;
+    return lexsort_packed_failed(as_stream(stream), workspace, P) ? MITRE_ERR_UNSUPPORTED : MITRE_OK;
 }
 
 extern "C" int mitre_lexsort_rows(void *stream, const uint64_t *rows, int64_t P, int W64, int N,
@@ -221,6 +261,8 @@ extern "C" int mitre_lexsort_rows(void *stream, const uint64_t *rows, int64_t P,
     if (!rows || !perm || !workspace) return MITRE_ERR_INVALID;
     if (workspace_bytes < mitre_lexsort_workspace_bytes(P, W64)) return MITRE_ERR_WORKSPACE;
     cudaStream_t st = as_stream(stream);
+    if (W64 == 1 && g_packed_sort && lexsort_packed_eligible(P, N))
+        return lexsort_packed(st, rows, P, N, 0, P, nullptr, 0, perm, sorted_rows, workspace, workspace_bytes);
     SortWs ws;
     sort_ws_layout(P, W64, workspace, &ws);
     const int64_t ntiles = ceil_div64(P, kSortTile);

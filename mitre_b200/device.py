@@ -467,6 +467,29 @@ def lexsort_rows(rows, N, want_sorted=True):
     ws = torch.empty(max(nbytes, 1), dtype=U8, device=dev())
     check(lib().mitre_lexsort_rows(_stream(), _p(rows), P, W64, int(N), _p(perm), _p(sorted_rows),
                                    _p(ws), nbytes), "mitre_lexsort_rows")
+    if W64 == 1:
+        check(lib().mitre_lexsort_check(_stream(), _p(ws), P, int(N)), "mitre_lexsort_check")
+    return perm, sorted_rows
+
+
+def lexsort_padded(rows_padded, N, P_valid, row_offsets):
+    """sort_base_rules straight from the padded detector output (2(N-1) slots per group, unused = ~0):
+    (perm int64[P_valid] of dense enumeration indices, sorted_rows int64[P_valid, 1]).  Tables that are not
+    eligible for the packed one-sweep sort (mitre_lexsort_padded) take the general sort over N + 1 bits and
+    mitre_densify_perm."""
+    P_slots = rows_padded.numel()
+    nbytes = lib().mitre_lexsort_workspace_bytes(P_slots, 1)
+    ws = torch.empty(max(nbytes, 1), dtype=U8, device=dev())
+    perm = torch.empty(P_valid, dtype=I64, device=dev())
+    sorted_rows = torch.empty((P_valid, 1), dtype=I64, device=dev())
+    rc = lib().mitre_lexsort_padded(_stream(), _p(rows_padded), P_slots, int(N), int(P_valid), _p(row_offsets),
+                                    _p(perm), _p(sorted_rows), _p(ws), nbytes)
+    if rc == -2:   # MITRE_ERR_UNSUPPORTED
+        del perm, sorted_rows, ws
+        perm_pad, sorted_pad = lexsort_rows(rows_padded.view(-1, 1), N + 1)
+        return densify_perm(perm_pad[:P_valid], N, row_offsets), sorted_pad[:P_valid].contiguous()
+    check(rc, "mitre_lexsort_padded")
+    check(lib().mitre_lexsort_check(_stream(), _p(ws), P_slots, int(N)), "mitre_lexsort_check")
     return perm, sorted_rows
 
 

@@ -494,9 +494,9 @@ class DiscreteRulePopulation:
         elif padded is not None:
             # padded table: sentinel slots sort last (N + 1 significant bits), valid rows keep the
             # reference's enumeration order among equals; slot indices -> dense enumeration indices
-            perm_pad, sorted_pad = D.lexsort_rows(padded.view(-1, 1), N + 1)
-            self._sorted_rows = sorted_pad[:self._P].contiguous()
-            self._perm = D.densify_perm(perm_pad[:self._P], N, self._row_offsets)
+            # (one-sweep sort of (row | slot) words when they fit 64 bits: sentinels dropped in its first pass,
+            # densified in its last)
+            self._perm, self._sorted_rows = D.lexsort_padded(padded, N, self._P, self._row_offsets)
         else:
             self._perm, self._sorted_rows = D.lexsort_rows(self._rows, N)
         self._rows = None   # enumeration-order rows are no longer needed

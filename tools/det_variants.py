@@ -74,7 +74,18 @@ def main():
     padded = ref[3]
     D.lexsort_rows(padded.view(-1, 1), N + 1)
     ms = min(bench.cuda_time_ms(torch, lambda: D.lexsort_rows(padded.view(-1, 1), N + 1), 3) for _ in range(2))
-    print("lexsort of the padded table (%d slots): %.2f ms" % (padded.numel(), ms))
+    print("lexsort of the padded table (%d slots), general path over N + 1 bits: %.2f ms" % (padded.numel(), ms))
+    K = ref[2]
+    off = D.detector_row_offsets(K)
+    P = int(off[-1].item())
+    p1, s1 = D.lexsort_padded(padded, N, P, off)
+    ms = min(bench.cuda_time_ms(torch, lambda: D.lexsort_padded(padded, N, P, off), 3) for _ in range(2))
+    lib().mitre_set_packed_sort(0)
+    p0, s0 = D.lexsort_padded(padded, N, P, off)
+    ms0 = min(bench.cuda_time_ms(torch, lambda: D.lexsort_padded(padded, N, P, off), 3) for _ in range(2))
+    lib().mitre_set_packed_sort(1)
+    print("sort_base_rules from the padded table (%d valid rows): packed one-sweep %.2f ms, general + densify %.2f ms, "
+          "identical=%s" % (P, ms, ms0, torch.equal(p0, p1) and torch.equal(s0, s1)))
 
 
 if __name__ == "__main__":
