@@ -314,13 +314,13 @@ static int launch_values_walk(cudaStream_t st, dim3 grid, size_t smem, const dou
     const int vpt = (g_walk_vpt == 2 && VB >= 2) ? 2 : 1;
     const int threads = ((((VB + vpt - 1) / vpt) * N + 31) / 32) * 32;
     if (vpt == 2) {
-        MITRE_CUDA_TRY(cudaFuncSetAttribute(values_walk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        values_walk_kernel<2><<<grid, threads, smem, st>>>(series, series_stride, times, t_offsets, S, N, V, windows, wlo,
+        MITRE_CUDA_TRY(cudaFuncSetAttribute(values_walkn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        values_walkn_kernel<2><<<grid, threads, smem, st>>>(series, series_stride, times, t_offsets, S, N, V, windows, wlo,
                                                            wcnt, winv_sxx, wtbar, group_base, slope_ok, sg_first, sg_base,
                                                            n_sg, sg_per_block, max_block_windows, values, group_flags);
     } else {
-        MITRE_CUDA_TRY(cudaFuncSetAttribute(values_walk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        values_walk_kernel<1><<<grid, threads, smem, st>>>(series, series_stride, times, t_offsets, S, N, V, windows, wlo,
+        MITRE_CUDA_TRY(cudaFuncSetAttribute(values_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        values_walk_kernel<<<grid, threads, smem, st>>>(series, series_stride, times, t_offsets, S, N, V, windows, wlo,
                                                            wcnt, winv_sxx, wtbar, group_base, slope_ok, sg_first, sg_base,
                                                            n_sg, sg_per_block, max_block_windows, values, group_flags);
     }

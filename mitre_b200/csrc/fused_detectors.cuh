@@ -910,6 +910,108 @@ __host__ __device__ inline size_t walk_smem_doubles(int N, int S, int max_block_
     return VB * (S | 1) + S + 129 + 2 * m + (m + 1) / 2 + (size_t)max_block_windows + ((size_t)max_block_windows + 1) / 2;
 }
 
+static __global__ void __launch_bounds__(kWalkMaxThreads)
+values_walk_kernel(const double *__restrict__ series, int64_t series_stride, const double *__restrict__ times,
+                   const int32_t *__restrict__ t_offsets, int S, int N, int V,
+                   const double *__restrict__ windows, const int32_t *__restrict__ wlo,
+                   const int32_t *__restrict__ wcnt, const double *__restrict__ winv_sxx,
+                   const double *__restrict__ wtbar, const int64_t *__restrict__ group_base,
+                   const uint8_t *__restrict__ slope_ok, const int32_t *__restrict__ sg_first, int sg_base,
+                   int n_sg, int sg_per_block, int max_block_windows, double *__restrict__ values,
+                   uint8_t *__restrict__ group_flags)
+{
+    extern __shared__ __align__(16) double wsm[];
+    const int VB = walk_vars_per_block(N);
+    const int Sp = S | 1;                               // odd row length: different variables, different banks
+    const int M = max_block_windows * N;
+    double *ser = wsm;                                  // [VB][Sp]
+    double *st = ser + (size_t)VB * Sp;                 // [S] sample times
+    double *rcp = st + S;                               // [129] 1/n
+    double *m_tb = rcp + 129;                           // [block windows][N] taubar
+    double *m_is = m_tb + M;                            // [block windows][N] 1/Sxx
+    int32_t *m_cnt = reinterpret_cast<int32_t *>(m_is + M);                           // [block windows][N]
+    long long *m_gb = reinterpret_cast<long long *>(m_cnt + ((M + 1) & ~1));          // [block windows] group_base * N
+    int32_t *m_nt = reinterpret_cast<int32_t *>(m_gb + max_block_windows);            // [block windows]
+    const int v0 = blockIdx.x * VB;
+    const int nv = min(VB, V - v0);
+    // this launch covers start groups [sg_base, n_sg), sg_per_block of them per blockIdx.y
+    const int sg_begin = sg_base + blockIdx.y * sg_per_block, sg_end = min(n_sg, sg_begin + sg_per_block);
+    if (sg_begin >= sg_end) return;
+    const int wb0 = sg_first[sg_begin], nbw = sg_first[sg_end] - wb0;      // the block's windows
+    for (int i = threadIdx.x; i < nv * S; i += blockDim.x) {
+        const int vl = i / S, j = i - vl * S;
+        ser[vl * Sp + j] = series[(int64_t)(v0 + vl) * series_stride + j];
+    }
+    for (int i = threadIdx.x; i < S; i += blockDim.x) st[i] = times[i];
+    for (int i = threadIdx.x; i <= 128; i += blockDim.x) rcp[i] = i ? __ddiv_rn(1.0, (double)i) : 0.0;
+    for (int i = threadIdx.x; i < nbw * N; i += blockDim.x) {
+        m_cnt[i] = wcnt[wb0 * N + i];
+        m_tb[i] = wtbar[wb0 * N + i];
+        m_is[i] = winv_sxx[wb0 * N + i];
+    }
+    for (int i = threadIdx.x; i < nbw; i += blockDim.x) {
+        m_gb[i] = group_base[wb0 + i] * N;               // element offset of the window's first group
+        m_nt[i] = 1 + slope_ok[wb0 + i];
+    }
+    __syncthreads();
+    const int vl = threadIdx.x / N, s = threadIdx.x - vl * N;
+    if (vl >= nv) return;
+    const double *x = ser + vl * Sp;
+    const int64_t vNs = (int64_t)(v0 + vl) * N + s;      // (variable, subject) offset inside a window's groups
+    for (int sg = sg_begin; sg < sg_end; ++sg) {
+        const int w_begin = sg_first[sg], nw = sg_first[sg + 1] - w_begin;
+        const int mb = (w_begin - wb0) * N + s;         // this thread's column in the block's tables
+        const double t0 = windows[2 * w_begin];
+        const int a = wlo[w_begin * N + s];            // first sample at or after t0: the same for the whole group
+        const double x0 = x[a];
+        int n = 0;
+        double res = -0.0, Sd = 0.0, Std = 0.0;
+        double r0 = 0, r1 = 0, r2 = 0, r3 = 0, r4 = 0, r5 = 0, r6 = 0, r7 = 0;
+        for (int wi = 0; wi < nw; ++wi) {
+            const int target = m_cnt[mb + wi * N];
+            while (n < target) {
+                const double xv = x[a + n];
+                const double d = __dadd_rn(xv, -x0);
+                Sd = __dadd_rn(Sd, d);
+                Std = __fma_rn(__dadd_rn(st[a + n], -t0), d, Std);
+                ++n;
+                if (n < 8 || (n & 7)) {
+                    res = __dadd_rn(res, xv);          // sequential head (n < 8) or the tail after the last block
+                } else {
+                    const double *b = x + a + n - 8;    // a block of 8 is complete
+                    if (n == 8) {
+                        r0 = b[0]; r1 = b[1]; r2 = b[2]; r3 = b[3]; r4 = b[4]; r5 = b[5]; r6 = b[6]; r7 = b[7];
+                    } else {
+                        r0 = __dadd_rn(r0, b[0]); r1 = __dadd_rn(r1, b[1]); r2 = __dadd_rn(r2, b[2]);
+                        r3 = __dadd_rn(r3, b[3]); r4 = __dadd_rn(r4, b[4]); r5 = __dadd_rn(r5, b[5]);
+                        r6 = __dadd_rn(r6, b[6]); r7 = __dadd_rn(r7, b[7]);
+                    }
+                    res = __dadd_rn(__dadd_rn(__dadd_rn(r0, r1), __dadd_rn(r2, r3)),
+                                    __dadd_rn(__dadd_rn(r4, r5), __dadd_rn(r6, r7)));
+                }
+            }
+            const int wl = w_begin - wb0 + wi;
+            const int nt = m_nt[wl];
+            // element offset of this thread's slope value (nt == 2) / mean (nt == 1): no 64-bit multiplies here
+            double *out = values + (m_gb[wl] + (nt == 2 ? 2 * vNs - s : vNs));
+            double mean;
+            if (n <= 128) mean = div_small_int_hot(res, (double)n, rcp[n]);
+            else mean = __ddiv_rn(pairwise_sum_col(SmemVec{x + a}, n), (double)n);   // numpy splits above 128
+            if (nt == 2) {
+                const double slope =
+                    __dmul_rn(__dadd_rn(Std, -__dmul_rn(m_tb[mb + wi * N], Sd)), m_is[mb + wi * N]);
+                out[0] = slope;
+                out[N] = mean;
+                // slope guard band: slope exactly 0 with a non-zero mean = constant non-zero series
+                if (group_flags && slope == 0.0 && mean != 0.0)
+                    group_flags[group_base[w_begin + wi] + (int64_t)(v0 + vl) * 2] = 1;
+            } else {
+                out[0] = mean;
+            }
+        }
+    }
+}
+
 // VPT = variables per thread (1 or 2).  With two, a thread walks the SAME subject's samples for two
 // neighbouring variables at once: the sample counts, the window tables, the centred times and all of the
 // control flow of the walk and of the emission are shared, and the two variables' fp64 chains interleave
@@ -918,7 +1020,7 @@ __host__ __device__ inline size_t walk_smem_doubles(int N, int S, int max_block_
 // operations in the same order for either VPT.
 template <int VPT>
 static __global__ void __launch_bounds__(VPT == 1 ? kWalkMaxThreads : kWalk2MaxThreads)
-values_walk_kernel(const double *__restrict__ series, int64_t series_stride, const double *__restrict__ times,
+values_walkn_kernel(const double *__restrict__ series, int64_t series_stride, const double *__restrict__ times,
                    const int32_t *__restrict__ t_offsets, int S, int N, int V,
                    const double *__restrict__ windows, const int32_t *__restrict__ wlo,
                    const int32_t *__restrict__ wcnt, const double *__restrict__ winv_sxx,

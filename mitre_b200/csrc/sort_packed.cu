@@ -28,7 +28,13 @@ namespace mitre {
 
 constexpr int kOsThreads = 512;
 constexpr int kOsWarps = kOsThreads / 32;
-constexpr int kOsItems = 8;
+#ifndef MITRE_OS_ITEMS
+#define MITRE_OS_ITEMS 8
+#endif
+#ifndef MITRE_OS_MINB
+#define MITRE_OS_MINB 2
+#endif
+constexpr int kOsItems = MITRE_OS_ITEMS;
 constexpr int kOsTile = kOsThreads * kOsItems;   // 4096 rows per CTA
 constexpr int kOsMaxBits = 9;
 constexpr int kOsBins = 1 << kOsMaxBits;
@@ -167,7 +173,7 @@ struct OsShared {
 // One pass.  FIRST: `in` is the caller's table (P slots; ~0 = dropped when `padded`), the index is OR-ed in.
 // LAST: the outputs are perm / rows_out instead of packed words.
 template <bool FIRST, bool LAST>
-__global__ void __launch_bounds__(kOsThreads, 2)
+__global__ void __launch_bounds__(kOsThreads, MITRE_OS_MINB)
 os_pass_kernel(const uint64_t *__restrict__ in, int64_t P, int padded, int shift, int bits, int idx_bits,
                const uint32_t *__restrict__ gofs /*[kOsBins]*/, uint32_t *__restrict__ status /*[ntiles][kOsBins]*/,
                uint32_t *__restrict__ ticket, uint64_t *__restrict__ out_packed, int64_t *__restrict__ perm_out,
