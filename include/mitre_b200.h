@@ -361,6 +361,12 @@ int mitre_slope_guard(void *stream, const double *values, int64_t G, int N, cons
 int mitre_densify_perm(void *stream, const int64_t *perm_padded, int64_t P, int N,
                        const int64_t *row_offsets, int64_t *perm);
 int mitre_set_detector_split(int enable); /* tuning/test hook, see above */
+int mitre_set_walk_tuning(int vb_cap, int emit_blocks_per_sm, int emit_priority); /* variables per walk CTA (1..16,
+                                             default 16); pipelined call (mitre_detectors_walk): resident sort/emit
+                                             blocks per SM while a values kernel runs beside them (0 = all) and
+                                             whether the sort/emit stream runs at high priority (takes effect when
+                                             the internal streams are created) */
+int mitre_walk_vars_per_block(int N);     /* the tile width the plan of mitre_detector_values_walk must assume */
 int mitre_set_walk_vpt(int vpt);          /* variables per thread of the walk-forward values kernel: 1 (default) or 2 (
                                              shared control flow, two interleaved fp64 chains; measured slower: 1.12 vs 0.82 ms at S5); same values.
                                              Returns the previous setting. */

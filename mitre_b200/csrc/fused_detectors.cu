@@ -9,6 +9,7 @@ namespace mitre {
 int g_detector_split = 1;
 int g_sort_emit_rolled = 0;
 SlopeGuardArgs g_slope_guard = {nullptr, nullptr, nullptr};
+int g_emit_blocks_per_sm = 0;
 int launch_slope_guard(cudaStream_t st, const double *values, int64_t G, int N, const uint8_t *group_type,
                        uint8_t *group_flags, unsigned long long *flagged);   // detectors.cu
 int launch_count_flags(cudaStream_t st, const uint8_t *group_flags, int64_t G, unsigned long long *flagged);
@@ -296,6 +297,19 @@ extern "C" int mitre_window_tbar(void *stream, const double *times, int N, const
 // memory next to the series tile: sg_first is a host-visible copy is not available here, so the launcher
 // takes the window count of the fullest chunk from the caller (max_block_windows) for a given split.
 static int g_walk_vpt = 1;   // variables per thread of values_walk_kernel
+static int g_walk_vb_cap = 16;       // variables per walk CTA (upper bound)
+static int g_pipe_emit_per_sm = 0;   // pipelined call: sort/emit blocks per SM while a values kernel runs beside it (0 = all)
+static int g_pipe_priority = 0;      // pipelined call: sort/emit stream at high priority
+
+extern "C" int mitre_set_walk_tuning(int vb_cap, int emit_blocks_per_sm, int emit_priority)
+{
+    g_walk_vb_cap = vb_cap < 1 ? 1 : (vb_cap > 16 ? 16 : vb_cap);
+    g_pipe_emit_per_sm = emit_blocks_per_sm < 0 ? 0 : emit_blocks_per_sm;
+    g_pipe_priority = emit_priority ? 1 : 0;
+    return MITRE_OK;
+}
+
+extern "C" int mitre_walk_vars_per_block(int N) { return N > 0 ? walk_vars_per_block(N, g_walk_vb_cap) : 0; }
 
 extern "C" int mitre_set_walk_vpt(int vpt)
 {
@@ -310,19 +324,19 @@ static int launch_values_walk(cudaStream_t st, dim3 grid, size_t smem, const dou
                               const int64_t *group_base, const uint8_t *slope_ok, const int32_t *sg_first, int sg_base,
                               int n_sg, int sg_per_block, int max_block_windows, double *values, uint8_t *group_flags)
 {
-    const int VB = walk_vars_per_block(N);
+    const int VB = walk_vars_per_block(N, g_walk_vb_cap);
     const int vpt = (g_walk_vpt == 2 && VB >= 2) ? 2 : 1;
     const int threads = ((((VB + vpt - 1) / vpt) * N + 31) / 32) * 32;
     if (vpt == 2) {
         MITRE_CUDA_TRY(cudaFuncSetAttribute(values_walkn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         values_walkn_kernel<2><<<grid, threads, smem, st>>>(series, series_stride, times, t_offsets, S, N, V, windows, wlo,
                                                            wcnt, winv_sxx, wtbar, group_base, slope_ok, sg_first, sg_base,
-                                                           n_sg, sg_per_block, max_block_windows, values, group_flags);
+                                                           n_sg, sg_per_block, max_block_windows, values, group_flags, VB);
     } else {
         MITRE_CUDA_TRY(cudaFuncSetAttribute(values_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         values_walk_kernel<<<grid, threads, smem, st>>>(series, series_stride, times, t_offsets, S, N, V, windows, wlo,
                                                            wcnt, winv_sxx, wtbar, group_base, slope_ok, sg_first, sg_base,
-                                                           n_sg, sg_per_block, max_block_windows, values, group_flags);
+                                                           n_sg, sg_per_block, max_block_windows, values, group_flags, VB);
     }
     MITRE_LAUNCH_CHECK();
     return MITRE_OK;
@@ -331,7 +345,7 @@ static int launch_values_walk(cudaStream_t st, dim3 grid, size_t smem, const dou
 extern "C" size_t mitre_values_walk_smem_bytes(int N, int S, int max_block_windows)
 {
     if (N <= 0 || S <= 0 || max_block_windows <= 0) return 0;
-    return sizeof(double) * walk_smem_doubles(N, S, max_block_windows);
+    return sizeof(double) * walk_smem_doubles(N, S, max_block_windows, walk_vars_per_block(N, g_walk_vb_cap));
 }
 
 extern "C" int mitre_detector_values_walk(void *stream, const double *series, int64_t series_stride,
@@ -351,7 +365,7 @@ extern "C" int mitre_detector_values_walk(void *stream, const double *series, in
         return MITRE_ERR_INVALID;
     const size_t smem = mitre_values_walk_smem_bytes(N, S, max_block_windows);
     if (smem > smem_optin()) return MITRE_ERR_UNSUPPORTED;
-    const int VB = walk_vars_per_block(N);
+    const int VB = walk_vars_per_block(N, g_walk_vb_cap);
     const int tiles = (V + VB - 1) / VB;
     const int chunks = (n_sg + sg_per_block - 1) / sg_per_block;
     return launch_values_walk(as_stream(stream), dim3((unsigned)tiles, (unsigned)chunks), smem, series, series_stride,
@@ -377,8 +391,12 @@ struct WalkPipe {
         cudaError_t e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return e;
         if (dev != device) {
+            int lo = 0, hi = 0;
+            if ((e = cudaDeviceGetStreamPriorityRange(&lo, &hi)) != cudaSuccess) return e;
             for (int i = 0; i < 2; ++i) {
-                if ((e = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking)) != cudaSuccess) return e;
+                // st[1] (sort/emit) at the highest priority: its pending blocks are placed before pending
+                // blocks of the values kernel whenever an SM frees resources
+                if ((e = cudaStreamCreateWithPriority(&st[i], cudaStreamNonBlocking, (i == 1 && g_pipe_priority) ? hi : lo)) != cudaSuccess) return e;
                 if ((e = cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming)) != cudaSuccess) return e;
             }
             if ((e = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming)) != cudaSuccess) return e;
@@ -424,7 +442,7 @@ extern "C" int mitre_detectors_walk(void *stream, const double *series, int64_t 
     MITRE_CUDA_TRY(cudaEventRecord(wp.fork, user));
     MITRE_CUDA_TRY(cudaStreamWaitEvent(wp.st[0], wp.fork, 0));
     MITRE_CUDA_TRY(cudaStreamWaitEvent(wp.st[1], wp.fork, 0));
-    const int VB = walk_vars_per_block(N);
+    const int VB = walk_vars_per_block(N, g_walk_vb_cap);
     const int tiles = (V + VB - 1) / VB;
     const int M = N - 1;
     const int saved = g_detector_split;
@@ -441,12 +459,14 @@ extern "C" int mitre_detectors_walk(void *stream, const double *series, int64_t 
         MITRE_CUDA_TRY(cudaEventRecord(wp.done[c], wp.st[0]));
         MITRE_CUDA_TRY(cudaStreamWaitEvent(wp.st[1], wp.done[c], 0));
         g_detector_split = 1;
+        g_emit_blocks_per_sm = (c + 1 < n_stages) ? g_pipe_emit_per_sm : 0;   // the last run has the SMs to itself
         g_slope_guard = (group_type && group_flags) ? SlopeGuardArgs{group_type + g0, group_flags + g0, nullptr}
                                                      : SlopeGuardArgs{nullptr, nullptr, nullptr};
         rc = nb_dispatch(wp.st[1], nullptr, 0, N, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0,
                          nullptr, nullptr, nullptr, nullptr, 0, g1 - g0, values + g0 * N, thresholds + g0 * M, K + g0,
                          rows_padded + g0 * 2 * M);
         g_slope_guard = SlopeGuardArgs{nullptr, nullptr, nullptr};
+        g_emit_blocks_per_sm = 0;
         g_detector_split = saved;
     }
     MITRE_CUDA_TRY(cudaEventRecord(wp.join[0], wp.st[0]));

@@ -33,6 +33,7 @@
 namespace mitre {
 
 extern int g_detector_split;  // see mitre_set_detector_split
+extern int g_emit_blocks_per_sm;   // > 0: cap on resident sort/emit blocks per SM for the next launch (pipelined call)
 extern int g_sort_emit_rolled; // 1: sort_emit_rolled_kernel instead of sort_emit_staged_kernel (mitre_set_sort_emit_rolled)
 
 // ---- slope guard band (SURVEY hard part 1) ------------------------------------------------------------
@@ -894,18 +895,18 @@ values_resident_kernel(const double *__restrict__ series_t, int64_t vstride, int
 constexpr int kWalkMaxThreads = 640;
 constexpr int kWalk2MaxThreads = 384;   // two variables per thread: ceil(VB / 2) * N <= 320 + N / 2, rounded to warps
 
-__host__ __device__ inline int walk_vars_per_block(int N)
+__host__ __device__ inline int walk_vars_per_block(int N, int cap = 16)
 {
     int v = kWalkMaxThreads / N;
-    return v > 16 ? 16 : (v < 1 ? 1 : v);
+    return v > cap ? cap : (v < 1 ? 1 : v);
 }
 
 // shared memory of values_walk_kernel, in doubles: series tile, sample times, 1/n table, then for ALL the
 // windows of the block's start groups the (window, subject) tables (taubar, 1/Sxx, counts as int32) and the
 // per-window group offsets / type counts -- loaded once, so that the walk itself has no barrier
-__host__ __device__ inline size_t walk_smem_doubles(int N, int S, int max_block_windows)
+__host__ __device__ inline size_t walk_smem_doubles(int N, int S, int max_block_windows, int VB_)
 {
-    const size_t VB = walk_vars_per_block(N);
+    const size_t VB = VB_;
     const size_t m = (size_t)max_block_windows * N;
     return VB * (S | 1) + S + 129 + 2 * m + (m + 1) / 2 + (size_t)max_block_windows + ((size_t)max_block_windows + 1) / 2;
 }
@@ -918,10 +919,9 @@ values_walk_kernel(const double *__restrict__ series, int64_t series_stride, con
                    const double *__restrict__ wtbar, const int64_t *__restrict__ group_base,
                    const uint8_t *__restrict__ slope_ok, const int32_t *__restrict__ sg_first, int sg_base,
                    int n_sg, int sg_per_block, int max_block_windows, double *__restrict__ values,
-                   uint8_t *__restrict__ group_flags)
+                   uint8_t *__restrict__ group_flags, int VB)
 {
     extern __shared__ __align__(16) double wsm[];
-    const int VB = walk_vars_per_block(N);
     const int Sp = S | 1;                               // odd row length: different variables, different banks
     const int M = max_block_windows * N;
     double *ser = wsm;                                  // [VB][Sp]
@@ -1027,10 +1027,9 @@ values_walkn_kernel(const double *__restrict__ series, int64_t series_stride, co
                    const double *__restrict__ wtbar, const int64_t *__restrict__ group_base,
                    const uint8_t *__restrict__ slope_ok, const int32_t *__restrict__ sg_first, int sg_base,
                    int n_sg, int sg_per_block, int max_block_windows, double *__restrict__ values,
-                   uint8_t *__restrict__ group_flags)
+                   uint8_t *__restrict__ group_flags, int VB)
 {
     extern __shared__ __align__(16) double wsm[];
-    const int VB = walk_vars_per_block(N);
     const int Sp = S | 1;                               // odd row length: different variables, different banks
     const int M = max_block_windows * N;
     double *ser = wsm;                                  // [VB][Sp]
@@ -1585,6 +1584,7 @@ static int launch_sort_emit_staged(cudaStream_t st, const double *values, int64_
     int per_sm = 1;
     MITRE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kStageThreads, smem));
     if (per_sm < 1) return MITRE_ERR_UNSUPPORTED;
+    if (g_emit_blocks_per_sm > 0 && g_emit_blocks_per_sm < per_sm) per_sm = g_emit_blocks_per_sm;
     int64_t blocks = (int64_t)sm_count() * per_sm;
     const int64_t need = ceil_div64(G, kStageThreads);
     if (need < blocks) blocks = need;

@@ -357,7 +357,7 @@ def values_walk_plan(N, S, V, sg_first):
     sg_first: host int array [n_sg + 1]."""
     info = device_info()
     n_sg = len(sg_first) - 1
-    vb = max(1, min(16, 640 // int(N)))
+    vb = lib().mitre_walk_vars_per_block(int(N))
     tiles = (int(V) + vb - 1) // vb
     best = None
     for chunks in range(1, n_sg + 1):

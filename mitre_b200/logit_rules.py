@@ -71,10 +71,7 @@ class LogisticRuleModel(object):
                  **kwargs):
         self.data = data
         self.tmin = tmin
-        self.rule_population = DiscreteRulePopulation(
-            self, self.tmin, N_intervals,
-            max_thresholds=kwargs.get('max_thresholds'),
-            tmax=kwargs.get('tmax', None))
+        self.rule_population = self._build_population(N_intervals, kwargs)
         self.data._primitive_result_cache = self.rule_population.truth_table
 
         self.prior_coefficient_variance = prior_coefficient_variance
@@ -99,6 +96,12 @@ class LogisticRuleModel(object):
         self.window_fraction_proposal_std = window_fraction_proposal_std
         self.window_duration_epsilon = 0.01
         self._device_state = None
+
+    def _build_population(self, N_intervals, kwargs):
+        """The resident candidate table (streaming.StreamingModel overrides this with a view of a
+        population that is never materialised)."""
+        return DiscreteRulePopulation(self, self.tmin, N_intervals, max_thresholds=kwargs.get('max_thresholds'),
+                                      tmax=kwargs.get('tmax', None))
 
     # ---- device-side per-model buffers (never pickled) ---------------------------------------------
     def __getstate__(self):
@@ -879,6 +882,15 @@ class LogisticRuleSampler(RuleListSampler):
         return (new_rl, log_relative_prior, log_likelihood_ratio, ('device', out, d_prior, deltas),
                 probability_remove_proposal)
 
+    def _draw_candidate(self, candidate_distribution):
+        """(index, PrimitiveRule) drawn from the distribution a consider_* function returned."""
+        if isinstance(candidate_distribution, tuple):
+            _tag, d_out, d_prior, deltas = candidate_distribution
+            k = self._device_draw(d_out, d_prior, deltas)
+        else:
+            k = choose_from_relative_probabilities(np.exp(candidate_distribution))
+        return k, PrimitiveRule(*self.model.rule_population.flat_rules[k])
+
     def add(self, force_acceptance=False):
         """logit_rules.py:1097-1192."""
         current_rl = self.current_state.rl
@@ -905,14 +917,9 @@ class LogisticRuleSampler(RuleListSampler):
         if (np.random.rand() < acceptance_ratio) or force_acceptance:
             comment += ': accepted (ratio %.3g)' % acceptance_ratio
             self.successes['add'] = self.successes.get('add', 0) + 1
-            if isinstance(candidate_distribution, tuple):
-                _tag, d_out, d_prior, deltas = candidate_distribution
-                k = self._device_draw(d_out, d_prior, deltas)
-            else:
-                k = choose_from_relative_probabilities(np.exp(candidate_distribution))
-            comment += ': adds detector %d' % k
-            primitives = self.model.rule_population.flat_rules
-            new_rl[rule_index][primitive_index] = PrimitiveRule(*primitives[k])
+            k, new_primitive = self._draw_candidate(candidate_distribution)
+            comment += ': adds detector %s' % (k,)
+            new_rl[rule_index][primitive_index] = new_primitive
             self.current_state.rl = new_rl
             self.ensure_current_rl_sorted()
             self.current_X = self.model.data.covariate_matrix(self.current_state.rl)

@@ -414,3 +414,254 @@ class StreamingDetectorGibbs:
         LogisticRuleSampler.step (logit_rules.py:469-504) at fixed structure."""
         self.update_detector()
         self.update_omega_beta(n_gibbs)
+
+
+# ---- the full sampler step over a streamed population ------------------------------------------------------
+#
+# LogisticRuleSampler.step (logit_rules.py:567-596) = omega / beta sweeps + one of {update_primitives, add /
+# remove, move_primitive} + the hyperparameter updates.  Everything in it that touches the candidate table does so
+# through four things: (a) the log-sum-exp of likelihood + prior (+ sparse terms) over all candidates under a trial
+# mask, (b) a draw from those weights, (c) the truth vector and (d) the prior of the handful of primitives that sit
+# in the rule list.  StreamingSweep provides (a) and (b) tile by tile, its tiles rebuilt on demand provide (c), the
+# factored prior tables (d) -- so the reference's step runs on a table that is never materialised (cfg3: 0.8 TB).
+
+class _StreamedTruth:
+    """Mapping view primitive tuple -> bool[N] (what Dataset._primitive_result_cache points at): the truth
+    vector comes from rebuilding the primitive's tile; the few primitives a chain holds are memoised."""
+
+    def __init__(self, pop):
+        self._pop = pop
+        self._rows = {}
+
+    def get(self, key, default=None):
+        row = self._rows.get(key)
+        if row is None:
+            loc = self._pop._locate(key)
+            if loc is None:
+                return default
+            sweep = self._pop.sweep
+            row = sweep.truth_row(sweep.build_tile(loc[0]), loc[1])
+            if len(self._rows) > 4096:
+                self._rows.clear()
+            self._rows[key] = row
+        return row
+
+    def __contains__(self, key):
+        return self.get(key) is not None
+
+    def __getitem__(self, key):
+        row = self.get(key)
+        if row is None:
+            raise KeyError(key)
+        return row
+
+
+class _StreamedPopulation:
+    """The slice of DiscreteRulePopulation's surface that LogisticRuleModel / LogisticRuleSampler use, over a
+    StreamingSweep.  A primitive's index is its (tile, position in the tile's enumeration order)."""
+
+    def __init__(self, sweep):
+        self.sweep = sweep
+        self.windows = sweep.windows
+        self.windows_ok_for_slope = [bool(x) for x in sweep.ok_slope]
+        self._window_lookup = {(float(a), float(b)): i for i, (a, b) in enumerate(self.windows)}
+        self._durations_by_window = sweep.durations
+        self.truth_table = _StreamedTruth(self)
+        self._filter_generation = 0
+        self._build_generation = 0
+        self._locs = {}
+        self._counts = None
+
+    def _locate(self, key):
+        if key not in self._locs:
+            if len(self._locs) > 4096:
+                self._locs.clear()
+            self._locs[key] = self.sweep.locate(key)
+        return self._locs[key]
+
+    def get_primitive_index(self, primitive):
+        return self._locate(primitive.as_tuple())
+
+    def sort_list_of_primitives(self, l):
+        l.sort(key=lambda p: self.get_primitive_index(p) or (-1, -1))
+
+    def count_matrix(self):
+        """float64[W, V]: candidates per (window, variable), both detector types and directions -- one detector
+        pass over all tiles (each rank its own tiles, then an all-reduce), kept for the life of the population."""
+        if self._counts is None:
+            import torch
+            from . import device as D
+            sw = self.sweep
+            C = torch.zeros((len(self.windows), sw.V), dtype=torch.float64, device=D.dev())
+            for t in range(sw.rank, len(sw.tiles), sw.ws):
+                tile = sw.build_tile(t)
+                gvar, w_of = sw._tile_static_tables(tile)
+                C.index_put_((w_of.long(), gvar.long()), 2.0 * tile['K'].to(torch.float64), accumulate=True)
+            if sw.ws > 1:
+                import torch.distributed as dist
+                dist.all_reduce(C, group=sw.group)
+            self._counts = C.cpu().numpy()
+        return self._counts
+
+    @property
+    def n_primitives(self):
+        return int(self.count_matrix().sum())
+
+    def __len__(self):
+        return self.n_primitives
+
+
+def make_streaming_model(data, tmin, tile_variables=64, group=None, **model_kwargs):
+    """LogisticRuleModel (same constructor arguments) over a streamed candidate population."""
+    from . import logit_rules as LR
+
+    class StreamingModel(LR.LogisticRuleModel):
+        """The model of logit_rules.py:77-457 with the candidate table behind a StreamingSweep.  The prior is
+        always the factored form (_prior_tables); the P-long host / device vectors of the resident model
+        (flat_prior, likelihoods_of_all_options) do not exist."""
+        fast_prior = True
+
+        def _build_population(self, N_intervals, kwargs):
+            self.sweep = StreamingSweep(self.data, self.tmin, N_intervals, tmax=kwargs.get('tmax', None),
+                                        tile_variables=tile_variables, group=group)
+            return _StreamedPopulation(self.sweep)
+
+        def _prior_count_matrix(self):
+            return self.rule_population.count_matrix()
+
+        def _prior_tables(self, state):
+            try:
+                return LR.LogisticRuleModel._prior_tables(self, state)
+            except AttributeError:
+                # degenerate hyperparameters (the resident model falls back to a per-group log-sum-exp): the
+                # same sum over the (window, variable) count matrix
+                from . import fastdist
+                pop = self.rule_population
+                log_vw = np.log(np.asarray(self.data.variable_weights, dtype=np.float64))
+                bv = fastdist.norm_logpdf(log_vw, state.phylogeny_mean, state.phylogeny_std)
+                total_duration = float(self.data.experiment_end - self.data.experiment_start)
+                durations = pop._durations_by_window / ((1.0 + self.window_duration_epsilon) * total_duration)
+                bw = fastdist.beta_logpdf(durations, state.window_concentration * state.window_typical_fraction,
+                                          state.window_concentration * (1.0 - state.window_typical_fraction))
+                C = pop.count_matrix()
+                terms = bw[:, None] + bv[None, :]
+                live = C > 0
+                norm = fastdist.logsumexp(terms[live], b=C[live]) if live.any() else 0.0
+                return bv, bw, float(norm)
+
+        def _no_table(self, *a, **k):
+            raise NotImplementedError("a streamed population has no P-long vectors; use StreamingSampler")
+        flat_prior = flat_prior_device = likelihoods_of_all_options = likelihoods_of_all_options_device = \
+            likelihoods_with_stats_device = _no_table
+
+    return StreamingModel(data, tmin, **model_kwargs)
+
+
+def make_streaming_sampler(model, r0, local_updates_per_structure_update=10, device_gibbs=True):
+    """LogisticRuleSampler over a make_streaming_model(...) model: the reference's full step -- detector
+    updates, add / remove, move, hyperparameter updates, omega / beta sweeps -- with np.random consumed in the
+    resident sampler's order."""
+    from scipy.special import gammaln
+    from . import logit_rules as LR
+    from .rules import PrimitiveRule
+
+    class StreamingSampler(LR.LogisticRuleSampler):
+        def _placeholder(self):
+            return PrimitiveRule(0, self.model.rule_population.windows[0], 'average', 'above', 0.0)
+
+        def _stream_sweep(self, rl, i, j, deltas):
+            """log-sum-exp of likelihood + prior + sparse terms over every candidate for position (i, j)."""
+            m = self.model
+            X, mask = m._sweep_inputs(rl, i, j)
+            log_total, _ = m.sweep.sweep(np.asarray(X, dtype=np.float64), self.current_state.omega,
+                                         m.data.y - 0.5, m.prior_coefficient_variance, mask=mask,
+                                         prior_tables=m._prior_tables(self.current_state), deltas=deltas or None)
+            return log_total
+
+        def _primitive_log_prior(self, primitive):
+            bv, bw, norm = self.model._prior_tables(self.current_state)
+            w = self.model.rule_population._window_lookup[(float(primitive.window[0]), float(primitive.window[1]))]
+            return bv[primitive.variable] + bw[w] - norm
+
+        def _draw_candidate(self, candidate_distribution):
+            t, k, primitive = self.model.sweep.draw(np.random.rand())
+            return (t, k), PrimitiveRule(*primitive)
+
+        # logit_rules.py:794-881
+        def update_primitives(self, N_updates=None):
+            pop = self.model.rule_population
+            rule_list = self.current_state.rl
+            positions = [(i, j) for i, rule in enumerate(rule_list) for j, _ in enumerate(rule)]
+            if len(positions) == 0:
+                self.comments.append('Null update')
+                return
+            for _ in range(1 if N_updates is None else N_updates):
+                i, j = positions[np.random.choice(len(positions))]
+                k0 = pop.get_primitive_index(rule_list[i][j])
+                counts = {}
+                for jj, p in enumerate(rule_list[i]):
+                    loc = pop.get_primitive_index(p)
+                    if jj != j and loc is not None:
+                        counts[loc] = counts.get(loc, 0) + 1
+                deltas = {loc: -1.0 * gammaln(n + 1 + 1) + np.log(1.0 + n) for loc, n in counts.items()}
+                self._stream_sweep(rule_list, i, j, deltas)
+                k, new_primitive = self._draw_candidate(None)
+                rule_list[i][j] = new_primitive
+                self.comments.append('At (%d,%d) replacing %s with %s' % (i, j, k0, k))
+            self.ensure_current_rl_sorted()
+            self.current_X = self.model.data.covariate_matrix(rule_list)
+
+        # logit_rules.py:894-970
+        def consider_addition_to_new_rule(self, base_rule, position_to_add_at):
+            m = self.model
+            new_rl = base_rule.copy()
+            new_rl.rules = (new_rl.rules[:position_to_add_at] + [[self._placeholder()]] +
+                            new_rl.rules[position_to_add_at:])
+            s = [m.structure_prior(rl, empty_probability=self.current_state.empty_probability)
+                 for rl in [base_rule, new_rl]]
+            log_relative_prior = s[1] - s[0]
+            old_likelihood = m.likelihood_z_given_X(self.current_state.omega, m.data.covariate_matrix(base_rule))
+            log_marginalized_likelihood = self._stream_sweep(new_rl, position_to_add_at, 0, None)
+            log_likelihood_ratio = log_marginalized_likelihood - old_likelihood
+            probability_remove_proposal = 1.0 / sum(map(len, new_rl))
+            return (new_rl, log_relative_prior, log_likelihood_ratio, ('stream',), probability_remove_proposal)
+
+        # logit_rules.py:972-1095
+        def consider_addition_to_existing_rule(self, base_rule, position_to_add_to):
+            m = self.model
+            pop = m.rule_population
+            base_subrule = base_rule[position_to_add_to]
+            base_n_istar = len(base_subrule)
+            counts, prior_of = {}, {}
+            for primitive in base_subrule:
+                loc = pop.get_primitive_index(primitive)
+                if loc is not None:
+                    counts[loc] = counts.get(loc, 0) + 1
+                    prior_of[loc] = self._primitive_log_prior(primitive)
+            c0 = np.log(base_n_istar + 1)
+            deltas = {loc: -1.0 * np.log(n + 1) for loc, n in counts.items()}
+            new_rl = base_rule.copy()
+            new_rl[position_to_add_to].append(self._placeholder())
+            s = [m.structure_prior(rl, empty_probability=self.current_state.empty_probability)
+                 for rl in [base_rule, new_rl]]
+            log_relative_structure_prior = s[1] - s[0]
+            old_likelihood = m.likelihood_z_given_X(self.current_state.omega, m.data.covariate_matrix(base_rule))
+            # A = lse(prior + deltas): the prior is normalised over the candidates, only the sparse terms move it
+            lse_A = np.log1p(sum(np.exp(prior_of[loc]) * np.expm1(d) for loc, d in deltas.items()))
+            # B = lse(prior + deltas + likelihood): the sweep (and what an accepted proposal draws from)
+            lse_B = self._stream_sweep(new_rl, position_to_add_to, base_n_istar, deltas)
+            # C = lse(prior + likelihood): B with the sparse terms taken back out of the few candidates that carry them
+            lse_C = lse_B + np.log1p(sum(np.expm1(-d) * np.exp(m.sweep.log_weight(*loc)[0] - lse_B)
+                                         for loc, d in deltas.items()))
+            log_relative_prior_primitive_piece = c0 + lse_A
+            log_relative_prior = log_relative_prior_primitive_piece + log_relative_structure_prior
+            log_marginalized_likelihood = (c0 + lse_B) - log_relative_prior_primitive_piece
+            log_likelihood_ratio = log_marginalized_likelihood - old_likelihood
+            new_total_n_primitives = sum(map(len, new_rl))
+            T_sstar_prefactor = (base_n_istar + 1.0) / new_total_n_primitives
+            T_sstar_other_factor = np.exp(lse_C - (c0 + lse_B))
+            return (new_rl, log_relative_prior, log_likelihood_ratio, ('stream',),
+                    T_sstar_prefactor * T_sstar_other_factor)
+
+    return StreamingSampler(model, r0, local_updates_per_structure_update, device_draw=True,
+                            device_gibbs=device_gibbs)
