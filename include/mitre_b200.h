@@ -147,6 +147,8 @@ int mitre_score_groups(void *stream, const double *values, const double *thresho
 int mitre_score_all_host(const double *X_host, const double *omega_host,
                          const double *response_host, const double *truth_host,
                          double sigma2, int N, int p, int64_t P, double *out_host);
+int mitre_set_host_chunk_bytes(int64_t bytes); /* test hook: packed bytes per staging chunk of
+                                                  mitre_score_all_host (0 = default, 64 MiB) */
 
 /* ---- dense single-rule-list likelihood: replaces mc_logpdf_np ------------------------------ */
 /*

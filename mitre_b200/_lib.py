@@ -89,6 +89,7 @@ SIGNATURES = {
     "mitre_slope_guard": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p, c_void_p]),
     "mitre_set_detector_split": (c_int, [c_int]),
     "mitre_set_walk_vpt": (c_int, [c_int]),
+    "mitre_set_host_chunk_bytes": (c_int, [c_i64]),
     "mitre_set_walk_tuning": (c_int, [c_int, c_int, c_int]),
     "mitre_walk_vars_per_block": (c_int, [c_int]),
     "mitre_set_sort_emit_rolled": (c_int, [c_int]),

@@ -96,13 +96,19 @@ def test_dropin_module_same_signature_as_reference():
 
 
 def test_dropin_host_entry_chunked_pipeline():
-    """More rows than one staging chunk (64 MiB of float64 rows) exercises the double-buffered path."""
+    """More rows than two staging chunks (set to 64 Ki rows here) exercises the double-buffered path, ragged
+    last chunk."""
     from mitre_b200 import efficient_likelihoods as EL
-    c = MG.scoring_inputs(seed=55, N=35, p=2, P=300000)
+    from mitre_b200._lib import lib
+    c = MG.scoring_inputs(seed=55, N=35, p=2, P=300001)
     opts = (c["truth"] * c["mask"]).astype(np.float64)
     z = (c["y"] - 0.5) / c["omega"]
-    got = EL.likelihoods_of_all_options(c["X"], c["omega"], z, opts, 100.0)
-    sel = np.r_[0:500, 150000:150500, 299500:300000]
+    lib().mitre_set_host_chunk_bytes(8 * 65536)
+    try:
+        got = EL.likelihoods_of_all_options(c["X"], c["omega"], z, opts, 100.0)
+    finally:
+        lib().mitre_set_host_chunk_bytes(0)
+    sel = np.r_[0:500, 65300:65800, 131000:131400, 299500:300001]
     want = oracle.likelihoods_of_all_options(c["X"], c["omega"], z, opts[sel], 100.0)
     assert rel(got[sel], want) < RTOL
     # every row equal to a row in the checked set must have the same value (pure function of the row)
