@@ -359,6 +359,10 @@ def values_walk_plan(N, S, V, sg_first):
     n_sg = len(sg_first) - 1
     vb = lib().mitre_walk_vars_per_block(int(N))
     tiles = (int(V) + vb - 1) // vb
+    # A CTA costs a fixed ~2.5 start groups' worth of time (tile and table loads behind one barrier, the tail
+    # of its slowest warps with nothing else resident on the SM) on top of the start groups it walks, and the
+    # grid runs in waves of one CTA per SM: take the split with the smallest waves x (2.5 + start groups per
+    # CTA).  Measured at S5 (24 start groups, 625 tiles): 12 per CTA 0.73 ms, 8: 0.77, 6: 0.81, 1: 1.46.
     best = None
     for chunks in range(1, n_sg + 1):
         per = (n_sg + chunks - 1) // chunks
@@ -368,11 +372,9 @@ def values_walk_plan(N, S, V, sg_first):
             continue
         blocks = tiles * ((n_sg + per - 1) // per)
         waves = -(-blocks // info['sm_count'])
-        fill = blocks / float(waves * info['sm_count']) - 0.01 * chunks
-        if best is None or fill > best[0]:
-            best = (fill, per, widest)
-        if chunks >= 8 and best is not None:
-            break
+        cost = waves * (2.5 + per)
+        if best is None or cost < best[0]:
+            best = (cost, per, widest)
     return None if best is None else (best[1], best[2])
 
 
