@@ -297,6 +297,7 @@ extern "C" int mitre_window_tbar(void *stream, const double *times, int N, const
 // memory next to the series tile: sg_first is a host-visible copy is not available here, so the launcher
 // takes the window count of the fullest chunk from the caller (max_block_windows) for a given split.
 static int g_walk_vpt = 1;   // variables per thread of values_walk_kernel
+static int g_walk_persistent = 0;    // 1: values_walk_kernel CTAs loop over variable tiles, tables loaded once (measured slower)
 static int g_walk_vb_cap = 16;       // variables per walk CTA (upper bound)
 static int g_pipe_emit_per_sm = 0;   // pipelined call: sort/emit blocks per SM while a values kernel runs beside it (0 = all)
 static int g_pipe_priority = 0;      // pipelined call: sort/emit stream at high priority
@@ -305,7 +306,8 @@ extern "C" int mitre_set_walk_tuning(int vb_cap, int emit_blocks_per_sm, int emi
 {
     g_walk_vb_cap = vb_cap < 1 ? 1 : (vb_cap > 16 ? 16 : vb_cap);
     g_pipe_emit_per_sm = emit_blocks_per_sm < 0 ? 0 : emit_blocks_per_sm;
-    g_pipe_priority = emit_priority ? 1 : 0;
+    g_pipe_priority = emit_priority & 1;
+    g_walk_persistent = (emit_priority & 2) ? 1 : 0;      // bit 1: CTAs persistent over the variable tiles
     return MITRE_OK;
 }
 
@@ -334,6 +336,12 @@ static int launch_values_walk(cudaStream_t st, dim3 grid, size_t smem, const dou
                                                            n_sg, sg_per_block, max_block_windows, values, group_flags, VB);
     } else {
         MITRE_CUDA_TRY(cudaFuncSetAttribute(values_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // persistent over the variable tiles: one CTA per SM (shared memory), the SMs dealt to the chunks
+        if (g_walk_persistent && grid.y > 0) {
+            unsigned per_chunk = (unsigned)sm_count() / grid.y;
+            if (per_chunk < 1) per_chunk = 1;
+            if (per_chunk < grid.x) grid.x = per_chunk;
+        }
         values_walk_kernel<<<grid, threads, smem, st>>>(series, series_stride, times, t_offsets, S, N, V, windows, wlo,
                                                            wcnt, winv_sxx, wtbar, group_base, slope_ok, sg_first, sg_base,
                                                            n_sg, sg_per_block, max_block_windows, values, group_flags, VB);

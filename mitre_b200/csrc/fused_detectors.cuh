@@ -932,16 +932,15 @@ values_walk_kernel(const double *__restrict__ series, int64_t series_stride, con
     int32_t *m_cnt = reinterpret_cast<int32_t *>(m_is + M);                           // [block windows][N]
     long long *m_gb = reinterpret_cast<long long *>(m_cnt + ((M + 1) & ~1));          // [block windows] group_base * N
     int32_t *m_nt = reinterpret_cast<int32_t *>(m_gb + max_block_windows);            // [block windows]
-    const int v0 = blockIdx.x * VB;
-    const int nv = min(VB, V - v0);
     // this launch covers start groups [sg_base, n_sg), sg_per_block of them per blockIdx.y
     const int sg_begin = sg_base + blockIdx.y * sg_per_block, sg_end = min(n_sg, sg_begin + sg_per_block);
     if (sg_begin >= sg_end) return;
     const int wb0 = sg_first[sg_begin], nbw = sg_first[sg_end] - wb0;      // the block's windows
-    for (int i = threadIdx.x; i < nv * S; i += blockDim.x) {
-        const int vl = i / S, j = i - vl * S;
-        ser[vl * Sp + j] = series[(int64_t)(v0 + vl) * series_stride + j];
-    }
+    // the (window, subject) tables depend on the start groups only: a CTA loads them once and then takes
+    // variable tiles blockIdx.x, blockIdx.x + gridDim.x, ...  By default gridDim.x = the number of tiles (one
+    // tile per CTA, placed dynamically by the hardware); a persistent grid of SMs / chunks CTAs saves two
+    // thirds of the start-up bytes and measured SLOWER (2.00 vs 1.62 ms for the pair at S5): tile times differ
+    // and a static deal of 8.4 tiles per CTA loses more than the table loads cost.
     for (int i = threadIdx.x; i < S; i += blockDim.x) st[i] = times[i];
     for (int i = threadIdx.x; i <= 128; i += blockDim.x) rcp[i] = i ? __ddiv_rn(1.0, (double)i) : 0.0;
     for (int i = threadIdx.x; i < nbw * N; i += blockDim.x) {
@@ -953,9 +952,18 @@ values_walk_kernel(const double *__restrict__ series, int64_t series_stride, con
         m_gb[i] = group_base[wb0 + i] * N;               // element offset of the window's first group
         m_nt[i] = 1 + slope_ok[wb0 + i];
     }
-    __syncthreads();
     const int vl = threadIdx.x / N, s = threadIdx.x - vl * N;
-    if (vl >= nv) return;
+    const int n_tiles = (V + VB - 1) / VB;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int v0 = tile * VB;
+    const int nv = min(VB, V - v0);
+    __syncthreads();                                     // every thread is done with the previous tile's samples
+    for (int i = threadIdx.x; i < nv * S; i += blockDim.x) {
+        const int vi = i / S, j = i - vi * S;
+        ser[vi * Sp + j] = series[(int64_t)(v0 + vi) * series_stride + j];
+    }
+    __syncthreads();
+    if (vl >= nv) continue;
     const double *x = ser + vl * Sp;
     const int64_t vNs = (int64_t)(v0 + vl) * N + s;      // (variable, subject) offset inside a window's groups
     for (int sg = sg_begin; sg < sg_end; ++sg) {
@@ -1010,6 +1018,7 @@ values_walk_kernel(const double *__restrict__ series, int64_t series_stride, con
             }
         }
     }
+    }   // tiles
 }
 
 // VPT = variables per thread (1 or 2).  With two, a thread walks the SAME subject's samples for two

@@ -23,9 +23,10 @@ def main():
     ref = D.detectors_walk(*wa)
     base = min(bench.cuda_time_ms(torch, lambda: D.detectors_walk(*wa), 10) for _ in range(3))
     print("default plan %s: pair %.3f ms" % (wa[14], base))
-    for vb in (16,):
-        lib().mitre_set_walk_tuning(vb, 0, 0)
-        for per in (6, 8, 9, 10, 12):
+    for vb, flags in ((16, 0), (16, 2)):
+        lib().mitre_set_walk_tuning(vb, 0, flags)
+        print("CTAs persistent over the variable tiles" if flags == 2 else "one CTA per (tile, chunk)")
+        for per in (3, 4, 6, 8, 12):
             widest = max(int(first[min(k + per, n_sg)] - first[k]) for k in range(0, n_sg, per))
             smem = lib().mitre_values_walk_smem_bytes(int(N), int(S), widest)
             if not 0 < smem <= 227 * 1024:
