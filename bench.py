@@ -388,6 +388,11 @@ def parity_check(args, torch, D, PL, sw, state, P, N, us):
     scores it in one sweep and checks (a) its slice of the sharded table is that slice of the whole table,
     bit for bit, (b) so are its log-likelihoods, (c) the index every sharded step drew is the index the
     single-table draw gives for the same u, (d) the exchanged log-sum-exp is the single-table one."""
+    # the step's output buffer was last written by the kernel-only timing loops (other kernel variants,
+    # whose sums round differently in the last bit): run the sharded step itself once more, on every rank
+    sw.stage(state["X"], state["omega"], state["kappa"], state["mask"], 0.5)
+    sw.launch(args.rules + 1, SIGMA2)
+    sw.result()
     data, pop, _ = build_population(args, 0, torch)
     if len(pop) != P:
         return "candidate count differs: %d vs %d" % (len(pop), P)
