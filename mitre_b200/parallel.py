@@ -502,8 +502,13 @@ class ShardedPopulation:
                 rows_local = pop._rows_padded[live].view(-1, 1)
             else:
                 rows_local = pop._rows
-            e_local = torch.as_tensor(global_enumeration_indices(pop._K_host, g_local, self._row_offsets_host),
-                                      device=dev)
+            # global_enumeration_indices on the device (the numpy form took 2.0 of the 2.4 s of an S5 build):
+            # row i of local group g has global index row_offsets[g_global] + (i - local_offset[g])
+            counts = 2 * pop._K.to(torch.int64)
+            shift = self.row_offsets[d_g_local] - (torch.cumsum(counts, 0) - counts)
+            e_local = torch.repeat_interleave(shift, counts, output_size=int(pop._P))
+            e_local += torch.arange(int(pop._P), dtype=torch.int64, device=dev)
+            del counts, shift
         else:
             rows_local = torch.empty((0, W64), dtype=torch.int64, device=dev)
             e_local = torch.empty(0, dtype=torch.int64, device=dev)
