@@ -40,12 +40,13 @@ def all_shard_bounds(P, world_size):
     return [shard_bounds(P, world_size, r) for r in range(world_size)]
 
 
-def balanced_bounds(sorted_rows, world_size, tile=128, extra_round_cost=0.5):
+def balanced_bounds(sorted_rows, world_size, tile=128, extra_round_cost=0.35):
     """Slice bounds [(start, stop)] * world_size that balance the WORK of the duplicate-aware scoring kernel
     instead of the row count.  The kernel scores the D distinct rows of a 128-row tile in ceil(D / 32)
     rounds, so a tile costs about 1 + extra_round_cost * (ceil(D / 32) - 1); the share of tiles needing a
     second round varies along a lexsorted table (few duplicates among the middle ranks), which left an
-    equal-rows split 5 % out of balance at 8 GPUs.  Bounds are multiples of the tile; every rank computes
+    equal-rows split 5 % out of balance at 8 GPUs.  extra_round_cost = 0.35 is fitted to the per-rank kernel
+    times of an 8-GPU S5 run (with 0.5 the end slices, 91 % duplicates, ran 5 % longer than the middle ones).  Bounds are multiples of the tile; every rank computes
     the same bounds from the same (replicated) sorted table."""
     P = int(sorted_rows.shape[0])
     if world_size == 1 or P < tile * world_size * 4:
