@@ -254,6 +254,7 @@ class DiscreteRulePopulation:
     """rules.py:245-810, mined on the GPU."""
 
     use_fused = True    # N <= 63: values + sort/emit kernels without a host round trip; False forces the phase-by-phase path
+    resort_after_update = False   # _update_truths: True re-lexsorts the re-evaluated table (the reference does not)
     use_walk = True     # ... with the walk-forward values kernel (mitre_detector_values_walk); False: mitre_detectors_fused
     walk_stages = 1     # > 1: values / sort-emit kernels pipelined over that many runs of start groups on two streams
                         # (mitre_detectors_walk; measured SLOWER on B200 -- the kernels do not co-reside -- so off)
@@ -505,14 +506,44 @@ class DiscreteRulePopulation:
         self.reset_filter()
 
     def _update_truths(self):
-        """rules.py:300-323 (cross-validation): keep the windows, regenerate everything else."""
+        """rules.py:300-323 (cross-validation): keep the windows, regenerate everything else.
+
+        The reference does NOT sort again here: after update_base_rules its flat arrays are in enumeration
+        order (rules.py:321-325 go straight to reset_filter), so a fold's primitive k is the k-th enumerated
+        one.  That is the default (indices, draws and chains on a fold then match the reference's; the scoring
+        kernels take rows in any order, a table without runs of equal rows just sweeps ~2.5x slower).
+        `resort_after_update = True` re-lexsorts instead."""
         self.calculate_values()
         self.update_base_rules()
         old_applied_filters = self.applied_filters[:]
-        self.sort_base_rules()
+        if self.resort_after_update:
+            self.sort_base_rules()
+        else:
+            self._keep_enumeration_order()
         for filter_method, args in old_applied_filters:
             getattr(self, filter_method)(*args)
         self.data._primitive_result_cache = self.truth_table
+
+    def _keep_enumeration_order(self):
+        """The population as update_base_rules leaves it (rules.py:465-511): identity permutation."""
+        from . import device as D
+        import torch
+        N = self.data.n_subjects
+        padded = getattr(self, '_rows_padded', None)
+        if self._P == 0:
+            rows = torch.empty((0, D.words_for(N)), dtype=torch.int64, device=D.dev())
+        elif padded is not None:
+            L = padded.shape[1]
+            live = torch.arange(L, device=padded.device)[None, :] < (2 * self._K.to(torch.int64))[:, None]
+            rows = padded[live].view(-1, 1)
+        else:
+            rows = self._rows
+        self._perm = torch.arange(self._P, dtype=torch.int64, device=D.dev())
+        self._sorted_rows = rows.contiguous()
+        self._rows = None
+        self._rows_padded = None
+        self._host_cache = {}
+        self.reset_filter()
 
     # -- host-side descriptor arithmetic ------------------------------------------------------------------
     @property

@@ -143,18 +143,32 @@ def test_no_windows_and_single_subject_edge_cases():
 
 
 def test_update_truths_rebuilds_identically():
+    """rules.py:300-323 regenerates the table WITHOUT sorting it again: enumeration order (same rows as before,
+    permuted back by the lexsort's permutation); resort_after_update = True gives the sorted table again."""
     d = synthetic.make_series(N=20, V=3, T=(5, 9), span=(0.0, 40.0), seed=5)
     data, pop = build_gpu_population(d, dict(tmin=1.0, N_intervals=4, tmax=None))
     before = pop.packed_truth.cpu().numpy().copy()
+    perm = pop._perm_host().copy()
+    rules_before = list(pop.flat_rules)
+    pop._update_truths()
+    enum = np.empty_like(before)
+    enum[perm] = before
+    assert np.array_equal(pop.packed_truth.cpu().numpy(), enum)
+    assert np.array_equal(pop._perm_host(), np.arange(len(perm)))
+    assert [pop.flat_rules[int(perm[i])] for i in (0, 5, len(perm) - 1)] == [rules_before[i] for i in (0, 5, len(perm) - 1)]
+    assert all(pop.primitive_index[pop.flat_rules[k]] == k for k in (0, 7, len(perm) - 1))
+    pop.resort_after_update = True
     pop._update_truths()
     assert np.array_equal(pop.packed_truth.cpu().numpy(), before)
+    assert np.array_equal(pop._perm_host(), perm)
 
 
 @pytest.mark.parametrize("held_out", [0, 7, 19])
 def test_update_truths_on_a_cross_validation_fold(held_out):
     """SURVEY 8f-4 (main.py:1192-1194, rules.py:300-323): leave-one-out keeps the population's windows
-    (and their slope flags) and re-evaluates everything else on the training subjects."""
-    from mitre_b200 import rules as R
+    (and their slope flags) and re-evaluates everything else on the training subjects; like the reference, the
+    re-evaluated table stays in enumeration order."""
+    from mitre_b200 import device as D, rules as R
     d = synthetic.make_series(N=20, V=3, T=(5, 9), span=(0.0, 40.0), seed=5)
     data, pop = build_gpu_population(d, dict(tmin=1.0, N_intervals=4, tmax=None))
     keep = [s for s in range(20) if s != held_out]
@@ -168,10 +182,23 @@ def test_update_truths_on_a_cross_validation_fold(held_out):
     assert list(pop.windows) == windows and list(pop.windows_ok_for_slope) == ok
     groups = DO.calculate_values(X, T, windows, ok)
     ref = DO.enumerate_primitives(groups, len(keep))
+    assert np.array_equal(pop.packed_truth.cpu().numpy().view(np.uint64), DO.pack_rows(ref["truth"]))
+    assert pop.flat_truth.shape == (ref["truth"].shape[0], len(keep))
+    assert train._primitive_result_cache is pop.truth_table
+    # scoring does not need sorted rows: the unsorted fold table against the oracle
+    c = synthetic.make_sweep_state(len(keep), 2, ref["truth"], seed=3)
+    out, status = D.score_all(pop.packed_truth, len(keep), c["X"], c["omega"], c["y"] - 0.5, 100.0)
+    D.raise_on_status(status)
+    import oracle
+    sel = np.r_[0:40, ref["truth"].shape[0] - 40:ref["truth"].shape[0]]
+    want = oracle.likelihoods_of_all_options(c["X"], c["omega"], (c["y"] - 0.5) / c["omega"],
+                                             ref["truth"][sel].astype(np.float64), 100.0)
+    got = out.cpu().numpy()[sel]
+    assert np.max(np.abs(got - want) / np.abs(want)) < 1e-9
+    pop.resort_after_update = True
+    pop._update_truths()
     order = DO.lexsort_rows(ref["truth"])
     assert np.array_equal(pop.packed_truth.cpu().numpy().view(np.uint64), DO.pack_rows(ref["truth"][order]))
-    assert pop.flat_truth.shape == (len(order), len(keep))
-    assert train._primitive_result_cache is pop.truth_table
 
 
 def test_constant_series_slope_divergence_is_confined_to_slope_rows():
