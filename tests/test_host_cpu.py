@@ -178,3 +178,33 @@ def test_split_r_hat_equals_the_reference_restatement():
     assert np.all(chains.split_r_hat(same) < 1.05)
     shifted = [rng.normal(size=(300, 2)) + 3.0 * i for i in range(4)]
     assert np.all(chains.split_r_hat(shifted) > 2.0)
+
+
+def test_streamed_add_to_existing_rule_algebra():
+    """streaming.make_streaming_sampler derives two of the three log-sum-exps of
+    consider_addition_to_existing_rule (logit_rules.py:1005-1095) from the one sweep it runs:
+    A = lse(prior + deltas) from the normalised prior, C = lse(prior + lik) from B = lse(prior + deltas + lik)
+    and the weights of the few candidates that carry a sparse term.  Same identities on explicit vectors."""
+    from scipy.special import logsumexp
+    rng = np.random.RandomState(3)
+    P = 5000
+    prior = rng.normal(size=P)
+    prior -= logsumexp(prior)                      # normalised over the candidates, like flat_prior
+    lik = rng.normal(scale=30.0, size=P) - 400.0
+    idx = np.array([17, 18, 4200])
+    counts = np.array([1, 3, 2])
+    deltas = -np.log(counts + 1.0)
+    sparse = np.zeros(P)
+    sparse[idx] = deltas
+    lse_A = np.log1p(np.sum(np.exp(prior[idx]) * np.expm1(deltas)))
+    assert abs(lse_A - logsumexp(prior + sparse)) < 1e-13
+    lse_B = logsumexp(prior + sparse + lik)
+    w = (prior + sparse + lik)[idx]                # what StreamingSweep.log_weight returns for those candidates
+    lse_C = lse_B + np.log1p(np.sum(np.expm1(-deltas) * np.exp(w - lse_B)))
+    assert abs(lse_C - logsumexp(prior + lik)) < 1e-12 * abs(lse_C)
+    # ... also when one of the carrying candidates dominates the sum
+    lik[17] += 200.0
+    lse_B = logsumexp(prior + sparse + lik)
+    w = (prior + sparse + lik)[idx]
+    lse_C = lse_B + np.log1p(np.sum(np.expm1(-deltas) * np.exp(w - lse_B)))
+    assert abs(lse_C - logsumexp(prior + lik)) < 1e-12 * abs(lse_C)
