@@ -266,7 +266,14 @@ def make_sharded_sampler(model, r0, local_updates_per_structure_update=10, devic
             test (the step makes its draw inside the sweep, and np.random must be consumed in the same order)."""
             _tag, rl, i, j, deltas = candidate_distribution
             k, _ = self._sharded_step(rl, i, j, deltas, np.random.rand())
-            return k, PrimitiveRule(*self.model.spop.describe(k))
+            return k, self._primitive_at(k)
+
+        def _primitive_at(self, k):
+            """PrimitiveRule of global sorted index k; its index is remembered (looking a tuple's position up
+            again would scan the slices' permutations)."""
+            tup = self.model.spop.describe(k)
+            self.model.rule_population._locs[tup] = k
+            return PrimitiveRule(*tup)
 
         # logit_rules.py:794-881
         def update_primitives(self, N_updates=None):
@@ -286,7 +293,7 @@ def make_sharded_sampler(model, r0, local_updates_per_structure_update=10, devic
                         counts[k] = counts.get(k, 0) + 1
                 deltas = {k: -1.0 * gammaln(n + 1 + 1) + np.log(1.0 + n) for k, n in counts.items()}
                 k, _ = self._sharded_step(rule_list, i, j, deltas, np.random.rand())
-                rule_list[i][j] = PrimitiveRule(*self.model.spop.describe(k))
+                rule_list[i][j] = self._primitive_at(k)
                 self.comments.append('At (%d,%d) replacing %d with %d' % (i, j, -1 if k0 is None else k0, k))
             self.ensure_current_rl_sorted()
             self.current_X = self.model.data.covariate_matrix(rule_list)
