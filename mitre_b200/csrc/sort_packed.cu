@@ -362,12 +362,9 @@ static int launch_pass(cudaStream_t st, int64_t ntiles, const uint64_t *in, int6
                        int idx_bits, const uint32_t *gofs, uint32_t *status, uint32_t *ticket, uint64_t *out_packed,
                        int64_t *perm_out, uint64_t *rows_out, const int64_t *row_offsets, uint32_t L, int32_t *err)
 {
-    static bool configured = false;
-    if (!configured) {
-        MITRE_CUDA_TRY(cudaFuncSetAttribute(os_pass_kernel<FIRST, LAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)sizeof(OsShared)));
-        configured = true;
-    }
+    // per launch, not once per process: the attribute belongs to the current device's copy of the kernel
+    MITRE_CUDA_TRY(cudaFuncSetAttribute(os_pass_kernel<FIRST, LAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)sizeof(OsShared)));
     os_pass_kernel<FIRST, LAST><<<(unsigned)ntiles, kOsThreads, sizeof(OsShared), st>>>(
         in, P, padded, shift, bits, idx_bits, gofs, status, ticket, out_packed, perm_out, rows_out, row_offsets, L, err);
     MITRE_LAUNCH_CHECK();
