@@ -205,3 +205,32 @@ def test_streaming_tile_pairs_are_taken_from_their_owner():
         gathered[t % ws, t] = truth[t]
     assert torch.equal(streaming.combine_tile_pairs(gathered), truth)
     assert torch.equal(streaming.combine_tile_pairs(truth[None]), truth)          # world of one
+
+
+def test_sharded_view_count_matrix_and_group_tables_against_brute_force():
+    """sharded_sampler._ShardedPopulationView derives the prior's (window, variable) count matrix and the
+    per-group (variable, window) tables from the global group layout (window-major, variable, slope before
+    average where the window admits slopes): brute-force enumeration on a stub population."""
+    import types
+    from mitre_b200 import sharded_sampler as SS
+    rng = np.random.RandomState(2)
+    V, ok = 7, np.array([True, False, True, True, False])
+    W = len(ok)
+    groups = [(w, v, t) for w in range(W) for v in range(V) for t in ((0, 1) if ok[w] else (1,))]
+    K = rng.randint(0, 6, size=len(groups))
+    row_offsets = np.concatenate([[0], np.cumsum(2 * K)]).astype(np.int64)
+    nt = 1 + ok.astype(np.int64)
+    GB = np.concatenate([[0], np.cumsum(V * nt)]).astype(np.int64)
+    spop = types.SimpleNamespace(windows=[(float(w), float(w) + 1.0) for w in range(W)], ok_slope=ok, V=V,
+                                 G=len(groups), GB=GB, _row_offsets_host=row_offsets, P=int(row_offsets[-1]))
+    view = SS._ShardedPopulationView.__new__(SS._ShardedPopulationView)
+    view.spop, view.windows, view._counts = spop, spop.windows, None
+    want = np.zeros((W, V))
+    for (w, v, t), k in zip(groups, K):
+        want[w, v] += 2 * k
+    assert np.array_equal(view.count_matrix(), want)
+    assert view.count_matrix().sum() == spop.P
+    # group_tables builds device tensors: check the same arithmetic on the host
+    w_of = np.repeat(np.arange(W, dtype=np.int64), V * nt)
+    within = np.arange(spop.G, dtype=np.int64) - GB[w_of]
+    assert [(int(a), int(b)) for a, b in zip(w_of, within // nt[w_of])] == [(w, v) for w, v, t in groups]
