@@ -112,6 +112,7 @@ class LogisticRuleModel(object):
         state.pop('_structure_terms', None)
         state.pop('_prior_device_cache', None)
         state.pop('_prior_count_cache', None)
+        state.pop('_step_memo', None)
         return state
 
     def _dev(self):
@@ -218,9 +219,31 @@ class LogisticRuleModel(object):
 
     # ---- priors (logit_rules.py:232-457) ----------------------------------------------------------
     def prior(self, state):
+        memo = self.__dict__.get('_step_memo')
+        if memo is not None:
+            return self._prior_with_fixed_terms(state, memo)
         terms = [self.prior_contribution_hyperpriors(state), self.rule_list_prior(state),
                  self.prior_contribution_coefficients(state)]
         return np.sum(terms)
+
+    def _prior_with_fixed_terms(self, state, memo):
+        """prior(state) while the sampler runs a step's four hyperparameter updates: the states that come
+        through differ in the phylogeny / window hyperparameters only, so the terms of the rule list's
+        structure, its multinomial coefficients, the empty probability and the coefficients are evaluated
+        once (the sampler opens and closes the memo, LogisticRuleSampler.step).  Same values summed in the
+        same order as prior()."""
+        fixed = memo.get('fixed')
+        if fixed is None:
+            fixed = memo['fixed'] = (
+                self.prior_contribution_empty_probability(state),
+                self.structure_prior(state.rl, empty_probability=state.empty_probability),
+                self.multinomial_prior(state.rl),
+                self.prior_contribution_coefficients(state))
+        empty_piece, structure_piece, multinomial_piece, coefficient_piece = fixed
+        hyperpriors = np.sum([self.prior_contribution_phylogeny_parameters(state),
+                              self.prior_contribution_window_parameters(state), empty_piece])
+        rule_list_piece = self.prior_contribution_from_primitives(state) + structure_piece + multinomial_piece
+        return np.sum([hyperpriors, rule_list_piece, coefficient_piece])
 
     def prior_contribution_coefficients(self, state):
         dimensions = len(state.beta)
@@ -522,12 +545,14 @@ class LogisticRuleSampler(RuleListSampler):
         self.update_beta()
         self.update_empty_probability()
         self._in_step = True
+        self.model._step_memo = {}      # the four updates below change hyperparameters only (model.prior)
         try:
             self.update_window_parameters()
             prior = self.update_phylogeny_parameters()
         finally:
             self._in_step = False
             self._current_prior_value = None
+            self.model._step_memo = None
         self.states.append(self.current_state.copy())
         self.likelihoods.append(
             self.model.likelihood_y_given_X_beta(self.current_X, self.current_state.beta))

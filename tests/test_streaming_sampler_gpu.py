@@ -45,6 +45,21 @@ def test_streamed_population_counts_and_prior_tables():
         assert np.array_equal(np.asarray(a), np.asarray(b))
     resident.fast_prior = True
     assert streamed.rule_list_prior(state) == resident.rule_list_prior(state)
+    # the memoised form the sampler uses during a step's hyperparameter updates: bit-identical to prior()
+    for model in (resident, streamed):
+        plain = [model.prior(state)]
+        model._step_memo = {}
+        memo = [model.prior(state)]
+        for name, value in (("phylogeny_mean", 0.3), ("phylogeny_std", 2.2), ("window_concentration", 3.1),
+                            ("window_typical_fraction", 0.21)):
+            other = state.copy()
+            setattr(other, name, value)
+            memo.append(model.prior(other))
+            model._step_memo, keep = None, model._step_memo
+            plain.append(model.prior(other))
+            model._step_memo = keep
+        model._step_memo = None
+        assert memo == plain
 
 
 @pytest.mark.parametrize("rules", [[[11]], [[40, 900], [7]], [[3, 3, 250], [77], [1500, 8]]])
