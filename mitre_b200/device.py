@@ -350,12 +350,12 @@ def window_tbar(times, windows, lo, cnt):
     return tbar
 
 
-def values_walk_plan(N, S, V, sg_first):
+def values_walk_plan(N, S, V, sg_first, info=None):
     """How the walk-forward values kernel splits the start groups over blockIdx.y: (sg_per_block,
     max_block_windows) such that the per-block window tables fit in shared memory and the grid fills whole
     waves, or None when not even one start group fits (then: mitre_detectors_fused).
-    sg_first: host int array [n_sg + 1]."""
-    info = device_info()
+    sg_first: host int array [n_sg + 1].  info: {'smem_optin', 'sm_count'} (default: the current device)."""
+    info = device_info() if info is None else info
     n_sg = len(sg_first) - 1
     vb = lib().mitre_walk_vars_per_block(int(N))
     tiles = (int(V) + vb - 1) // vb

@@ -208,3 +208,38 @@ def test_streamed_add_to_existing_rule_algebra():
     w = (prior + sparse + lik)[idx]
     lse_C = lse_B + np.log1p(np.sum(np.expm1(-deltas) * np.exp(w - lse_B)))
     assert abs(lse_C - logsumexp(prior + lik)) < 1e-12 * abs(lse_C)
+
+
+def test_values_walk_plan_cost_model():
+    """device.values_walk_plan: (start groups per CTA, widest window count) minimising
+    waves x (2.5 + start groups per CTA) among the splits whose tables fit in shared memory (no GPU needed: the
+    shared-memory size is host arithmetic of the library)."""
+    from mitre_b200 import device as D
+    from mitre_b200._lib import lib
+    info = {'smem_optin': 227 * 1024, 'sm_count': 148}
+    # the S5 shape: 24 start groups, the k-th start has 24 - k windows (minus the inadmissible ones ~ ignore)
+    counts = [23 - k for k in range(23)]
+    first = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    N, S, V = 35, 561, 10000
+    per, widest = D.values_walk_plan(N, S, V, first, info=info)
+    n_sg = len(first) - 1
+    assert widest == max(int(first[min(k + per, n_sg)] - first[k]) for k in range(0, n_sg, per))
+    assert 0 < lib().mitre_values_walk_smem_bytes(N, S, widest) <= info['smem_optin']
+    # it is the argmin of the model over the feasible splits
+    vb = lib().mitre_walk_vars_per_block(N)
+    tiles = -(-V // vb)
+
+    def cost(p):
+        w = max(int(first[min(k + p, n_sg)] - first[k]) for k in range(0, n_sg, p))
+        if not 0 < lib().mitre_values_walk_smem_bytes(N, S, w) <= info['smem_optin']:
+            return None
+        return -(-(tiles * -(-n_sg // p)) // info['sm_count']) * (2.5 + p)
+    feasible = {p: cost(p) for p in range(1, n_sg + 1) if cost(p) is not None}
+    assert per in feasible and feasible[per] == min(feasible.values())
+    assert per >= 8                       # fewer, larger CTAs (the previous plan took 6)
+    # nothing fits: a population whose single start group already needs more shared memory than there is
+    huge = np.array([0, 4000], dtype=np.int32)
+    assert D.values_walk_plan(63, 3000, 100, huge, info=info) is None
+    # a tiny problem: both start groups get a CTA of their own (two CTAs still are one wave)
+    small = np.array([0, 2, 3], dtype=np.int32)
+    assert D.values_walk_plan(10, 60, 16, small, info=info)[0] == 1
